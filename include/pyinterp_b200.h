@@ -1,0 +1,159 @@
+/*
+ * pyinterp_b200.h — C ABI of libpyinterp_b200.so (hand-written CUDA for sm_100a).
+ *
+ * The reference (DataverseLabs/pyinterpolate 1.0.3) is pure Python and has no FFI of its own;
+ * its drop-in boundary is the set of Python call signatures re-exported in
+ * src/pyinterpolate/__init__.py:15-24.  Each entry point below replaces the NumPy/SciPy
+ * internals behind one of those calls (file:line relative to src/pyinterpolate/).  The
+ * Python binding a maintainer adds is a ctypes stub — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - `*_device` entry points take DEVICE pointers and enqueue on `stream`
+ *     (a cudaStream_t passed as void*, NULL = legacy default stream) WITHOUT synchronising
+ *   - `*_host` entry points take HOST pointers, do their own H2D / D2H copies and return
+ *     after the results are in host memory
+ *   - every function returns PIB_OK (0) or a negative error; pib_last_error() has the text
+ *   - inputs are borrowed and never modified; outputs are caller-allocated
+ *   - all floating point is IEEE fp64; pair counts are int64; neighbour indices int32
+ */
+#ifndef PYINTERP_B200_H
+#define PYINTERP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PIB_API __attribute__((visibility("default")))
+#else
+#define PIB_API
+#endif
+
+#define PIB_OK 0
+#define PIB_ERR_INVALID -1      /* bad argument (NULL pointer, n < 0, non-ascending lags, ...) */
+#define PIB_ERR_CUDA -2         /* a CUDA runtime call failed */
+#define PIB_ERR_UNSUPPORTED -3  /* size outside what the kernels are built for */
+
+/* theoretical variogram model ids — alphabetical, as in
+ * semivariogram/theoretical/variogram_models/functions.py:8-14 (ALL_MODELS) */
+#define PIB_MODEL_CIRCULAR 0
+#define PIB_MODEL_CUBIC 1
+#define PIB_MODEL_EXPONENTIAL 2
+#define PIB_MODEL_GAUSSIAN 3
+#define PIB_MODEL_LINEAR 4
+#define PIB_MODEL_POWER 5
+#define PIB_MODEL_SPHERICAL 6
+
+#define PIB_KRIGE_ORDINARY 0    /* kriging/point/ordinary.py:30-131  (ok_calc)  */
+#define PIB_KRIGE_SIMPLE 1      /* kriging/point/simple.py:26-126    (sk_calc)  */
+
+/* per-location status written by the kriging entry points */
+#define PIB_STATUS_OK 0
+#define PIB_STATUS_SINGULAR 1        /* zero pivot: the reference raises RuntimeError (kriging/utils/errors.py:1-15) */
+#define PIB_STATUS_NEGATIVE_VARIANCE 2 /* sigma^2 < 0 -> NaN, like ordinary.py:125-126 */
+
+PIB_API const char *pib_last_error(void);
+PIB_API int pib_version(void);
+/* number of SMs of the current device (grid sizing evidence for callers / tests) */
+PIB_API int pib_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Experimental variogram — one fused pass over point pairs.
+ *
+ * Replaces, for omnidirectional variograms (n_dirs == 0):
+ *   distance/point.py:14-58            point_distance (scipy cdist, N x N matrix)
+ *   distance/point.py:61-92            select_values_in_range (one masked pass per lag)
+ *   semivariogram/experimental/functions/general.py:78-147, :235-303
+ *                                      omnidirectional_variogram / _calc_omnidirectional_values
+ *   semivariogram/experimental/functions/semivariance.py:4-24, covariance.py:4-26
+ * and for ellipse-directional variograms (n_dirs >= 1, method 'e'):
+ *   semivariogram/experimental/functions/directional.py:11-80, :395-465   from_ellipse
+ *   distance/angular.py:412-456, :641-681   select_points_within_ellipse
+ *
+ * xyz        [n][3] row-major rows [x, y, value]
+ * edges      [n_lags] ascending lag upper limits (semivariogram/lags/lags.py:6-31, host-made so
+ *            they are bit-identical to the reference's np.arange); lag b is (edges[b-1], edges[b]],
+ *            edges[-1] := 0                                           (HOST pointer)
+ * lower      NULL, or [n_lags] lower limits for the ellipse path computed the reference's way,
+ *            edges[b] - (edges[b] - edges[b-1]) (directional.py:432, angular.py:672-673);
+ *            NULL means lower[b] = edges[b-1]                         (HOST pointer)
+ * W          [n_dirs][4] row-major 2x2 whitening matrices (distance/angular.py:221-250), made on
+ *            the host with the reference's own formula; ignored when n_dirs == 0   (HOST pointer)
+ * shard_index, shard_count   this call evaluates the shard_index-th of shard_count interleaved
+ *            slices of the tile-pair list (multi-GPU: one slice per rank, then a SUM all-reduce
+ *            of the four outputs); (0, 1) = everything
+ * outputs    [max(n_dirs,1)][n_lags], sums over UNORDERED pairs (i < j) that fall in the lag:
+ *            sum_sq = sum (z_i - z_j)^2, sum_prod = sum z_i z_j, sum_val = sum (z_i + z_j),
+ *            count = number of pairs.  The reference's ordered-pair outputs follow as
+ *            semivariance = sum_sq / (2 count), covariance = sum_prod / count - (sum_val / (2 count))^2,
+ *            n_pairs = 2 count.
+ * pairs_evaluated  optional (may be NULL): number of point pairs whose distance was actually
+ *            computed (tile pairs farther apart than the last lag are skipped)    (HOST pointer)
+ * ---------------------------------------------------------------------------------------- */
+PIB_API int pib_variogram_device(const double *d_xyz, int64_t n,
+                         const double *edges, const double *lower, int n_lags,
+                         const double *W, int n_dirs,
+                         int shard_index, int shard_count,
+                         double *d_sum_sq, double *d_sum_prod, double *d_sum_val, int64_t *d_count,
+                         int64_t *pairs_evaluated, void *stream);
+
+PIB_API int pib_variogram_host(const double *xyz, int64_t n,
+                       const double *edges, const double *lower, int n_lags,
+                       const double *W, int n_dirs,
+                       int shard_index, int shard_count,
+                       double *sum_sq, double *sum_prod, double *sum_val, int64_t *count,
+                       int64_t *pairs_evaluated);
+
+/* ------------------------------------------------------------------------------------------
+ * Point kriging — batched neighbour search + system assembly + solve.
+ *
+ * Replaces the per-location Python loop of
+ *   kriging/point/ordinary.py:134-221 (ordinary_kriging) / simple.py:129-223 (simple_kriging)
+ * and everything below it:
+ *   transform/select_points.py:42-101          select_kriging_data (cdist + full argsort)
+ *   kriging/utils/point_kriging_solve.py:20-101  get_predictions (k vector, Gamma matrix)
+ *   semivariogram/theoretical/variogram_models/models.py:41-440   gamma(h)
+ *   kriging/utils/point_kriging_solve.py:104-149  solve_weights (np.linalg.solve = dgesv)
+ *
+ * known      [n][3] rows [x, y, value]
+ * values     NULL, or [n_sets][n] alternative value columns sharing the known coordinates
+ *            (indicator kriging: one 0/1 column per threshold, kriging/point/indicator.py:269-291);
+ *            NULL means one set taken from known[:, 2]
+ * params     [n_sets][3] = nugget, (partial) sill, range per set            (HOST pointer)
+ * unknown    [m][2] rows [x, y]
+ * model      PIB_MODEL_*; mode PIB_KRIGE_*; process_mean only used by simple kriging
+ * k          no_neighbors; the k nearest known points by (distance, index) are used, all n when
+ *            n < k (select_points.py:95-101 with use_all_neighbors_in_range=False)
+ * out        [n_sets][m][4] rows [zhat, sigma^2 (NaN if negative), x, y]
+ * nbr_idx    NULL, or [m][k] indices into `known`, ascending distance, -1 padded
+ * status     NULL, or [n_sets][m] PIB_STATUS_*
+ * shard: locations are independent, so multi-GPU callers simply pass their own slice of `unknown`.
+ * ---------------------------------------------------------------------------------------- */
+PIB_API int pib_krige_device(const double *d_known, int64_t n,
+                     const double *d_values, int n_sets, const double *params,
+                     const double *d_unknown, int64_t m,
+                     int model, int mode, double process_mean, int k,
+                     double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, void *stream);
+
+PIB_API int pib_krige_host(const double *known, int64_t n,
+                   const double *values, int n_sets, const double *params,
+                   const double *unknown, int64_t m,
+                   int model, int mode, double process_mean, int k,
+                   double *out, int32_t *nbr_idx, uint8_t *status);
+
+/* gamma(h) for h[0..n) with the device implementation of the seven models (for tests) */
+PIB_API int pib_gamma_host(int model, double nugget, double sill, double rang,
+                   const double *h, int64_t n, double *out);
+
+/* FP64 throughput probe: runs a dependent-chain-free DFMA kernel and returns TFLOP/s
+ * (2 flop per DFMA) measured with CUDA events.  Used by bench.py for the roofline
+ * denominator because MEASURED_PEAKS.json carries no FP64 figure. */
+PIB_API int pib_fp64_peak_tflops(double *tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYINTERP_B200_H */

@@ -1,0 +1,203 @@
+// extern "C" surface of libpyinterp_b200.so — see include/pyinterp_b200.h for the contract.
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+
+namespace pib {
+
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+
+int sm_count()
+{
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            cached = sms;
+        else
+            return 148;
+    }
+    return cached;
+}
+
+int variogram_device(const double *d_xyz, int64_t n, const double *edges, const double *lower, int n_lags,
+                     const double *W, int n_dirs, int shard_index, int shard_count,
+                     double *d_sum_sq, double *d_sum_prod, double *d_sum_val, int64_t *d_count,
+                     int64_t *pairs_evaluated, cudaStream_t stream);
+int krige_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
+                 const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
+                 double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, cudaStream_t stream);
+int gamma_device(int model, double nugget, double sill, double rang, const double *d_h, int64_t n, double *d_out,
+                 cudaStream_t stream);
+
+// 8 independent DFMA chains per thread, 4096 DFMAs each
+__global__ void dfma_peak_kernel(double *out, double a, double b, int iters)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+            x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+}  // namespace pib
+
+using namespace pib;
+
+extern "C" {
+
+const char *pib_last_error(void) { return g_error.c_str(); }
+int pib_version(void) { return 100; }
+int pib_device_sm_count(void) { return sm_count(); }
+
+int pib_variogram_device(const double *d_xyz, int64_t n, const double *edges, const double *lower, int n_lags,
+                         const double *W, int n_dirs, int shard_index, int shard_count, double *d_sum_sq,
+                         double *d_sum_prod, double *d_sum_val, int64_t *d_count, int64_t *pairs_evaluated, void *stream)
+{
+    PIB_CHECK(d_xyz || n == 0, PIB_ERR_INVALID, "variogram: xyz is NULL");
+    PIB_CHECK(d_sum_sq && d_sum_prod && d_sum_val && d_count, PIB_ERR_INVALID, "variogram: output pointer is NULL");
+    return variogram_device(d_xyz, n, edges, lower, n_lags, W, n_dirs, shard_index, shard_count, d_sum_sq, d_sum_prod,
+                            d_sum_val, d_count, pairs_evaluated, static_cast<cudaStream_t>(stream));
+}
+
+int pib_variogram_host(const double *xyz, int64_t n, const double *edges, const double *lower, int n_lags,
+                       const double *W, int n_dirs, int shard_index, int shard_count, double *sum_sq, double *sum_prod,
+                       double *sum_val, int64_t *count, int64_t *pairs_evaluated)
+{
+    PIB_CHECK(xyz || n == 0, PIB_ERR_INVALID, "variogram: xyz is NULL");
+    PIB_CHECK(sum_sq && sum_prod && sum_val && count, PIB_ERR_INVALID, "variogram: output pointer is NULL");
+    PIB_CHECK(n >= 0 && n_lags >= 1, PIB_ERR_INVALID, "variogram: need n >= 0 and at least one lag");
+    cudaStream_t stream;
+    PIB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    int rc;
+    {
+        Scratch ws(stream);
+        const size_t out_n = (size_t)(n_dirs > 0 ? n_dirs : 1) * n_lags;
+        double *d_xyz, *d_sums;
+        int64_t *d_count;
+        rc = ws.alloc(&d_xyz, (size_t)n * 3);
+        if (rc == PIB_OK) rc = ws.alloc(&d_sums, out_n * 3);
+        if (rc == PIB_OK) rc = ws.alloc(&d_count, out_n);
+        if (rc == PIB_OK && n > 0 &&
+            cudaMemcpyAsync(d_xyz, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, stream) != cudaSuccess) {
+            set_error("variogram: H2D copy failed"); rc = PIB_ERR_CUDA;
+        }
+        if (rc == PIB_OK)
+            rc = variogram_device(d_xyz, n, edges, lower, n_lags, W, n_dirs, shard_index, shard_count, d_sums,
+                                  d_sums + out_n, d_sums + 2 * out_n, d_count, pairs_evaluated, stream);
+        if (rc == PIB_OK) {
+            cudaError_t e = cudaMemcpyAsync(sum_sq, d_sums, sizeof(double) * out_n, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(sum_prod, d_sums + out_n, sizeof(double) * out_n, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(sum_val, d_sums + 2 * out_n, sizeof(double) * out_n, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(count, d_count, sizeof(int64_t) * out_n, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) { set_error(std::string("variogram: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; }
+        }
+    }
+    cudaStreamSynchronize(stream);
+    cudaStreamDestroy(stream);
+    return rc;
+}
+
+int pib_krige_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
+                     const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
+                     double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, void *stream)
+{
+    PIB_CHECK(d_known && (d_unknown || m == 0) && (d_out || m == 0), PIB_ERR_INVALID, "krige: NULL pointer");
+    return krige_device(d_known, n, d_values, n_sets, params, d_unknown, m, model, mode, process_mean, k, d_out,
+                        d_nbr_idx, d_status, static_cast<cudaStream_t>(stream));
+}
+
+int pib_krige_host(const double *known, int64_t n, const double *values, int n_sets, const double *params,
+                   const double *unknown, int64_t m, int model, int mode, double process_mean, int k, double *out,
+                   int32_t *nbr_idx, uint8_t *status)
+{
+    PIB_CHECK(known && (unknown || m == 0) && (out || m == 0), PIB_ERR_INVALID, "krige: NULL pointer");
+    PIB_CHECK(n >= 1 && m >= 0 && k >= 1 && n_sets >= 1, PIB_ERR_INVALID, "krige: need n >= 1, m >= 0, k >= 1");
+    if (m == 0) return PIB_OK;
+    cudaStream_t stream;
+    PIB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    int rc;
+    {
+        Scratch ws(stream);
+        double *d_known, *d_values = nullptr, *d_unknown, *d_out;
+        int32_t *d_idx = nullptr;
+        uint8_t *d_status = nullptr;
+        rc = ws.alloc(&d_known, (size_t)n * 3);
+        if (rc == PIB_OK) rc = ws.alloc(&d_unknown, (size_t)m * 2);
+        if (rc == PIB_OK) rc = ws.alloc(&d_out, (size_t)n_sets * m * 4);
+        if (rc == PIB_OK && values) rc = ws.alloc(&d_values, (size_t)n_sets * n);
+        if (rc == PIB_OK && nbr_idx) rc = ws.alloc(&d_idx, (size_t)m * k);
+        if (rc == PIB_OK && status) rc = ws.alloc(&d_status, (size_t)n_sets * m);
+        cudaError_t e = cudaSuccess;
+        if (rc == PIB_OK) {
+            e = cudaMemcpyAsync(d_known, known, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_unknown, unknown, sizeof(double) * 2 * m, cudaMemcpyHostToDevice, stream);
+            if (e == cudaSuccess && values)
+                e = cudaMemcpyAsync(d_values, values, sizeof(double) * n_sets * n, cudaMemcpyHostToDevice, stream);
+            if (e != cudaSuccess) { set_error(std::string("krige: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; }
+        }
+        if (rc == PIB_OK)
+            rc = krige_device(d_known, n, d_values, n_sets, params, d_unknown, m, model, mode, process_mean, k, d_out,
+                              d_idx, d_status, stream);
+        if (rc == PIB_OK) {
+            e = cudaMemcpyAsync(out, d_out, sizeof(double) * 4 * n_sets * m, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess && nbr_idx) e = cudaMemcpyAsync(nbr_idx, d_idx, sizeof(int32_t) * m * k, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess && status) e = cudaMemcpyAsync(status, d_status, (size_t)n_sets * m, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) { set_error(std::string("krige: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; }
+        }
+    }
+    cudaStreamSynchronize(stream);
+    cudaStreamDestroy(stream);
+    return rc;
+}
+
+int pib_gamma_host(int model, double nugget, double sill, double rang, const double *h, int64_t n, double *out)
+{
+    PIB_CHECK(model >= 0 && model <= 6, PIB_ERR_INVALID, "gamma: unknown model id");
+    if (n <= 0) return PIB_OK;
+    double *d_h, *d_o;
+    PIB_CUDA(cudaMalloc(&d_h, sizeof(double) * n));
+    PIB_CUDA(cudaMalloc(&d_o, sizeof(double) * n));
+    int rc = PIB_OK;
+    if (cudaMemcpy(d_h, h, sizeof(double) * n, cudaMemcpyHostToDevice) != cudaSuccess) rc = PIB_ERR_CUDA;
+    if (rc == PIB_OK) rc = gamma_device(model, nugget, sill, rang, d_h, n, d_o, 0);
+    if (rc == PIB_OK && cudaMemcpy(out, d_o, sizeof(double) * n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = PIB_ERR_CUDA;
+    cudaFree(d_h); cudaFree(d_o);
+    if (rc == PIB_ERR_CUDA) set_error("gamma: CUDA copy failed");
+    return rc;
+}
+
+int pib_fp64_peak_tflops(double *tflops_out)
+{
+    PIB_CHECK(tflops_out, PIB_ERR_INVALID, "fp64 peak: NULL output");
+    const int blocks = sm_count() * 8, threads = 256, iters = 2048;
+    double *d_out;
+    PIB_CUDA(cudaMalloc(&d_out, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    PIB_CUDA(cudaEventCreate(&e0)); PIB_CUDA(cudaEventCreate(&e1));
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 6; ++rep) {
+        PIB_CUDA(cudaEventRecord(e0, 0));
+        dfma_peak_kernel<<<blocks, threads>>>(d_out, 1.0000001, 1e-9, iters);
+        PIB_CUDA(cudaEventRecord(e1, 0));
+        PIB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        PIB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+    *tflops_out = flops / (best_ms * 1e-3) / 1e12;
+    return PIB_OK;
+}
+
+}  // extern "C"

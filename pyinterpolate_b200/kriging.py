@@ -1,0 +1,127 @@
+"""Point kriging — the reference's public calls, backed by the batched CUDA kNN + solve kernels.
+
+Mirrors (file:line relative to /root/reference/src/pyinterpolate/):
+  * kriging/point/ordinary.py:134-221     ordinary_kriging        (+ ok_calc :30-131)
+  * kriging/point/simple.py:129-223       simple_kriging          (+ sk_calc :26-126)
+  * core/pipelines/interpolate.py:12-92   interpolate_points
+  * kriging/point/indicator.py:200-325    IndicatorKriging._estimate (batched: one neighbour search,
+                                          one solve per threshold)
+
+Not built yet (NotImplementedError, there is no CPU fallback): models with a ``direction``
+(angular neighbour selection, transform/select_points.py:104-257), ``use_all_neighbors_in_range=True``
+(variable-size systems) and ``allow_approximate_solutions=True`` (lstsq fallback).
+"""
+import warnings
+
+import numpy as np
+
+from . import _lib, core
+from .models import model_parameters
+
+# kriging/utils/errors.py:10-15, verbatim message
+_SINGULAR_MSG = ("Singular matrix in Kriging system detected, "
+                 "check if you have duplicated coordinates "
+                 "in the ``known_locations`` variable. If your "
+                 "data doesn't have duplicates then set "
+                 "``allow_lsa`` parameter to ``True``.")
+
+
+def _prepare(theoretical_model, known_locations, unknown_locations, use_all_neighbors_in_range,
+             allow_approximate_solutions):
+    mid, nugget, sill, rang, direction = model_parameters(theoretical_model)
+    if direction is not None:
+        raise NotImplementedError("kriging with a directional theoretical model is not implemented in "
+                                  "pyinterpolate_b200 yet (SURVEY.md §8f-3)")
+    if use_all_neighbors_in_range:
+        raise NotImplementedError("use_all_neighbors_in_range=True is not implemented in pyinterpolate_b200 yet")
+    if allow_approximate_solutions:
+        raise NotImplementedError("allow_approximate_solutions=True (least-squares fallback) is not implemented "
+                                  "in pyinterpolate_b200 yet")
+    known = np.ascontiguousarray(core.variogram_points(known_locations), dtype=np.float64)
+    unknown = np.ascontiguousarray(core.interpolation_points(unknown_locations), dtype=np.float64)
+    if known.ndim != 2 or known.shape[1] != 3:
+        raise ValueError("known_locations must be rows of [x, y, value]")
+    if unknown.ndim != 2 or unknown.shape[1] != 2:
+        raise ValueError("unknown_locations must be rows of [x, y]")
+    return mid, np.array([[nugget, sill, rang]]), known, unknown
+
+
+def _raise_on_singular(status):
+    if (status == _lib.STATUS_SINGULAR).any():
+        # kriging/utils/errors.py:1-15 via ordinary.py:130-131
+        raise RuntimeError(_SINGULAR_MSG)
+
+
+def ordinary_kriging(theoretical_model, known_locations, unknown_locations=None, neighbors_range=None,
+                     no_neighbors=4, max_tick=5., use_all_neighbors_in_range=False,
+                     allow_approximate_solutions=False, progress_bar=True, unknown_location=None,
+                     return_neighbors=False):
+    """``[predicted value, variance error, x, y]`` rows — kriging/point/ordinary.py:134-221.
+
+    ``neighbors_range`` does not change the result when ``use_all_neighbors_in_range`` is False
+    (transform/select_points.py:95-101: the k nearest are used either way), ``max_tick`` only applies to
+    directional models and ``progress_bar`` has nothing to show: one batched launch replaces the loop.
+    ``unknown_location=`` (the README's spelling) is accepted as an alias."""
+    if unknown_locations is None:
+        unknown_locations = unknown_location
+    mid, params, known, unknown = _prepare(theoretical_model, known_locations, unknown_locations,
+                                           use_all_neighbors_in_range, allow_approximate_solutions)
+    out, idx, status = _lib.krige_host(known, unknown, mid, params, _lib.KRIGE_ORDINARY, int(no_neighbors),
+                                       want_neighbors=return_neighbors)
+    _raise_on_singular(status)
+    return (out[0], idx) if return_neighbors else out[0]
+
+
+def simple_kriging(theoretical_model, known_locations, unknown_locations=None, process_mean=None,
+                   neighbors_range=None, no_neighbors=4, max_tick=5., use_all_neighbors_in_range=False,
+                   allow_approximate_solutions=False, progress_bar=True, unknown_location=None,
+                   return_neighbors=False):
+    """``[predicted value, variance error, x, y]`` rows — kriging/point/simple.py:129-223."""
+    if unknown_locations is None:
+        unknown_locations = unknown_location
+    if process_mean is None:
+        raise TypeError("simple_kriging() missing required argument: 'process_mean'")
+    mid, params, known, unknown = _prepare(theoretical_model, known_locations, unknown_locations,
+                                           use_all_neighbors_in_range, allow_approximate_solutions)
+    out, idx, status = _lib.krige_host(known, unknown, mid, params, _lib.KRIGE_SIMPLE, int(no_neighbors),
+                                       process_mean=float(process_mean), want_neighbors=return_neighbors)
+    _raise_on_singular(status)
+    return (out[0], idx) if return_neighbors else out[0]
+
+
+def interpolate_points(theoretical_model, known_locations, unknown_locations, neighbors_range=None,
+                       no_neighbors=4, max_tick=5., use_all_neighbors_in_range=False,
+                       allow_approximate_solutions=False, progress_bar=True):
+    """core/pipelines/interpolate.py:12-92 — ordinary kriging of many points."""
+    return ordinary_kriging(theoretical_model, known_locations, unknown_locations, neighbors_range, no_neighbors,
+                            max_tick, use_all_neighbors_in_range, allow_approximate_solutions, progress_bar)
+
+
+def indicator_kriging(theoretical_models, thresholds, known_locations, unknown_locations, no_neighbors=4,
+                      reference_variance_column=True):
+    """Batched core of kriging/point/indicator.py:200-325 for ``kriging_type='ok'``.
+
+    ``theoretical_models`` are the per-threshold models (same model family), ``thresholds`` the cut values;
+    indicators are ``(z <= threshold)`` (indicator.py:272-275).  All thresholds share one neighbour search.
+    Returns ``[M, T]`` clipped to [0, 1].  With ``reference_variance_column=True`` the column the reference
+    stores is reproduced — it keeps ``_pred_arr[0][1]``, the kriging VARIANCE, not zhat (indicator.py:312-313);
+    pass False to get the indicator predictions themselves."""
+    known = np.ascontiguousarray(core.variogram_points(known_locations), dtype=np.float64)
+    unknown = np.ascontiguousarray(core.interpolation_points(unknown_locations), dtype=np.float64)
+    parsed = [model_parameters(m) for m in theoretical_models]
+    if len({p[0] for p in parsed}) != 1:
+        raise NotImplementedError("indicator models of different families need one call per family")
+    if any(p[4] is not None for p in parsed):
+        raise NotImplementedError("directional indicator models are not implemented")
+    params = np.array([[p[1], p[2], p[3]] for p in parsed])
+    values = np.stack([(known[:, 2] <= float(t)).astype(np.float64) for t in thresholds])
+    out, _, status = _lib.krige_host(known, unknown, parsed[0][0], params, _lib.KRIGE_ORDINARY, int(no_neighbors),
+                                     values=values)
+    _raise_on_singular(status)
+    col = 1 if reference_variance_column else 0
+    res = out[:, :, col].T.copy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res[res < 0] = 0                                              # indicator.py:399-403
+        res[res > 1] = 1
+    return res

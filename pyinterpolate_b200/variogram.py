@@ -1,0 +1,225 @@
+"""Experimental variogram — the reference's public calls, backed by the CUDA pair kernels.
+
+Mirrors (file:line relative to /root/reference/src/pyinterpolate/):
+  * semivariogram/experimental/experimental_semivariogram.py:19-229   calculate_semivariance
+  * semivariogram/experimental/experimental_covariogram.py:17-172     calculate_covariance
+  * semivariogram/experimental/classes/experimental_variogram.py:16-496  ExperimentalVariogram,
+                                                                      build_experimental_variogram
+  * semivariogram/experimental/classes/directional_variogram.py:8-209 DirectionalVariogram
+
+One kernel pass yields semivariance, covariance and pair counts together, so the class computes
+both curves from a single launch where the reference runs its whole pipeline twice.
+Not built yet (raise NotImplementedError, there is no CPU fallback): the triangle selection
+method ('t'), custom_weights, and the point-cloud output (as_cloud).
+"""
+import numpy as np
+
+from . import _lib, core
+
+
+def _finalize(sums, directional):
+    """Unordered-pair sums -> the reference's per-lag numbers (ordered pairs):
+    semivariance = mean((v0-vh)^2)/2 (functions/semivariance.py:22-23),
+    covariance = mean(v0*vh) - mean(vh)^2 (functions/covariance.py:22-26), n = len(v0) = 2*count.
+    Empty omnidirectional lag: (0, 0) for lag index 0 else (nan, nan) (functions/general.py:283-287)."""
+    cnt = np.asarray(sums["count"], dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sem = np.asarray(sums["sum_sq"]) / cnt / 2.0
+        mean = np.asarray(sums["sum_val"]) / (2.0 * cnt)
+        cov = np.asarray(sums["sum_prod"]) / cnt - mean * mean
+    npairs = 2.0 * cnt
+    empty = cnt == 0
+    if empty.any():
+        sem = np.where(empty, np.nan, sem)
+        cov = np.where(empty, np.nan, cov)
+        npairs = np.where(empty, np.nan, npairs)
+        if not directional and empty[..., 0].any():
+            sem[..., 0] = np.where(empty[..., 0], 0.0, sem[..., 0])
+            cov[..., 0] = np.where(empty[..., 0], 0.0, cov[..., 0])
+            npairs[..., 0] = np.where(empty[..., 0], 0.0, npairs[..., 0])
+    return sem, cov, npairs
+
+
+def _check_method(direction, method, custom_weights):
+    if custom_weights is not None:
+        raise NotImplementedError("custom_weights are not implemented in pyinterpolate_b200 yet "
+                                  "(weighted semivariance, SURVEY.md §8f-4)")
+    if direction is not None and method not in ("e", "ellipse"):
+        raise NotImplementedError("only dir_neighbors_selection_method='e' (ellipse) is implemented in "
+                                  "pyinterpolate_b200; the triangle method 't' is not built yet")
+
+
+def experimental_curves(ds, step_size=None, max_range=None, direction=None, tolerance=None,
+                        dir_neighbors_selection_method="t", custom_bins=None, custom_weights=None,
+                        directions=None, shard=(0, 1), reduce_fn=None):
+    """Shared driver: returns (lags, semivariances, covariances, n_pairs).
+
+    ``directions`` (a sequence of angles) evaluates several ellipse directions in one library call and
+    returns ``[D, L]`` arrays.  ``shard`` / ``reduce_fn`` let a multi-GPU caller evaluate one slice of
+    the tile-pair list per rank and sum the partial results (see ``distributed.py``)."""
+    points = core.variogram_points(ds)
+    core.validate_bins(step_size, max_range, custom_bins)
+    core.validate_semivariance_weights(points, custom_weights)
+    if directions is None:
+        core.validate_direction_and_tolerance(direction, tolerance)
+    else:
+        for angle in directions:
+            core.validate_direction_and_tolerance(angle, tolerance)
+    lags = core.get_lags(step_size, max_range, custom_bins)
+    directional = (direction is not None and tolerance is not None) or directions is not None
+    _check_method(direction if directions is None else 0, dir_neighbors_selection_method, custom_weights)
+    lags64 = np.ascontiguousarray(lags, dtype=np.float64)
+    xyz = np.ascontiguousarray(points, dtype=np.float64)
+    if xyz.ndim != 2 or xyz.shape[1] < 3:
+        raise ValueError("points must be rows of [x, y, value]")
+    xyz = np.ascontiguousarray(xyz[:, [0, 1, xyz.shape[1] - 1]]) if xyz.shape[1] != 3 else xyz
+    if directional:
+        angles = [direction] if directions is None else list(directions)
+        W = np.stack([core.define_whitening_matrix(a, tolerance) for a in angles]).reshape(len(angles), 4)
+        sums = _lib.variogram_host(xyz, lags64, lower=core.ellipse_lower_limits(lags64), W=W, shard=shard)
+    else:
+        sums = _lib.variogram_host(xyz, lags64, shard=shard)
+    if reduce_fn is not None:
+        sums = reduce_fn(sums)
+    sem, cov, npairs = _finalize(sums, directional)
+    if directional:
+        if directions is None:
+            sem, cov, npairs = sem[0], cov[0], npairs[0]
+        bad = np.argwhere(~(np.atleast_2d(npairs) > 0))
+        if bad.size:
+            # functions/directional.py:68-74 (idx 0 with lags[0] == 0 is the only tolerated empty lag)
+            idx = int(bad[0][-1])
+            if not (idx == 0 and lags[0] == 0):
+                raise RuntimeError(f'There are no neighbors for a lag {lags[idx]},'
+                                   f' the process has been stopped.')
+    return lags, sem, cov, npairs
+
+
+def calculate_semivariance(ds, step_size=None, max_range=None, direction=None, tolerance=None,
+                           dir_neighbors_selection_method="t", custom_bins=None, custom_weights=None):
+    """``[lag, semivariance, number of point pairs]`` — experimental_semivariogram.py:19-229."""
+    lags, sem, _, npairs = experimental_curves(ds, step_size, max_range, direction, tolerance,
+                                               dir_neighbors_selection_method, custom_bins, custom_weights)
+    return np.column_stack([lags, sem, npairs])
+
+
+def calculate_covariance(ds, step_size=None, max_range=None, direction=None, tolerance=None,
+                         dir_neighbors_selection_method="t", custom_bins=None):
+    """``[lag, covariance, number of point pairs]`` — experimental_covariogram.py:17-172."""
+    lags, _, cov, npairs = experimental_curves(ds, step_size, max_range, direction, tolerance,
+                                               dir_neighbors_selection_method, custom_bins)
+    return np.column_stack([lags, cov, npairs])
+
+
+class ExperimentalVariogram:
+    """classes/experimental_variogram.py:16-402: attributes ``lags``, ``semivariances``,
+    ``covariances``, ``points_per_lag``, ``variance``, ``direction``, ``tolerance``, ``step_size``,
+    ``max_range``, ``custom_weights``, ``model`` (a plain dict of those)."""
+
+    def __init__(self, ds, step_size=None, max_range=None, direction=None, tolerance=None,
+                 dir_neighbors_selection_method="t", custom_bins=None, custom_weights=None,
+                 is_semivariance=True, is_covariance=True, as_cloud=False):
+        if as_cloud:
+            raise NotImplementedError("as_cloud=True (variogram point cloud) is not implemented in "
+                                      "pyinterpolate_b200 yet (SURVEY.md §8f-2)")
+        self.ds = core.variogram_points(ds)
+        self.lags = None if custom_bins is None else custom_bins
+        self.points_per_lag = None
+        self.semivariances = None
+        self.covariances = None
+        self.point_cloud_semivariances = None
+        self.variance = np.var(self.ds[:, -1])                       # :155
+        self.step_size = step_size
+        self.max_range = max_range
+        self.custom_weights = custom_weights
+        self.direction = direction
+        self.tolerance = tolerance
+        self.method = dir_neighbors_selection_method
+        self.as_cloud = as_cloud
+        if is_semivariance or is_covariance:
+            lags, sem, cov, npairs = experimental_curves(
+                self.ds, step_size, max_range, direction, tolerance, dir_neighbors_selection_method,
+                self.lags, custom_weights)
+            self.lags = lags
+            self.points_per_lag = npairs
+            if is_semivariance:
+                self.semivariances = sem
+            if is_covariance:
+                self.covariances = cov
+        self.model = self.get_model_params()
+
+    def get_model_params(self):
+        return {
+            "lags": self.lags, "points_per_lag": self.points_per_lag,
+            "semivariances": self.semivariances, "covariances": self.covariances,
+            "variance": self.variance, "direction": self.direction, "tolerance": self.tolerance,
+            "max_range": self.max_range, "step_size": self.step_size,
+            "custom_weights": self.custom_weights,
+        }
+
+    def __repr__(self):
+        return f"ExperimentalVariogram(lags={None if self.lags is None else len(self.lags)}, direction={self.direction})"
+
+    def __str__(self):
+        if self.lags is None:
+            return "Empty object"
+        rows = ["lag | semivariance | covariance | var_cov_diff"]
+        for i, lag in enumerate(self.lags):
+            s = self.semivariances[i] if self.semivariances is not None else np.nan
+            c = self.covariances[i] if self.covariances is not None else np.nan
+            rows.append(f"{lag} | {s} | {c} | {self.variance - c}")
+        return "\n".join(rows)
+
+
+def build_experimental_variogram(ds, step_size=None, max_range=None, direction=None, tolerance=None,
+                                 dir_neighbors_selection_method="t", custom_bins=None, custom_weights=None,
+                                 is_semivariance=True, is_covariance=True, as_cloud=False):
+    """classes/experimental_variogram.py:405-496."""
+    return ExperimentalVariogram(ds, step_size, max_range, direction, tolerance, dir_neighbors_selection_method,
+                                 custom_bins, custom_weights, is_semivariance, is_covariance, as_cloud)
+
+
+class DirectionalVariogram:
+    """classes/directional_variogram.py:8-209 — ISO + NS (90), WE (0), NE-SW (45), NW-SE (135).
+    The four directional variograms come from ONE library call (one sort, four kernel passes)."""
+
+    def __init__(self, ds, step_size, max_range, tolerance=0.2, dir_neighbors_selection_method="t",
+                 custom_weights=None, custom_bins=None):
+        self.ds = ds
+        self.custom_bins = custom_bins
+        self.step_size = step_size
+        self.max_range = max_range
+        self.tolerance = tolerance
+        self.custom_weights = custom_weights
+        self.dir_neighbors_selection_method = dir_neighbors_selection_method
+        self.possible_variograms = ['ISO', 'NS', 'WE', 'NE-SW', 'NW-SE']
+        self.directions = {'NS': 90, 'WE': 0, 'NE-SW': 45, 'NW-SE': 135}
+        self.directional_variograms = {}
+        self._build_experimental_variograms()
+
+    def _build_experimental_variograms(self):
+        _check_method(0, self.dir_neighbors_selection_method, self.custom_weights)
+        self.directional_variograms['ISO'] = ExperimentalVariogram(
+            self.ds, self.step_size, self.max_range, custom_bins=self.custom_bins)
+        names = list(self.directions)
+        lags, sem, cov, npairs = experimental_curves(
+            self.ds, self.step_size, self.max_range, tolerance=self.tolerance, direction=None,
+            dir_neighbors_selection_method=self.dir_neighbors_selection_method, custom_bins=self.custom_bins,
+            directions=[self.directions[k] for k in names])
+        for t, name in enumerate(names):
+            ev = ExperimentalVariogram.__new__(ExperimentalVariogram)
+            iso = self.directional_variograms['ISO']
+            ev.__dict__.update(iso.__dict__)
+            ev.lags, ev.semivariances, ev.covariances, ev.points_per_lag = lags, sem[t], cov[t], npairs[t]
+            ev.direction, ev.tolerance, ev.method = self.directions[name], self.tolerance, self.dir_neighbors_selection_method
+            ev.model = ev.get_model_params()
+            self.directional_variograms[name] = ev
+
+    def get(self, direction=None):
+        if direction is None:
+            return self.directional_variograms
+        if direction in self.possible_variograms:
+            return self.directional_variograms[direction]
+        raise KeyError(f'Given direction is not possible to retrieve, pass one direction from a '
+                       f'possible_variograms: {self.possible_variograms} or leave None to get a dictionary with all '
+                       f'possible variograms.')

@@ -1,0 +1,39 @@
+"""Ad-hoc timings on the GPU box (not the bench): python scripts/quick_perf.py [n_points]"""
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from pyinterpolate_b200 import _lib
+from pyinterpolate_b200.synthetic import dem_like_field, uniform_locations
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+print("fp64 peak (DFMA probe):", _lib.fp64_peak_tflops(), "TFLOP/s")
+pts = dem_like_field(n, seed=2)
+lags = np.arange(500.0, 40500.0, 500.0)
+d = torch.from_numpy(pts).cuda()
+for rep in range(3):
+    torch.cuda.synchronize(); t0 = time.time()
+    r = _lib.variogram_device(d, lags, want_pairs=True)
+    torch.cuda.synchronize(); dt = time.time() - t0
+    ev = r["pairs_evaluated"]
+    print(f"variogram n={n}: {dt*1e3:.1f} ms  evaluated={ev:.3e} pairs -> {ev/dt:.3e} pairs/s evaluated, "
+          f"{n*(n-1)/2/dt:.3e} equivalent pairs/s, {13*ev/dt/1e12:.2f} TFLOP/s algorithmic")
+W = np.array([[1, 0, 0, 2.23606797749979]])
+torch.cuda.synchronize(); t0 = time.time()
+r = _lib.variogram_device(d[: n // 5].contiguous(), lags, W=W, want_pairs=True)
+torch.cuda.synchronize(); dt = time.time() - t0
+print(f"ellipse 1 dir n={n//5}: {dt*1e3:.1f} ms evaluated={r['pairs_evaluated']:.3e}")
+
+known = d
+for k, m in ((32, 1_000_000), (64, 1_000_000)):
+    unk = torch.from_numpy(uniform_locations(m, seed=5)).cuda()
+    params = np.array([[1.0, float(np.var(pts[:, 2])), 20000.0]])
+    for mode in (0, 1):
+        for rep in range(2):
+            torch.cuda.synchronize(); t0 = time.time()
+            out, _, st = _lib.krige_device(known, unk, 6, params, mode, k)
+            torch.cuda.synchronize(); dt = time.time() - t0
+        print(f"krige mode={mode} k={k} n={n} m={m}: {dt*1e3:.1f} ms -> {m/dt:.3e} pts/s")

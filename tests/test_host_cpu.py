@@ -1,0 +1,158 @@
+"""CPU-side tests (-m "not gpu"): the C-ABI library loads and exports every declared symbol, the
+host-side mirror of the reference interface validates like the reference, and the multi-rank plumbing
+works over gloo with world_size 2.  No CUDA compute call is made here."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    import __graft_entry__ as entry
+    from pyinterpolate_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        entry.build()
+    header = open(os.path.join(ROOT, "include", "pyinterp_b200.h")).read()
+    declared = set(re.findall(r"PIB_API\s+(?:const\s+)?\w+\s*\*?\s*(pib_\w+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pib_version() >= 100
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {line.split()[-1] for line in nm.splitlines() if " T " in line}
+    assert declared <= exported
+    # nothing but the C ABI leaks out of the library
+    assert all(s.startswith("pib_") for s in exported if not s.startswith("_")), exported
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pyinterpolate_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "synthetic.py", f
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from pyinterpolate_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.PibError, match="no CPU fallback"):
+        _lib.variogram_host(np.zeros((4, 3)), np.array([1.0]))
+    monkeypatch.undo()
+
+
+def test_lags_and_validation_match_reference_rules():
+    from pyinterpolate_b200 import core
+    np.testing.assert_array_equal(core.get_lags(500, 40000, None), np.arange(500, 40000, 500))
+    assert len(core.get_lags(500, 40000, None)) == 79 and len(core.get_lags(500, 40500, None)) == 80
+    np.testing.assert_array_equal(core.get_lags(None, None, [0, 1, 2.5]), [1, 2.5])
+    np.testing.assert_array_equal(core.get_lags(None, None, [1, 2.5]), [1, 2.5])
+    with pytest.raises(ValueError):
+        core.validate_bins(None, None, None)
+    core.validate_direction_and_tolerance(None, None)
+    core.validate_direction_and_tolerance(-360, 1)
+    for bad in ((361, 0.5), (10, 0), (10, 1.5), (None, 0.5), (10, None)):
+        with pytest.raises(ValueError):
+            core.validate_direction_and_tolerance(*bad)
+    with pytest.raises(IndexError):
+        core.validate_semivariance_weights(np.zeros((3, 3)), [1, 2])
+    with pytest.raises(ValueError):
+        core.validate_semivariance_weights(np.zeros((2, 3)), [1, 0])
+    assert core.interpolation_points([1.0, 2.0]).shape == (1, 2)
+    assert core.interpolation_points([[1.0, 2.0], [3.0, 4.0]]).shape == (2, 2)
+    assert core.variogram_points([[0, 0, 1], [1, 1, 2]]).shape == (2, 3)
+
+
+def test_whitening_matrix_and_lower_limits_match_golden(golden):
+    from pyinterpolate_b200 import core
+    for (ang, tol), W in zip(golden["whiten_cfg"], golden["whiten_W"]):
+        np.testing.assert_array_equal(core.define_whitening_matrix(ang, tol), W)
+    for lags in (np.arange(500.0, 40500.0, 500.0), np.arange(0.1, 3.05, 0.1), np.arange(1.5, 6, 1.5)):
+        lower = core.ellipse_lower_limits(lags)
+        np.testing.assert_array_equal(lower, np.concatenate([[0.0], lags[:-1]]))   # regular bins tile exactly
+
+
+def test_finalize_matches_oracle_conventions(oracle):
+    from pyinterpolate_b200.variogram import _finalize
+    sums = dict(sum_sq=np.array([0.0, 8.0, 0.0]), sum_prod=np.array([0.0, 6.0, 0.0]),
+                sum_val=np.array([0.0, 10.0, 0.0]), count=np.array([0, 2, 0]))
+    sem, cov, n = _finalize(sums, directional=False)
+    o_sem, o_cov, o_n = oracle.finalize(sums)
+    np.testing.assert_array_equal(sem, o_sem)
+    np.testing.assert_array_equal(cov, o_cov)
+    np.testing.assert_array_equal(n, o_n)
+    assert sem[0] == 0 and np.isnan(sem[2]) and n[1] == 4
+
+
+def test_model_container():
+    import pyinterpolate_b200 as pib
+    m = pib.TheoreticalVariogram({"variogram_model_type": "spherical", "nugget": 1, "sill": 2, "rang": 3})
+    assert m.to_dict() == dict(nugget=1, sill=2, rang=3, variogram_model_type="spherical", direction=None)
+    assert m.name == "spherical"
+    with pytest.raises(KeyError):
+        pib.TheoreticalVariogram({"variogram_model_type": "matern", "nugget": 1, "sill": 2, "rang": 3})
+    from pyinterpolate_b200.models import model_parameters
+
+    class Duck:
+        nugget, sill, rang, model_type, direction = 0.5, 2.0, 10.0, "cubic", None
+    assert model_parameters(Duck()) == (1, 0.5, 2.0, 10.0, None)
+
+
+def test_shard_bounds_cover_everything():
+    from pyinterpolate_b200.distributed import shard_bounds
+    for m in (0, 1, 7, 10_000_001):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(m, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == m
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle"))
+import numpy as np, torch.distributed as dist
+import oracle
+from pyinterpolate_b200 import distributed as pd
+from pyinterpolate_b200.synthetic import dem_like_field
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank, world = pd.rank_world()
+pts = dem_like_field(1500, seed=3)
+lags = np.arange(2500.0, 40000.0, 2500.0)
+# each rank contributes the pair rows it owns (the GPU path shards tile pairs; the reduction is the same)
+b, e = pd.shard_bounds(len(pts), rank, world)
+part = oracle.variogram_sums(pts, lags, rows=(b, e))
+part["pairs_evaluated"] = 10 + rank
+total = pd.allreduce_variogram_sums(part)
+full = oracle.variogram_sums(pts, lags)
+assert np.array_equal(total["count"], full["count"])
+assert np.allclose(total["sum_sq"], full["sum_sq"], rtol=1e-12)
+assert total["pairs_evaluated"] == 21
+rows = np.arange(2 * 11, dtype=np.float64).reshape(11, 2)
+b, e = pd.shard_bounds(11, rank, world)
+back = pd.gather_rows(rows[b:e] * 1.0, 11)
+assert np.array_equal(back, rows)
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_gloo_allreduce_and_gather(tmp_path, oracle):
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"rank {r} ok" in o
