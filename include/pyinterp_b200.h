@@ -10,7 +10,9 @@
  * Conventions
  *   - plain pointers and sizes only; no torch / C++ types cross this boundary
  *   - `*_device` entry points take DEVICE pointers and enqueue on `stream`
- *     (a cudaStream_t passed as void*, NULL = legacy default stream) WITHOUT synchronising
+ *     (a cudaStream_t passed as void*, NULL = legacy default stream); results are ready when the
+ *     stream reaches the end of the enqueued work (the call itself only waits for a 32-byte
+ *     bounding-box read-back while planning)
  *   - `*_host` entry points take HOST pointers, do their own H2D / D2H copies and return
  *     after the results are in host memory
  *   - every function returns PIB_OK (0) or a negative error; pib_last_error() has the text
@@ -147,6 +149,12 @@ PIB_API int pib_krige_host(const double *known, int64_t n,
 /* gamma(h) for h[0..n) with the device implementation of the seven models (for tests) */
 PIB_API int pib_gamma_host(int model, double nugget, double sill, double rang,
                    const double *h, int64_t n, double *out);
+
+/* Device time (CUDA events on the launching stream) spent in one hot kernel during the LAST
+ * variogram / kriging call of this process: which = 0 pair kernel, 1 neighbour-search kernel,
+ * 2 assemble+solve kernel.  launches_out (may be NULL) receives how many times it was launched.
+ * Synchronises on the recorded events. */
+PIB_API int pib_last_kernel_ms(int which, double *ms_out, int *launches_out);
 
 /* FP64 throughput probe: runs a dependent-chain-free DFMA kernel and returns TFLOP/s
  * (2 flop per DFMA) measured with CUDA events.  Used by bench.py for the roofline

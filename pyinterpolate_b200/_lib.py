@@ -18,7 +18,7 @@ STATUS_OK, STATUS_SINGULAR, STATUS_NEGATIVE_VARIANCE = 0, 1, 2
 
 EXPORTS = ("pib_last_error", "pib_version", "pib_device_sm_count", "pib_variogram_device",
            "pib_variogram_host", "pib_krige_device", "pib_krige_host", "pib_gamma_host",
-           "pib_fp64_peak_tflops")
+           "pib_fp64_peak_tflops", "pib_last_kernel_ms")
 
 _lib = None
 
@@ -49,6 +49,7 @@ def load():
     L.pib_krige_host.argtypes = kr_args
     L.pib_gamma_host.argtypes = [i32, f64, f64, f64, dp, i64, dp]
     L.pib_fp64_peak_tflops.argtypes = [dp]
+    L.pib_last_kernel_ms.argtypes = [i32, dp, dp]
     for name in EXPORTS:
         getattr(L, name).restype = getattr(L, name).restype or i32
     L.pib_last_error.restype = ctypes.c_char_p
@@ -172,3 +173,15 @@ def fp64_peak_tflops():
     v = ctypes.c_double(0.0)
     check(L.pib_fp64_peak_tflops(ctypes.cast(ctypes.byref(v), ctypes.c_void_p)), "pib_fp64_peak_tflops")
     return float(v.value)
+
+
+KERNEL_PAIR, KERNEL_KNN, KERNEL_SOLVE = 0, 1, 2
+
+
+def last_kernel_ms(which):
+    """(milliseconds, launches) of one hot kernel during the last library call (CUDA events)."""
+    L = load()
+    ms, launches = ctypes.c_double(0.0), ctypes.c_int(0)
+    check(L.pib_last_kernel_ms(int(which), ctypes.cast(ctypes.byref(ms), ctypes.c_void_p),
+                               ctypes.cast(ctypes.byref(launches), ctypes.c_void_p)), "pib_last_kernel_ms")
+    return float(ms.value), int(launches.value)

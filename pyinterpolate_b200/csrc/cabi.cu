@@ -23,6 +23,30 @@ int sm_count()
     return cached;
 }
 
+struct Segment { cudaEvent_t a, b; };
+static std::vector<Segment> g_segments[PIB_T_COUNT];
+static std::mutex g_timing_mutex;
+
+void timing_reset(int which)
+{
+    std::lock_guard<std::mutex> lock(g_timing_mutex);
+    for (auto &s : g_segments[which]) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    g_segments[which].clear();
+}
+void timing_begin(int which, cudaStream_t stream)
+{
+    std::lock_guard<std::mutex> lock(g_timing_mutex);
+    Segment s;
+    if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
+    cudaEventRecord(s.a, stream);
+    g_segments[which].push_back(s);
+}
+void timing_end(int which, cudaStream_t stream)
+{
+    std::lock_guard<std::mutex> lock(g_timing_mutex);
+    if (!g_segments[which].empty()) cudaEventRecord(g_segments[which].back().b, stream);
+}
+
 int variogram_device(const double *d_xyz, int64_t n, const double *edges, const double *lower, int n_lags,
                      const double *W, int n_dirs, int shard_index, int shard_count,
                      double *d_sum_sq, double *d_sum_prod, double *d_sum_val, int64_t *d_count,
@@ -174,6 +198,22 @@ int pib_gamma_host(int model, double nugget, double sill, double rang, const dou
     cudaFree(d_h); cudaFree(d_o);
     if (rc == PIB_ERR_CUDA) set_error("gamma: CUDA copy failed");
     return rc;
+}
+
+int pib_last_kernel_ms(int which, double *ms_out, int *launches_out)
+{
+    PIB_CHECK(which >= 0 && which < PIB_T_COUNT && ms_out, PIB_ERR_INVALID, "last_kernel_ms: bad argument");
+    std::lock_guard<std::mutex> lock(g_timing_mutex);
+    double total = 0.0;
+    for (auto &s : g_segments[which]) {
+        PIB_CUDA(cudaEventSynchronize(s.b));
+        float ms = 0;
+        PIB_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
+        total += ms;
+    }
+    *ms_out = total;
+    if (launches_out) *launches_out = (int)g_segments[which].size();
+    return PIB_OK;
 }
 
 int pib_fp64_peak_tflops(double *tflops_out)

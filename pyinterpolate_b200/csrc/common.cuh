@@ -62,6 +62,14 @@ struct Scratch {
 
 int sm_count();
 
+// Per-kernel device timing for bench.py's roofline: CUDA events recorded on the launching stream
+// around the hot kernels of the LAST library call (several segments when a call launches the kernel
+// more than once).  Read back with pib_last_kernel_ms().
+enum { PIB_T_PAIR = 0, PIB_T_KNN = 1, PIB_T_SOLVE = 2, PIB_T_COUNT = 3 };
+void timing_reset(int which);
+void timing_begin(int which, cudaStream_t stream);
+void timing_end(int which, cudaStream_t stream);
+
 // ---- spatial preprocessing (spatial.cu) --------------------------------------------------
 // Morton-ordered structure-of-arrays copy of the points, padded to a multiple of `pad_to`
 // with far-away sentinels, plus one bounding box per `tile` consecutive points.

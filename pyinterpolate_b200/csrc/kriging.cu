@@ -369,6 +369,8 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
     PIB_CHECK(m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31), PIB_ERR_UNSUPPORTED, "krige: more than 2^31-1 rows");
     const int kk = (int)std::min<int64_t>(k, n);
     PIB_CHECK(kk <= MAX_K, PIB_ERR_UNSUPPORTED, "krige: no_neighbors above 128 is not supported");
+    timing_reset(PIB_T_KNN);
+    timing_reset(PIB_T_SOLVE);
     if (m == 0) return PIB_OK;
 
     Scratch ws(stream);
@@ -406,14 +408,18 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
         KnnParams kp;
         kp.g = g; kp.unknown = d_unknown; kp.order = order + begin; kp.count = count; kp.kk = kk; kp.k2 = k2; kp.r0 = r0;
         kp.nbr_pos = nbr_pos; kp.nbr_d = nbr_d; kp.nbr_idx = d_nbr_idx; kp.k = k;
+        timing_begin(PIB_T_KNN, stream);
         knn_kernel<<<(int)((count + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, knn_smem, stream>>>(kp);
+        timing_end(PIB_T_KNN, stream);
         PIB_CUDA(cudaGetLastError());
         SolveParams sp;
         sp.g = g; sp.unknown = d_unknown; sp.order = order + begin; sp.count = count; sp.m = m; sp.n = n; sp.kk = kk; sp.k = k;
         sp.nbr_pos = nbr_pos; sp.nbr_d = nbr_d; sp.values = d_values; sp.params = d_params; sp.n_sets = n_sets;
         sp.model = model; sp.mode = mode; sp.process_mean = process_mean; sp.out = d_out; sp.status = d_status;
         sp.warps = solve_warps; sp.stride = stride;
+        timing_begin(PIB_T_SOLVE, stream);
         solve_kernel<<<(int)((count + solve_warps - 1) / solve_warps), solve_warps * 32, per_warp * solve_warps, stream>>>(sp);
+        timing_end(PIB_T_SOLVE, stream);
         PIB_CUDA(cudaGetLastError());
     }
     return PIB_OK;

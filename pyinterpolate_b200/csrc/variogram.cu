@@ -95,51 +95,51 @@ static __device__ __forceinline__ double box_min_d2(const double4 a, const doubl
     return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
 }
 
-// Shared memory layout (dynamic):
-//   double2  acc[n_slots][NT]     private (sum dz, sum dz^2)
-//   uint32_t cnt[n_slots][NT]     private pair counts
-//   double   upper[n_slots]
-//   uint16_t lut[LUT_N]
-//   double2  txy[2][TILE]; double tz[2][TILE]    B tile double buffer
-//   uint64_t bar[2]; uint64_t live_mask
+// Shared memory:
+//   static : B tile double buffer (TMA destination), slot thresholds, distance->slot table, mbarriers
+//   dynamic: double2 acc[n_slots][NT] private (sum dz, sum dz^2); uint32_t cnt[n_slots][NT] private counts
+// The read-only tables are separate static objects so the compiler can prove that loads from them never
+// alias the private histogram stores and may hoist them freely (that is what lets it overlap the
+// distance / slot computation of one batch of pairs with the read-modify-writes of the previous batch).
+constexpr int MAX_SLOTS = 352;
+constexpr int STATIC_SMEM = 2 * TILE * 24 + MAX_SLOTS * 8 + LUT_N * 2 + 64;
+
 template <int NT>
 static size_t pair_smem_bytes(int n_slots)
 {
-    size_t b = (size_t)n_slots * NT * (sizeof(double2) + sizeof(uint32_t));
-    b += ((size_t)n_slots * sizeof(double) + 15) / 16 * 16;
-    b += LUT_N * sizeof(uint16_t);
-    b += 2 * TILE * (sizeof(double2) + sizeof(double));
-    b += 64;
-    return b;
+    return (size_t)n_slots * NT * (sizeof(double2) + sizeof(uint32_t));
 }
 
-template <int NT, bool ELLIPSE>
+// FIX = number of branch-free threshold steps after the table lookup (0: data-dependent loop)
+template <int NT, bool ELLIPSE, int FIX>
 __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
 {
     static_assert(TILE % NT == 0, "an A sub-tile is NT consecutive points of one tile");
     constexpr int A_PER_TILE = TILE / NT;          // thread t owns point t of the A sub-tile
+    constexpr int U = 8;                           // pairs per batch
+    static_assert(TILE % (2 * U) == 0, "tile must hold an even number of batches");
+    __shared__ __align__(16) double2 s_txy[2][TILE];
+    __shared__ __align__(16) double s_tz[2][TILE];
+    __shared__ long long s_upper[MAX_SLOTS];       // thresholds as bit patterns: d2 >= 0, so integer order == fp order
+    __shared__ uint16_t s_lut[LUT_N];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint64_t s_live;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_slots = p.n_slots;
 
-    double2 *acc = reinterpret_cast<double2 *>(smem_raw);
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(acc + (size_t)n_slots * NT);
-    double *upper = reinterpret_cast<double *>(cnt + (size_t)n_slots * NT);
-    uint16_t *lut = reinterpret_cast<uint16_t *>(upper + (n_slots + 1) / 2 * 2);
-    double2 *txy = reinterpret_cast<double2 *>(lut + LUT_N);
-    double *tz = reinterpret_cast<double *>(txy + 2 * TILE);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(tz + 2 * TILE);
-    uint64_t *live_mask = bar + 2;
+    double2 *acc = reinterpret_cast<double2 *>(smem_raw) + tid;            // acc[s * NT]
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw + (size_t)n_slots * NT * sizeof(double2)) + tid;
 
     for (int s = 0; s < n_slots; ++s) {
-        acc[s * NT + tid] = make_double2(0.0, 0.0);
-        cnt[s * NT + tid] = 0u;
+        acc[s * NT] = make_double2(0.0, 0.0);
+        cnt[s * NT] = 0u;
     }
-    for (int s = tid; s < n_slots; s += NT) upper[s] = p.upper[s];
-    for (int s = tid; s < LUT_N; s += NT) lut[s] = p.lut[s];
+    for (int s = tid; s < n_slots; s += NT) s_upper[s] = __double_as_longlong(p.upper[s]);
+    for (int s = tid; s < LUT_N; s += NT) s_lut[s] = p.lut[s];
     if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
     unsigned long long evaluated = 0;
     double *my_partial = p.partial + ((size_t)blockIdx.x * (NT / 32) + warp) * n_slots * 4;
     const float lut_scale = p.lut_scale;
+    const double w00 = p.w00, w01 = p.w01, w10 = p.w10, w11 = p.w11;
 
     for (int64_t item = ((int64_t)blockIdx.x) * p.shard_count + p.shard_index; item < n_items;
          item += (int64_t)gridDim.x * p.shard_count) {
@@ -176,13 +177,13 @@ __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
                 }
                 m |= (uint64_t)__ballot_sync(0xffffffffu, live) << (32 * h);
             }
-            if (lane == 0) *live_mask = m;
+            if (lane == 0) s_live = m;
         }
         __syncthreads();
-        uint64_t live = *live_mask;
+        uint64_t live = s_live;
         if (live == 0) { __syncthreads(); continue; }
 
-        // ---- my A points -------------------------------------------------------------------
+        // ---- my A point ----------------------------------------------------------------------
         const int ig = (int)a0 + tid;
         const double2 pa = p.xy[ig];
         const double xi = pa.x, yi = pa.y, zi = p.z[ig];
@@ -192,9 +193,9 @@ __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
         live &= live - 1;
         if (tid == 0) {
             const uint32_t b = seq & 1;
-            mbar_expect_tx(&bar[b], TILE * (sizeof(double2) + sizeof(double)));
-            tma_load_1d(txy + b * TILE, p.xy + (size_t)tb * TILE, TILE * sizeof(double2), &bar[b]);
-            tma_load_1d(tz + b * TILE, p.z + (size_t)tb * TILE, TILE * sizeof(double), &bar[b]);
+            mbar_expect_tx(&s_bar[b], TILE * (sizeof(double2) + sizeof(double)));
+            tma_load_1d(s_txy[b], p.xy + (size_t)tb * TILE, TILE * sizeof(double2), &s_bar[b]);
+            tma_load_1d(s_tz[b], p.z + (size_t)tb * TILE, TILE * sizeof(double), &s_bar[b]);
         }
         while (true) {
             const uint32_t b = seq & 1, phase = (seq >> 1) & 1;
@@ -202,15 +203,15 @@ __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
             live &= live - 1;
             if (tid == 0 && tb_next >= 0) {                   // buffer b^1 was released by the barrier below
                 const uint32_t nb = b ^ 1;
-                mbar_expect_tx(&bar[nb], TILE * (sizeof(double2) + sizeof(double)));
-                tma_load_1d(txy + nb * TILE, p.xy + (size_t)tb_next * TILE, TILE * sizeof(double2), &bar[nb]);
-                tma_load_1d(tz + nb * TILE, p.z + (size_t)tb_next * TILE, TILE * sizeof(double), &bar[nb]);
+                mbar_expect_tx(&s_bar[nb], TILE * (sizeof(double2) + sizeof(double)));
+                tma_load_1d(s_txy[nb], p.xy + (size_t)tb_next * TILE, TILE * sizeof(double2), &s_bar[nb]);
+                tma_load_1d(s_tz[nb], p.z + (size_t)tb_next * TILE, TILE * sizeof(double), &s_bar[nb]);
             }
-            mbar_wait(&bar[b], phase);
+            mbar_wait(&s_bar[b], phase);
             ++seq;
 
-            const double2 *bxy = txy + b * TILE;
-            const double *bz = tz + b * TILE;
+            const double2 *bxy = s_txy[b];
+            const double *bz = s_tz[b];
             const bool diagonal = (tb == ta);
             const int jbase = tb * TILE;
             if (tid == 0) {
@@ -219,40 +220,85 @@ __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
                 evaluated += diagonal ? (unsigned long long)(va * (jbase + vb - 1) - va * a0 - va * (va - 1) / 2)
                                       : (unsigned long long)(va * vb);
             }
-#pragma unroll 2
-            for (int j = 0; j < TILE; ++j) {
-                const double2 pj = bxy[j];
-                const double zj = bz[j];
-                {
-                    double d2;
+
+            // slot and dz of U consecutive pairs, written stage by stage (all U distances, then all U
+            // table lookups, ...) so the U independent dependency chains are interleaved in the schedule:
+            // with one warp per scheduler the latency of each step is hidden by the other U-1 pairs
+            auto compute = [&](int j0, int (&slot)[U], double (&dzv)[U]) {
+                double d2[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const double2 pj = bxy[j0 + u];
+                    dzv[u] = __dsub_rn(zi, bz[j0 + u]);
                     if (ELLIPSE) {
                         // vector_distance = other - centre (angular.py:448); W @ d as OpenBLAS dgemm
                         // evaluates it: fma(W[r][1], dy, W[r][0]*dx); einsum: n0*n0 + n1*n1 un-fused
                         const double dx = __dsub_rn(pj.x, xi), dy = __dsub_rn(pj.y, yi);
-                        const double n0 = __fma_rn(p.w01, dy, __dmul_rn(p.w00, dx));
-                        const double n1 = __fma_rn(p.w11, dy, __dmul_rn(p.w10, dx));
-                        d2 = __dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1));
+                        const double n0 = __fma_rn(w01, dy, __dmul_rn(w00, dx));
+                        const double n1 = __fma_rn(w11, dy, __dmul_rn(w10, dx));
+                        d2[u] = __dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1));
                     } else {
                         // scipy cdist euclidean: sqrt(dx*dx + dy*dy), nothing fused (distance/point.py:56)
                         const double dx = __dsub_rn(xi, pj.x), dy = __dsub_rn(yi, pj.y);
-                        d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                        d2[u] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
                     }
-                    // first candidate slot from a float estimate of the distance, then exact fix-up
-                    float r;
-                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__double2float_rn(d2)));
-                    int e = __float2int_rz(r * lut_scale);
-                    e = min(e, LUT_N - 1);
-                    int s = lut[e];
-                    while (d2 > upper[s]) ++s;
-                    if (diagonal && !(jbase + j > ig)) s = 0;     // keep i < j only
-                    const double dz = __dsub_rn(zi, zj);
-                    double2 a = acc[s * NT + tid];
-                    a.x += dz;
-                    a.y = __fma_rn(dz, dz, a.y);
-                    acc[s * NT + tid] = a;
-                    cnt[s * NT + tid] += 1u;
                 }
+                // first candidate slot from a float estimate of the distance ...
+                int e[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    float r;
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__double2float_rn(d2[u])));
+                    e[u] = min(__float2int_rz(r * lut_scale), LUT_N - 1);
+                }
+                int sl[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) sl[u] = s_lut[e[u]];
+                // ... then the exact fix-up on the bit pattern of the fp64 squared distance
+                if (FIX > 0) {
+#pragma unroll
+                    for (int t = 0; t < FIX; ++t) {
+                        long long thr[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) thr[u] = s_upper[sl[u]];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) sl[u] += (__double_as_longlong(d2[u]) > thr[u]) ? 1 : 0;
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        while (__double_as_longlong(d2[u]) > s_upper[sl[u]]) ++sl[u];
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (diagonal && !(jbase + j0 + u > ig)) sl[u] = 0;     // keep i < j only
+                    slot[u] = sl[u] * NT;
+                }
+            };
+            auto rmw = [&](const int (&slot)[U], const double (&dzv)[U]) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    double2 a = acc[slot[u]];
+                    a.x += dzv[u];
+                    a.y = __fma_rn(dzv[u], dzv[u], a.y);
+                    acc[slot[u]] = a;
+                    cnt[slot[u]] += 1u;
+                }
+            };
+            int sA[U], sB[U];
+            double dA[U], dB[U];
+            // software pipeline: the slots of batch k+1 are computed while batch k is accumulated
+            compute(0, sA, dA);
+#pragma unroll 1
+            for (int j0 = 0; j0 < TILE - 2 * U; j0 += 2 * U) {
+                compute(j0 + U, sB, dB);
+                rmw(sA, dA);
+                compute(j0 + 2 * U, sA, dA);
+                rmw(sB, dB);
             }
+            compute(TILE - U, sB, dB);
+            rmw(sA, dA);
+            rmw(sB, dB);
             __syncthreads();                                  // everyone is done with buffer b
             if (tb_next < 0) break;
             tb = tb_next;
@@ -262,15 +308,15 @@ __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
         //   sum z_i z_j   = sum z_i (z_i - dz) = c z_i^2 - z_i S1
         //   sum (z_i+z_j) = 2 c z_i - S1
         for (int s = 1; s < n_slots - 1; ++s) {
-            const double2 a = acc[s * NT + tid];
-            const uint32_t c = cnt[s * NT + tid];
+            const uint32_t c = cnt[s * NT];
+            // any lane with something to add?  (most slots are empty for a given item)
+            if (__ballot_sync(0xffffffffu, c != 0u) == 0u) continue;
+            const double2 a = acc[s * NT];
             const double cd = (double)c;
             double v_sq = a.y;
             double v_prod = __fma_rn(-zi, a.x, cd * zi * zi);
             double v_val = __fma_rn(2.0 * cd, zi, -a.x);
             unsigned long long v_cnt = c;
-            // any lane with something to add?  (most slots are empty for a given item)
-            if (__ballot_sync(0xffffffffu, c != 0u) == 0u) continue;
             for (int o = 16; o; o >>= 1) {
                 v_sq += __shfl_xor_sync(0xffffffffu, v_sq, o);
                 v_prod += __shfl_xor_sync(0xffffffffu, v_prod, o);
@@ -282,12 +328,320 @@ __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
                 dst[0] += v_sq; dst[1] += v_prod; dst[2] += v_val;
                 reinterpret_cast<unsigned long long *>(dst)[3] += v_cnt;
             }
-            acc[s * NT + tid] = make_double2(0.0, 0.0);
-            cnt[s * NT + tid] = 0u;
+            acc[s * NT] = make_double2(0.0, 0.0);
+            cnt[s * NT] = 0u;
         }
-        // trash slots are never read; reset their counters so they cannot overflow
-        cnt[tid] = 0u; cnt[(n_slots - 1) * NT + tid] = 0u;
-        acc[tid] = make_double2(0.0, 0.0); acc[(n_slots - 1) * NT + tid] = make_double2(0.0, 0.0);
+        // trash slots are never read; reset them so their counters cannot overflow
+        cnt[0] = 0u; cnt[(n_slots - 1) * NT] = 0u;
+        acc[0] = make_double2(0.0, 0.0); acc[(n_slots - 1) * NT] = make_double2(0.0, 0.0);
+    }
+    if (tid == 0 && evaluated) atomicAdd(p.pairs_evaluated, evaluated);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ring-window kernel: the fast path when tiles are small against the lag width.
+//
+// The full-histogram kernel above is limited to 128 threads per SM (one private histogram of
+// n_lags + 2 slots per thread fills the shared memory), i.e. one warp per scheduler, and the
+// per-pair dependency chain (distance -> slot -> read-modify-write) is then exposed latency.
+// A tile pair only touches the few lags between the smallest and largest distance of its two
+// bounding boxes, so here a thread keeps a RING of 32 slots (slot = (lag & 31)) plus one trash slot:
+// 660 B per thread -> 256 threads per CTA (two warps per scheduler).  The CTA tracks the range of
+// lags touched since the last fold; before a tile pair that would stretch the range to 32 or more
+// lags, every warp folds its rings into the per-warp global partials (lane l sums ring slot l over
+// the 32 threads of the warp).  A tile pair that alone spans >= 32 lags takes a slow path
+// (global atomics); the host only picks this kernel when that is rare.
+// ---------------------------------------------------------------------------------------------
+constexpr int RING = 32;
+constexpr int RING_NT = 256;
+constexpr int RING_TILES = RING_NT / TILE;     // A sub-tile = 2 tiles
+
+template <bool ELLIPSE, int FIX>
+__global__ void __launch_bounds__(RING_NT, 1) pair_ring_kernel(const PairParams p)
+{
+    constexpr int NT = RING_NT;
+    constexpr int U = 8;
+    __shared__ __align__(16) double2 s_txy[2][TILE];
+    __shared__ __align__(16) double s_tz[2][TILE];
+    __shared__ long long s_upper[MAX_SLOTS];
+    __shared__ uint16_t s_lut[LUT_N];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint64_t s_live;
+    __shared__ short2 s_range[CHUNK];              // lag-slot range [lo, hi] of each B tile of the chunk
+    __shared__ double s_zi[NT];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_slots = p.n_slots, n_lags = n_slots - 2;
+
+    double2 *acc_all = reinterpret_cast<double2 *>(smem_raw);                         // [RING + 1][NT]
+    uint32_t *cnt_all = reinterpret_cast<uint32_t *>(smem_raw + (size_t)(RING + 1) * NT * sizeof(double2));
+    double2 *acc = acc_all + tid;
+    uint32_t *cnt = cnt_all + tid;
+
+    for (int s = 0; s <= RING; ++s) {
+        acc[s * NT] = make_double2(0.0, 0.0);
+        cnt[s * NT] = 0u;
+    }
+    for (int s = tid; s < n_slots; s += NT) s_upper[s] = __double_as_longlong(p.upper[s]);
+    for (int s = tid; s < LUT_N; s += NT) s_lut[s] = p.lut[s];
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int n_tiles = p.n_tiles;
+    const int n_atiles = (n_tiles + RING_TILES - 1) / RING_TILES;
+    const int n_chunks = (n_tiles + CHUNK - 1) / CHUNK;
+    const int64_t n_items = (int64_t)n_atiles * n_chunks;
+    uint32_t seq = 0;
+    unsigned long long evaluated = 0;
+    double *my_partial = p.partial + ((size_t)blockIdx.x * (NT / 32) + warp) * n_slots * 4;
+    const float lut_scale = p.lut_scale;
+    const double w00 = p.w00, w01 = p.w01, w10 = p.w10, w11 = p.w11;
+
+    for (int64_t item = ((int64_t)blockIdx.x) * p.shard_count + p.shard_index; item < n_items;
+         item += (int64_t)gridDim.x * p.shard_count) {
+        const int64_t a0 = (item / n_chunks) * NT;            // first point of my A sub-tile
+        const int ta = (int)(a0 / TILE);                      // first of its RING_TILES tiles
+        const int ta_last = min(ta + RING_TILES, n_tiles) - 1;
+        const int tb0 = (int)(item % n_chunks) * CHUNK;
+        const int tb1 = min(tb0 + CHUNK, n_tiles);
+        const int valid_a = (int)max((int64_t)0, min((int64_t)NT, p.n - a0));
+        if (tb1 <= ta || valid_a == 0) continue;
+        const int tb_first = max(tb0, ta);
+
+        // bounding box of the A sub-tile
+        double4 abox = p.tile_box[ta];
+        for (int t = ta + 1; t <= ta_last; ++t) {
+            const double4 o = p.tile_box[t];
+            abox.x = fmin(abox.x, o.x); abox.y = fmin(abox.y, o.y);
+            abox.z = fmax(abox.z, o.z); abox.w = fmax(abox.w, o.w);
+        }
+        // ---- per B tile: can it hold a pair within range, and which lags can it touch? ----------
+        if (warp == 0) {
+            uint64_t m = 0;
+            for (int h = 0; h < CHUNK / 32; ++h) {
+                const int tb = tb0 + h * 32 + lane;
+                bool live = false;
+                if (tb >= tb_first && tb < tb1) {
+                    const double4 bbox = p.tile_box[tb];
+                    const double dmin = box_min_d2(abox, bbox);
+                    live = dmin * (1.0 - 1e-12) <= p.max_d2;
+                    if (live) {
+                        // every pair of the two boxes has dmin <= d2 <= dmax in the kernel's own arithmetic
+                        const double dxm = fmax(abox.z - bbox.x, bbox.z - abox.x);
+                        const double dym = fmax(abox.w - bbox.y, bbox.w - abox.y);
+                        const double dmax = __dadd_rn(__dmul_rn(dxm, dxm), __dmul_rn(dym, dym));
+                        int lo = 0, hi = 0;
+                        {   // first slot whose threshold is >= value (binary search over ascending thresholds)
+                            int a = 0, b = n_slots - 1;
+                            const long long v = __double_as_longlong(dmin);
+                            while (a < b) { const int mid = (a + b) >> 1; if (v <= s_upper[mid]) b = mid; else a = mid + 1; }
+                            lo = a;
+                            a = 0; b = n_slots - 1;
+                            const long long w = __double_as_longlong(dmax);
+                            while (a < b) { const int mid = (a + b) >> 1; if (w <= s_upper[mid]) b = mid; else a = mid + 1; }
+                            hi = a;
+                        }
+                        lo = max(lo, 1); hi = min(hi, n_lags);
+                        s_range[h * 32 + lane] = make_short2((short)lo, (short)hi);
+                    }
+                }
+                m |= (uint64_t)__ballot_sync(0xffffffffu, live) << (32 * h);
+            }
+            if (lane == 0) s_live = m;
+        }
+        __syncthreads();
+        uint64_t live = s_live;
+        if (live == 0) { __syncthreads(); continue; }
+
+        const int ig = (int)a0 + tid;
+        const double2 pa = p.xy[ig];
+        const double xi = pa.x, yi = pa.y, zi = p.z[ig];
+        s_zi[tid] = zi;
+        int win_lo = 0x7fff, win_hi = 0;                      // lag slots touched since the last fold (empty)
+
+        // fold the rings of my warp into its global partials (lane l owns ring slot l)
+        auto fold = [&]() {
+            __syncwarp();
+            if (win_hi >= win_lo) {
+                const int abs_slot = win_lo + ((lane - win_lo) & (RING - 1));       // the slot of the window that maps to ring `lane`
+                double v_sq = 0.0, v_prod = 0.0, v_val = 0.0;
+                unsigned long long v_cnt = 0;
+                const int row = lane * NT + warp * 32;
+                for (int t = 0; t < 32; ++t) {
+                    const int tt = (t + lane) & 31;           // rotate so the lanes of a quarter-warp hit different banks
+                    const uint32_t c = cnt_all[row + tt];
+                    if (c) {
+                        const double2 a = acc_all[row + tt];
+                        const double z = s_zi[warp * 32 + tt], cd = (double)c;
+                        //   sum z_i z_j = c z_i^2 - z_i S1 ;  sum (z_i + z_j) = 2 c z_i - S1   (z_j = z_i - dz)
+                        v_sq += a.y;
+                        v_prod += __fma_rn(-z, a.x, cd * z * z);
+                        v_val += __fma_rn(2.0 * cd, z, -a.x);
+                        v_cnt += c;
+                        acc_all[row + tt] = make_double2(0.0, 0.0);
+                        cnt_all[row + tt] = 0u;
+                    }
+                }
+                if (v_cnt && abs_slot <= win_hi) {
+                    double *dst = my_partial + (size_t)abs_slot * 4;
+                    dst[0] += v_sq; dst[1] += v_prod; dst[2] += v_val;
+                    reinterpret_cast<unsigned long long *>(dst)[3] += v_cnt;
+                }
+            }
+            __syncwarp();
+            win_lo = 0x7fff; win_hi = 0;
+        };
+
+        int tb = tb0 + __ffsll((long long)live) - 1;
+        live &= live - 1;
+        if (tid == 0) {
+            const uint32_t b = seq & 1;
+            mbar_expect_tx(&s_bar[b], TILE * (sizeof(double2) + sizeof(double)));
+            tma_load_1d(s_txy[b], p.xy + (size_t)tb * TILE, TILE * sizeof(double2), &s_bar[b]);
+            tma_load_1d(s_tz[b], p.z + (size_t)tb * TILE, TILE * sizeof(double), &s_bar[b]);
+        }
+        while (true) {
+            const uint32_t b = seq & 1, phase = (seq >> 1) & 1;
+            const int tb_next = live ? tb0 + __ffsll((long long)live) - 1 : -1;
+            live &= live - 1;
+            if (tid == 0 && tb_next >= 0) {
+                const uint32_t nb = b ^ 1;
+                mbar_expect_tx(&s_bar[nb], TILE * (sizeof(double2) + sizeof(double)));
+                tma_load_1d(s_txy[nb], p.xy + (size_t)tb_next * TILE, TILE * sizeof(double2), &s_bar[nb]);
+                tma_load_1d(s_tz[nb], p.z + (size_t)tb_next * TILE, TILE * sizeof(double), &s_bar[nb]);
+            }
+            // ---- ring window bookkeeping (uniform over the CTA) ---------------------------------
+            const short2 rng = s_range[tb - tb0];
+            const bool wide = (rng.y - rng.x >= RING);
+            if (!wide && rng.y >= rng.x) {
+                const int nlo = min(win_lo, (int)rng.x), nhi = max(win_hi, (int)rng.y);
+                if (nhi - nlo >= RING) { fold(); win_lo = rng.x; win_hi = rng.y; }
+                else { win_lo = nlo; win_hi = nhi; }
+            }
+            mbar_wait(&s_bar[b], phase);
+            ++seq;
+
+            const double2 *bxy = s_txy[b];
+            const double *bz = s_tz[b];
+            const bool diagonal = (tb <= ta_last);
+            const int jbase = tb * TILE;
+            if (tid == 0) {
+                const long long vb = min((int64_t)TILE, p.n - (int64_t)tb * TILE), va = valid_a;
+                // pairs with j > i, i in [a0, a0+va), j in [jbase, jbase+vb)
+                unsigned long long np = 0;
+                if (!diagonal) np = (unsigned long long)(va * vb);
+                else
+                    for (long long i = a0; i < a0 + va; ++i) {
+                        const long long first = max(i + 1, (long long)jbase);
+                        if (jbase + vb > first) np += (unsigned long long)(jbase + vb - first);
+                    }
+                evaluated += np;
+            }
+
+            auto compute = [&](int j0, int (&slot)[U], double (&dzv)[U], int (&sabs)[U]) {
+                double d2[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const double2 pj = bxy[j0 + u];
+                    dzv[u] = __dsub_rn(zi, bz[j0 + u]);
+                    if (ELLIPSE) {
+                        const double dx = __dsub_rn(pj.x, xi), dy = __dsub_rn(pj.y, yi);
+                        const double n0 = __fma_rn(w01, dy, __dmul_rn(w00, dx));
+                        const double n1 = __fma_rn(w11, dy, __dmul_rn(w10, dx));
+                        d2[u] = __dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1));
+                    } else {
+                        const double dx = __dsub_rn(xi, pj.x), dy = __dsub_rn(yi, pj.y);
+                        d2[u] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                    }
+                }
+                int e[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    float r;
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__double2float_rn(d2[u])));
+                    e[u] = min(__float2int_rz(r * lut_scale), LUT_N - 1);
+                }
+                int sl[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) sl[u] = s_lut[e[u]];
+                if (FIX > 0) {
+#pragma unroll
+                    for (int t = 0; t < FIX; ++t) {
+                        long long thr[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) thr[u] = s_upper[sl[u]];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) sl[u] += (__double_as_longlong(d2[u]) > thr[u]) ? 1 : 0;
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        while (__double_as_longlong(d2[u]) > s_upper[sl[u]]) ++sl[u];
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (diagonal && !(jbase + j0 + u > ig)) sl[u] = 0;                 // keep i < j only
+                    sabs[u] = sl[u];
+                    // lags -> ring slot, everything else (d2 <= 0, masked, beyond range) -> trash slot RING
+                    const unsigned t = (unsigned)(sl[u] - 1);
+                    slot[u] = ((t < (unsigned)n_lags) ? (sl[u] & (RING - 1)) : RING) * NT;
+                }
+            };
+            auto rmw = [&](const int (&slot)[U], const double (&dzv)[U]) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    double2 a = acc[slot[u]];
+                    const uint32_t c = cnt[slot[u]];
+                    a.x += dzv[u];
+                    a.y = __fma_rn(dzv[u], dzv[u], a.y);
+                    acc[slot[u]] = a;
+                    cnt[slot[u]] = c + 1u;
+                }
+            };
+            int sA[U], sB[U], aA[U], aB[U];
+            double dA[U], dB[U];
+            if (!wide) {
+                compute(0, sA, dA, aA);
+#pragma unroll 1
+                for (int j0 = 0; j0 < TILE - 2 * U; j0 += 2 * U) {
+                    compute(j0 + U, sB, dB, aB);
+                    rmw(sA, dA);
+                    compute(j0 + 2 * U, sA, dA, aA);
+                    rmw(sB, dB);
+                }
+                compute(TILE - U, sB, dB, aB);
+                rmw(sA, dA);
+                rmw(sB, dB);
+            } else {
+                // this tile pair alone spans >= RING lags: accumulate straight into the overflow part
+                double *ovf = p.partial + (size_t)gridDim.x * (NT / 32) * n_slots * 4;
+#pragma unroll 1
+                for (int j0 = 0; j0 < TILE; j0 += U) {
+                    compute(j0, sA, dA, aA);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (aA[u] >= 1 && aA[u] <= n_lags) {
+                            const double dz = dA[u], zj = zi - dz;
+                            double *dst = ovf + (size_t)aA[u] * 4;
+                            atomicAdd(dst, dz * dz);
+                            atomicAdd(dst + 1, zi * zj);
+                            atomicAdd(dst + 2, zi + zj);
+                            atomicAdd(reinterpret_cast<unsigned long long *>(dst) + 3, 1ull);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (tb_next < 0) break;
+            tb = tb_next;
+        }
+        fold();                                               // my z_i changes with the next item
+        cnt[RING * NT] = 0u;
+        acc[RING * NT] = make_double2(0.0, 0.0);
     }
     if (tid == 0 && evaluated) atomicAdd(p.pairs_evaluated, evaluated);
 }
@@ -367,13 +721,22 @@ static double sq_threshold(double e)
     return t;
 }
 
-template <int NT, bool ELLIPSE>
-static int launch_pair_kernel(const PairParams &p, size_t smem, int grid, cudaStream_t stream)
+template <int NT, bool ELLIPSE, int FIX>
+static int launch_pair_kernel_fix(const PairParams &p, size_t smem, int grid, cudaStream_t stream)
 {
-    PIB_CUDA(cudaFuncSetAttribute(pair_kernel<NT, ELLIPSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pair_kernel<NT, ELLIPSE><<<grid, NT, smem, stream>>>(p);
+    PIB_CUDA(cudaFuncSetAttribute(pair_kernel<NT, ELLIPSE, FIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pair_kernel<NT, ELLIPSE, FIX><<<grid, NT, smem, stream>>>(p);
     PIB_CUDA(cudaGetLastError());
     return PIB_OK;
+}
+
+template <int NT, bool ELLIPSE>
+static int launch_pair_kernel(const PairParams &p, int fix_steps, int grid, cudaStream_t stream)
+{
+    const size_t smem = pair_smem_bytes<NT>(p.n_slots);
+    if (fix_steps <= 2) return launch_pair_kernel_fix<NT, ELLIPSE, 2>(p, smem, grid, stream);
+    if (fix_steps <= 4) return launch_pair_kernel_fix<NT, ELLIPSE, 4>(p, smem, grid, stream);
+    return launch_pair_kernel_fix<NT, ELLIPSE, 0>(p, smem, grid, stream);
 }
 
 int variogram_device(const double *d_xyz, int64_t n, const double *edges, const double *lower, int n_lags,
@@ -396,6 +759,7 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
     PIB_CUDA(cudaMemsetAsync(d_sum_val, 0, out_n * sizeof(double), stream));
     PIB_CUDA(cudaMemsetAsync(d_count, 0, out_n * sizeof(int64_t), stream));
     if (pairs_evaluated) *pairs_evaluated = 0;
+    timing_reset(PIB_T_PAIR);
     if (n < 2) return PIB_OK;
 
     Scratch ws(stream);
@@ -421,9 +785,12 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
     PIB_CUDA(cudaMemsetAsync(d_evaluated, 0, sizeof(unsigned long long), stream));
 
     int nt = 0;
-    if (pair_smem_bytes<128>(n_slots) <= (size_t)MAX_SMEM) nt = 128;
-    else if (pair_smem_bytes<64>(n_slots) <= (size_t)MAX_SMEM) nt = 64;
-    else if (pair_smem_bytes<32>(n_slots) <= (size_t)MAX_SMEM) nt = 32;
+    const size_t dyn_max = (size_t)MAX_SMEM - STATIC_SMEM - 256;
+    if (n_slots <= MAX_SLOTS) {
+        if (pair_smem_bytes<128>(n_slots) <= dyn_max) nt = 128;
+        else if (pair_smem_bytes<64>(n_slots) <= dyn_max) nt = 64;
+        else if (pair_smem_bytes<32>(n_slots) <= dyn_max) nt = 32;
+    }
     const char *force = std::getenv("PIB_FORCE_GENERIC");
     const bool generic = !regular || nt == 0 || (force && force[0] == '1');
 
@@ -448,12 +815,21 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         const double rmax = edges[n_lags - 1];
         const double scale = (LUT_N - 2) / rmax;
         std::vector<uint16_t> lut(LUT_N);
+        int fix_steps = 0;                 // most threshold steps any table cell can need
         for (int e = 0; e < LUT_N; ++e) {
             const double r_lo = std::max(0.0, (e - 0.5) / scale);
             const double t = r_lo * r_lo * (1.0 - 1e-6);
             int s = 0;
             while (s < n_slots - 1 && t > up[s]) ++s;
             lut[e] = (uint16_t)s;
+            int s_hi = s;
+            if (e == LUT_N - 1) s_hi = n_slots - 1;
+            else {
+                const double r_hi = (e + 1.5) / scale;
+                const double t_hi = r_hi * r_hi * (1.0 + 1e-6);
+                while (s_hi < n_slots - 1 && t_hi > up[s_hi]) ++s_hi;
+            }
+            fix_steps = std::max(fix_steps, s_hi - s);
         }
         double *d_upper;
         uint16_t *d_lut;
@@ -463,11 +839,36 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
 
         const int n_tiles = (int)(sp.n_pad / TILE);
         const int n_chunks = (n_tiles + CHUNK - 1) / CHUNK;
-        const int64_t n_items = ((int64_t)n_tiles * (TILE / nt) * n_chunks + shard_count - 1) / shard_count;
+
+        // ring-window kernel or full-histogram kernel?  The ring needs a tile pair to span < 32 lags:
+        // estimate the span from the tile bounding boxes (A sub-tile = 2 tiles, B tile = 1 tile).
+        bool use_ring = false;
+        const char *force_full = std::getenv("PIB_FORCE_FULL");
+        if (n_dirs == 0 && n_lags <= MAX_SLOTS - 2 && !(force_full && force_full[0] == '1')) {
+            std::vector<double4> boxes(n_tiles);
+            PIB_CUDA(cudaMemcpyAsync(boxes.data(), sp.tile_box, sizeof(double4) * n_tiles, cudaMemcpyDeviceToHost, stream));
+            PIB_CUDA(cudaStreamSynchronize(stream));
+            std::vector<double> diag;
+            diag.reserve(n_tiles);
+            for (auto &b : boxes)
+                if (b.z >= b.x) diag.push_back(std::hypot(b.z - b.x, b.w - b.y));
+            double min_width = edges[0];
+            for (int b = 1; b < n_lags; ++b) min_width = std::min(min_width, edges[b] - edges[b - 1]);
+            if (!diag.empty()) {
+                std::sort(diag.begin(), diag.end());
+                const double d90 = diag[(size_t)(0.9 * (diag.size() - 1))];
+                use_ring = (2.5 * d90 / min_width + 2.0) <= 24.0;
+            }
+            const char *force_ring = std::getenv("PIB_FORCE_RING");
+            if (force_ring && force_ring[0] == '1') use_ring = true;
+        }
+        if (use_ring) nt = RING_NT;
+        const int64_t a_tiles = use_ring ? (n_tiles + RING_TILES - 1) / RING_TILES : (int64_t)n_tiles * (TILE / nt);
+        const int64_t n_items = (a_tiles * n_chunks + shard_count - 1) / shard_count;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sm_count(), n_items));
         const int warps = nt / 32;
         double *d_partial;
-        const size_t part_n = (size_t)grid * warps * n_slots * 4;
+        const size_t part_n = ((size_t)grid * warps + 1) * n_slots * 4;       // + 1: overflow part of the ring kernel
         PIB_TRY(ws.alloc(&d_partial, part_n));
 
         PairParams p;
@@ -478,20 +879,37 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         for (int t = 0; t < out_dirs; ++t) {
             PIB_CUDA(cudaMemsetAsync(d_partial, 0, part_n * sizeof(double), stream));
             int rc;
+            timing_begin(PIB_T_PAIR, stream);
             if (n_dirs > 0) {
                 p.w00 = W[4 * t]; p.w01 = W[4 * t + 1]; p.w10 = W[4 * t + 2]; p.w11 = W[4 * t + 3];
-                rc = nt == 128 ? launch_pair_kernel<128, true>(p, pair_smem_bytes<128>(n_slots), grid, stream)
-                   : nt == 64 ? launch_pair_kernel<64, true>(p, pair_smem_bytes<64>(n_slots), grid, stream)
-                              : launch_pair_kernel<32, true>(p, pair_smem_bytes<32>(n_slots), grid, stream);
+                rc = nt == 128 ? launch_pair_kernel<128, true>(p, fix_steps, grid, stream)
+                   : nt == 64 ? launch_pair_kernel<64, true>(p, fix_steps, grid, stream)
+                              : launch_pair_kernel<32, true>(p, fix_steps, grid, stream);
+            } else if (use_ring) {
+                p.w00 = p.w01 = p.w10 = p.w11 = 0;
+                const size_t smem = (size_t)(RING + 1) * RING_NT * (sizeof(double2) + sizeof(uint32_t));
+                if (fix_steps <= 2) {
+                    PIB_CUDA(cudaFuncSetAttribute(pair_ring_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    pair_ring_kernel<false, 2><<<grid, RING_NT, smem, stream>>>(p);
+                } else if (fix_steps <= 4) {
+                    PIB_CUDA(cudaFuncSetAttribute(pair_ring_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    pair_ring_kernel<false, 4><<<grid, RING_NT, smem, stream>>>(p);
+                } else {
+                    PIB_CUDA(cudaFuncSetAttribute(pair_ring_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    pair_ring_kernel<false, 0><<<grid, RING_NT, smem, stream>>>(p);
+                }
+                rc = cudaGetLastError() == cudaSuccess ? PIB_OK : PIB_ERR_CUDA;
+                if (rc != PIB_OK) set_error("pair_ring_kernel launch failed");
             } else {
                 p.w00 = p.w01 = p.w10 = p.w11 = 0;
-                rc = nt == 128 ? launch_pair_kernel<128, false>(p, pair_smem_bytes<128>(n_slots), grid, stream)
-                   : nt == 64 ? launch_pair_kernel<64, false>(p, pair_smem_bytes<64>(n_slots), grid, stream)
-                              : launch_pair_kernel<32, false>(p, pair_smem_bytes<32>(n_slots), grid, stream);
+                rc = nt == 128 ? launch_pair_kernel<128, false>(p, fix_steps, grid, stream)
+                   : nt == 64 ? launch_pair_kernel<64, false>(p, fix_steps, grid, stream)
+                              : launch_pair_kernel<32, false>(p, fix_steps, grid, stream);
             }
+            timing_end(PIB_T_PAIR, stream);
             PIB_TRY(rc);
             reduce_partials_kernel<<<(n_lags + 127) / 128, 128, 0, stream>>>(
-                d_partial, grid * warps, n_slots, n_lags, d_sum_sq + (size_t)t * n_lags, d_sum_prod + (size_t)t * n_lags,
+                d_partial, grid * warps + 1, n_slots, n_lags, d_sum_sq + (size_t)t * n_lags, d_sum_prod + (size_t)t * n_lags,
                 d_sum_val + (size_t)t * n_lags, d_count + (size_t)t * n_lags);
             PIB_CUDA(cudaGetLastError());
         }

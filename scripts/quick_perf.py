@@ -10,7 +10,9 @@ from pyinterpolate_b200 import _lib
 from pyinterpolate_b200.synthetic import dem_like_field, uniform_locations
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+import os
 print("fp64 peak (DFMA probe):", _lib.fp64_peak_tflops(), "TFLOP/s")
+only = os.environ.get("QP_ONLY", "")
 pts = dem_like_field(n, seed=2)
 lags = np.arange(500.0, 40500.0, 500.0)
 d = torch.from_numpy(pts).cuda()
@@ -19,7 +21,8 @@ for rep in range(3):
     r = _lib.variogram_device(d, lags, want_pairs=True)
     torch.cuda.synchronize(); dt = time.time() - t0
     ev = r["pairs_evaluated"]
-    print(f"variogram n={n}: {dt*1e3:.1f} ms  evaluated={ev:.3e} pairs -> {ev/dt:.3e} pairs/s evaluated, "
+    kms, _ = _lib.last_kernel_ms(_lib.KERNEL_PAIR)
+    print(f"variogram n={n}: {dt*1e3:.1f} ms (pair kernel {kms:.1f} ms) evaluated={ev:.3e} pairs -> {ev/dt:.3e} pairs/s evaluated, "
           f"{n*(n-1)/2/dt:.3e} equivalent pairs/s, {13*ev/dt/1e12:.2f} TFLOP/s algorithmic")
 W = np.array([[1, 0, 0, 2.23606797749979]])
 torch.cuda.synchronize(); t0 = time.time()
@@ -27,6 +30,8 @@ r = _lib.variogram_device(d[: n // 5].contiguous(), lags, W=W, want_pairs=True)
 torch.cuda.synchronize(); dt = time.time() - t0
 print(f"ellipse 1 dir n={n//5}: {dt*1e3:.1f} ms evaluated={r['pairs_evaluated']:.3e}")
 
+if only == "variogram":
+    sys.exit(0)
 known = d
 for k, m in ((32, 1_000_000), (64, 1_000_000)):
     unk = torch.from_numpy(uniform_locations(m, seed=5)).cuda()

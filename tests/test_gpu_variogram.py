@@ -161,6 +161,39 @@ def test_generic_kernel_matches_tiled_kernel(pib, monkeypatch):
         np.testing.assert_allclose(a["sum_sq"], b["sum_sq"], rtol=1e-12)
 
 
+@pytest.mark.parametrize("n,step,maxr", [(30000, 2000.0, 40500.0), (5000, 250.0, 30000.0), (1000, 500.0, 40500.0)])
+def test_ring_kernel_vs_oracle(pib, oracle, monkeypatch, n, step, maxr):
+    """The ring-window kernel (the 1M-point fast path) forced onto sizes the oracle can check:
+    coarse lags (ring slots only), fine lags (tile pairs wider than the ring -> overflow path)."""
+    from pyinterpolate_b200 import _lib
+    pts = dem_like_field(n, seed=31)
+    lags = np.arange(step, maxr, step)
+    monkeypatch.setenv("PIB_FORCE_RING", "1")
+    got = _lib.variogram_host(pts, lags)
+    monkeypatch.delenv("PIB_FORCE_RING")
+    want = oracle.variogram_sums(pts, lags)
+    np.testing.assert_array_equal(got["count"], want["count"])
+    np.testing.assert_allclose(got["sum_sq"], want["sum_sq"], rtol=RTOL)
+    np.testing.assert_allclose(got["sum_prod"], want["sum_prod"], rtol=RTOL)
+    np.testing.assert_allclose(got["sum_val"], want["sum_val"], rtol=RTOL)
+    assert got["pairs_evaluated"] <= n * (n - 1) // 2
+
+
+def test_ring_and_full_kernels_agree_300k(pib, monkeypatch):
+    from pyinterpolate_b200 import _lib
+    pts = dem_like_field(300_000, seed=33)
+    lags = np.arange(500.0, 40500.0, 500.0)
+    monkeypatch.setenv("PIB_FORCE_RING", "1")
+    ring = _lib.variogram_host(pts, lags)
+    monkeypatch.delenv("PIB_FORCE_RING")
+    monkeypatch.setenv("PIB_FORCE_FULL", "1")
+    full = _lib.variogram_host(pts, lags)
+    monkeypatch.delenv("PIB_FORCE_FULL")
+    np.testing.assert_array_equal(ring["count"], full["count"])
+    for key in ("sum_sq", "sum_prod", "sum_val"):
+        np.testing.assert_allclose(ring[key], full[key], rtol=1e-12)
+
+
 def test_edge_cases(pib):
     from pyinterpolate_b200 import _lib
     lags = np.array([1.0, 2.0, 3.0])
