@@ -9,14 +9,30 @@ namespace pib {
 static thread_local std::string g_error;
 void set_error(const std::string &msg) { g_error = msg; }
 
+// keep the stream-ordered pool's memory across synchronisations (the default trims it to zero at
+// every sync, which turns each call's scratch allocation into a driver allocation)
+void init_device_pool()
+{
+    static bool done[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[dev] = true;
+}
+
 int sm_count()
 {
     static int cached = 0;
     if (!cached) {
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) {
             cached = sms;
+        }
         else
             return 148;
     }

@@ -40,11 +40,13 @@ void set_error(const std::string &msg);
 
 // Stream-ordered scratch allocation (cudaMallocAsync pool); freed in the destructor on the same
 // stream, so a call never synchronises just to release its workspace.
+void init_device_pool();
+
 struct Scratch {
     cudaStream_t stream;
     void *ptrs[128];
     int n = 0;
-    explicit Scratch(cudaStream_t s) : stream(s) {}
+    explicit Scratch(cudaStream_t s) : stream(s) { init_device_pool(); }
     ~Scratch() {
         for (int i = 0; i < n; ++i) cudaFreeAsync(ptrs[i], stream);
     }

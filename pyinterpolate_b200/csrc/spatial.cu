@@ -67,26 +67,31 @@ static int bounding_box(const double *d_pts, int64_t n, int stride, Scratch &ws,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Morton order
+// Hilbert order (16 bits per axis).  Unlike a Morton curve the Hilbert curve never jumps: any run of
+// consecutive points is spatially compact, so every 128-point tile has a tight bounding box.
 // ---------------------------------------------------------------------------------------------
-static __device__ __forceinline__ uint32_t spread16(uint32_t v)
+static __device__ __forceinline__ uint32_t hilbert16(uint32_t x, uint32_t y)
 {
-    v &= 0xffffu;
-    v = (v | (v << 8)) & 0x00ff00ffu;
-    v = (v | (v << 4)) & 0x0f0f0f0fu;
-    v = (v | (v << 2)) & 0x33333333u;
-    v = (v | (v << 1)) & 0x55555555u;
-    return v;
+    uint32_t d = 0;
+    for (uint32_t s = 32768u; s > 0; s >>= 1) {
+        const uint32_t rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
+        d += s * s * ((3u * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) { x = 65535u - x; y = 65535u - y; }
+            const uint32_t t = x; x = y; y = t;
+        }
+    }
+    return d;
 }
 
-__global__ void morton_key_kernel(const double *__restrict__ xyz, int64_t n, double x0, double y0,
+__global__ void curve_key_kernel(const double *__restrict__ xyz, int64_t n, double x0, double y0,
                                   double scale, uint32_t *__restrict__ keys, int32_t *__restrict__ vals)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int ix = clampi((int)((xyz[3 * i] - x0) * scale), 0, 65535);
     const int iy = clampi((int)((xyz[3 * i + 1] - y0) * scale), 0, 65535);
-    keys[i] = spread16((uint32_t)ix) | (spread16((uint32_t)iy) << 1);
+    keys[i] = hilbert16((uint32_t)ix, (uint32_t)iy);
     vals[i] = (int32_t)i;
 }
 
@@ -161,7 +166,7 @@ int build_sorted_points(const double *d_xyz, int64_t n, int tile, int pad_to, Sc
     PIB_TRY(ws.alloc(&keys, n)); PIB_TRY(ws.alloc(&keys_s, n));
     PIB_TRY(ws.alloc(&vals, n)); PIB_TRY(ws.alloc(&vals_s, n));
     const int blocks = (int)((n + 255) / 256);
-    morton_key_kernel<<<blocks, 256, 0, stream>>>(d_xyz, n, box[0], box[1], scale, keys, vals);
+    curve_key_kernel<<<blocks, 256, 0, stream>>>(d_xyz, n, box[0], box[1], scale, keys, vals);
     PIB_CUDA(cudaGetLastError());
     PIB_TRY(radix_sort_pairs(keys, keys_s, vals, vals_s, n, 32, ws, stream));
 

@@ -542,7 +542,9 @@ __global__ void __launch_bounds__(RING_NT, 1) pair_ring_kernel(const PairParams 
                 evaluated += np;
             }
 
-            auto compute = [&](int j0, int (&slot)[U], double (&dzv)[U], int (&sabs)[U]) {
+            int wlo = 1;                                      // lag slots accepted by the ring: [wlo, wlo + wlen)
+            unsigned wlen = (unsigned)n_lags;
+            auto compute = [&](int j0, int (&slot)[U], double (&dzv)[U]) {
                 double d2[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -585,10 +587,10 @@ __global__ void __launch_bounds__(RING_NT, 1) pair_ring_kernel(const PairParams 
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (diagonal && !(jbase + j0 + u > ig)) sl[u] = 0;                 // keep i < j only
-                    sabs[u] = sl[u];
-                    // lags -> ring slot, everything else (d2 <= 0, masked, beyond range) -> trash slot RING
-                    const unsigned t = (unsigned)(sl[u] - 1);
-                    slot[u] = ((t < (unsigned)n_lags) ? (sl[u] & (RING - 1)) : RING) * NT;
+                    // lag slots of the current window -> ring slot, everything else (d2 <= 0, masked, beyond
+                    // range, outside the window of a wide tile pair) -> trash slot RING
+                    const unsigned t = (unsigned)(sl[u] - wlo);
+                    slot[u] = ((t < wlen) ? (sl[u] & (RING - 1)) : RING) * NT;
                 }
             };
             auto rmw = [&](const int (&slot)[U], const double (&dzv)[U]) {
@@ -602,38 +604,34 @@ __global__ void __launch_bounds__(RING_NT, 1) pair_ring_kernel(const PairParams 
                     cnt[slot[u]] = c + 1u;
                 }
             };
-            int sA[U], sB[U], aA[U], aB[U];
+            int sA[U], sB[U];
             double dA[U], dB[U];
-            if (!wide) {
-                compute(0, sA, dA, aA);
+            auto sweep = [&]() {                              // all 128 points of the B tile, software pipelined
+                compute(0, sA, dA);
 #pragma unroll 1
                 for (int j0 = 0; j0 < TILE - 2 * U; j0 += 2 * U) {
-                    compute(j0 + U, sB, dB, aB);
+                    compute(j0 + U, sB, dB);
                     rmw(sA, dA);
-                    compute(j0 + 2 * U, sA, dA, aA);
+                    compute(j0 + 2 * U, sA, dA);
                     rmw(sB, dB);
                 }
-                compute(TILE - U, sB, dB, aB);
+                compute(TILE - U, sB, dB);
                 rmw(sA, dA);
                 rmw(sB, dB);
+            };
+            if (!wide) {
+                sweep();
             } else {
-                // this tile pair alone spans >= RING lags: accumulate straight into the overflow part
-                double *ovf = p.partial + (size_t)gridDim.x * (NT / 32) * n_slots * 4;
-#pragma unroll 1
-                for (int j0 = 0; j0 < TILE; j0 += U) {
-                    compute(j0, sA, dA, aA);
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (aA[u] >= 1 && aA[u] <= n_lags) {
-                            const double dz = dA[u], zj = zi - dz;
-                            double *dst = ovf + (size_t)aA[u] * 4;
-                            atomicAdd(dst, dz * dz);
-                            atomicAdd(dst + 1, zi * zj);
-                            atomicAdd(dst + 2, zi + zj);
-                            atomicAdd(reinterpret_cast<unsigned long long *>(dst) + 3, 1ull);
-                        }
-                    }
+                // this tile pair alone spans >= RING lags: sweep it once per window of RING lags, folding in
+                // between (no atomics, so the result stays deterministic)
+                fold();
+                for (int w0 = rng.x; w0 <= rng.y; w0 += RING) {
+                    wlo = w0; wlen = (unsigned)(min(w0 + RING - 1, (int)rng.y) - w0 + 1);
+                    sweep();
+                    win_lo = w0; win_hi = w0 + (int)wlen - 1;
+                    fold();
                 }
+                if (tid == 0) evaluated += 0;                 // counted once above
             }
             __syncthreads();
             if (tb_next < 0) break;
