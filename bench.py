@@ -65,6 +65,7 @@ def cpu_variogram_sample(pts, lags, target_s=12.0):
     triangle of the SAME field; R is sized from a short probe so the sample takes ~target_s."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
+    oracle.set_threads(os.cpu_count() or 1)         # torchrun exports OMP_NUM_THREADS=1
     n = len(pts)
     probe_rows = 64
     t0 = time.perf_counter()

@@ -41,6 +41,7 @@ def lib():
         dp = ctypes.POINTER(ctypes.c_double)
         ip = ctypes.POINTER(ctypes.c_int64)
         L.oracle_num_threads.restype = ctypes.c_int
+        L.oracle_set_threads.argtypes = [ctypes.c_int]
         L.oracle_variogram_omni_rows.argtypes = [dp, ctypes.c_int64, dp, ctypes.c_int,
                                                  ctypes.c_int64, ctypes.c_int64, dp, dp, dp, ip]
         L.oracle_variogram_ellipse_rows.argtypes = [dp, ctypes.c_int64, dp, dp, ctypes.c_int,
@@ -59,6 +60,11 @@ def lib():
 
 def num_threads():
     return lib().oracle_num_threads()
+
+
+def set_threads(n):
+    """Use n OpenMP threads (torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants every core)."""
+    lib().oracle_set_threads(int(n))
 
 
 def _dp(a):

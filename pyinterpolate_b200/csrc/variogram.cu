@@ -46,8 +46,10 @@ struct PairParams {
     int n_tiles;
     int n_slots;                 // n_lags + 2: slot 0 = "d2 <= 0 / masked", slot s = lag s-1, last = beyond range
     const double *upper;         // [n_slots] slot upper thresholds on d2: U[0] = 0, U[s] = T(edge[s-1]), U[last] = +inf
-    const uint16_t *lut;         // [LUT_N]
+    const uint16_t *lut;         // [LUT_N] full-histogram kernel: float distance estimate -> first candidate slot
     float lut_scale;
+    const uint16_t *lut2;        // [lut2_n] ring kernel: (hi word of d2 - lut2_base) >> 13 -> first candidate slot
+    int lut2_base, lut2_n;
     double max_d2;               // T(edges[n_lags-1])
     double w00, w01, w10, w11;   // whitening matrix (ellipse)
     int shard_index, shard_count;
@@ -342,29 +344,40 @@ __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
 // Ring-window kernel: the fast path when tiles are small against the lag width.
 //
 // The full-histogram kernel above is limited to 128 threads per SM (one private histogram of
-// n_lags + 2 slots per thread fills the shared memory), i.e. one warp per scheduler, and the
-// per-pair dependency chain (distance -> slot -> read-modify-write) is then exposed latency.
-// A tile pair only touches the few lags between the smallest and largest distance of its two
-// bounding boxes, so here a thread keeps a RING of 32 slots (slot = (lag & 31)) plus one trash slot:
-// 660 B per thread -> 256 threads per CTA (two warps per scheduler).  The CTA tracks the range of
-// lags touched since the last fold; before a tile pair that would stretch the range to 32 or more
-// lags, every warp folds its rings into the per-warp global partials (lane l sums ring slot l over
-// the 32 threads of the warp).  A tile pair that alone spans >= 32 lags takes a slow path
-// (global atomics); the host only picks this kernel when that is rare.
+// n_lags + 2 slots per thread fills the shared memory), and it pays one 40-byte shared-memory
+// read-modify-write per pair: ncu shows the shared-memory pipe, not the FP64 pipe, as its limit.
+// This kernel removes both limits:
+//  * RING.  A tile pair only touches the few lags between the smallest and largest distance of its
+//    two bounding boxes, so a thread keeps a ring of RING slots (slot = lag & (RING-1)) plus two trash
+//    slots instead of a full histogram: 680 B per thread -> 256 threads per CTA.  The CTA tracks the
+//    range of lags touched since the last fold; before a tile pair that would stretch the range to
+//    RING or more lags, every warp folds its rings into the per-warp global partials (lane l sums
+//    ring slot l over the 32 threads of the warp).  A tile pair that alone spans >= RING lags is swept
+//    once per window of RING lags.  No atomics: the result is deterministic.
+//  * TWO-LAG REGISTERS.  Points are Hilbert sorted, so 8 consecutive points of a B tile are a few
+//    hundred metres apart and their distances to a thread's own point fall into at most two adjacent
+//    lags (lo, lo + 1) almost always.  A thread accumulates each group of 8 pairs in registers
+//    (sum over all 8, sum over those in lo + 1) and touches shared memory twice per GROUP instead of
+//    once per PAIR.  The rare pair outside {lo, lo + 1} takes a per-pair read-modify-write under a
+//    warp vote.
+//  * The first slot comes from a table indexed by the exponent and top 7 mantissa bits of the fp64
+//    squared distance (integer ops only, no conversion / sqrt on the quarter-rate XU pipe); one or two
+//    64-bit integer compares against the exact thresholds finish the assignment.
 // ---------------------------------------------------------------------------------------------
-constexpr int RING = 32;
-constexpr int RING_NT = 256;
-constexpr int RING_TILES = RING_NT / TILE;     // A sub-tile = 2 tiles
+constexpr int LUT2_MAX = 4096;
+constexpr int LUT2_SHIFT = 13;                 // keep 7 of the 20 mantissa bits of the high word: 128 cells per octave
 
-template <bool ELLIPSE, int FIX>
-__global__ void __launch_bounds__(RING_NT, 1) pair_ring_kernel(const PairParams p)
+template <int RING, int NT, int FIX>
+__global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
 {
-    constexpr int NT = RING_NT;
     constexpr int U = 8;
+    constexpr int A_TILES = NT / TILE;             // tiles per A sub-tile
+    constexpr int TRASH_LO = RING, TRASH_HI = RING + 1;
+    static_assert(NT % TILE == 0 && RING <= 32, "A sub-tile is whole tiles; one lane folds one ring slot");
     __shared__ __align__(16) double2 s_txy[2][TILE];
     __shared__ __align__(16) double s_tz[2][TILE];
     __shared__ long long s_upper[MAX_SLOTS];
-    __shared__ uint16_t s_lut[LUT_N];
+    __shared__ uint16_t s_lut[LUT2_MAX];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint64_t s_live;
     __shared__ short2 s_range[CHUNK];              // lag-slot range [lo, hi] of each B tile of the chunk
@@ -373,17 +386,17 @@ __global__ void __launch_bounds__(RING_NT, 1) pair_ring_kernel(const PairParams 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_slots = p.n_slots, n_lags = n_slots - 2;
 
-    double2 *acc_all = reinterpret_cast<double2 *>(smem_raw);                         // [RING + 1][NT]
-    uint32_t *cnt_all = reinterpret_cast<uint32_t *>(smem_raw + (size_t)(RING + 1) * NT * sizeof(double2));
+    double2 *acc_all = reinterpret_cast<double2 *>(smem_raw);                         // [RING + 2][NT]
+    uint32_t *cnt_all = reinterpret_cast<uint32_t *>(smem_raw + (size_t)(RING + 2) * NT * sizeof(double2));
     double2 *acc = acc_all + tid;
     uint32_t *cnt = cnt_all + tid;
 
-    for (int s = 0; s <= RING; ++s) {
+    for (int s = 0; s < RING + 2; ++s) {
         acc[s * NT] = make_double2(0.0, 0.0);
         cnt[s * NT] = 0u;
     }
     for (int s = tid; s < n_slots; s += NT) s_upper[s] = __double_as_longlong(p.upper[s]);
-    for (int s = tid; s < LUT_N; s += NT) s_lut[s] = p.lut[s];
+    for (int s = tid; s < p.lut2_n; s += NT) s_lut[s] = p.lut2[s];
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -392,20 +405,19 @@ __global__ void __launch_bounds__(RING_NT, 1) pair_ring_kernel(const PairParams 
     __syncthreads();
 
     const int n_tiles = p.n_tiles;
-    const int n_atiles = (n_tiles + RING_TILES - 1) / RING_TILES;
+    const int n_atiles = (n_tiles + A_TILES - 1) / A_TILES;
     const int n_chunks = (n_tiles + CHUNK - 1) / CHUNK;
     const int64_t n_items = (int64_t)n_atiles * n_chunks;
     uint32_t seq = 0;
     unsigned long long evaluated = 0;
     double *my_partial = p.partial + ((size_t)blockIdx.x * (NT / 32) + warp) * n_slots * 4;
-    const float lut_scale = p.lut_scale;
-    const double w00 = p.w00, w01 = p.w01, w10 = p.w10, w11 = p.w11;
+    const int base_hi = p.lut2_base, lut_last = p.lut2_n - 1;
 
     for (int64_t item = ((int64_t)blockIdx.x) * p.shard_count + p.shard_index; item < n_items;
          item += (int64_t)gridDim.x * p.shard_count) {
         const int64_t a0 = (item / n_chunks) * NT;            // first point of my A sub-tile
-        const int ta = (int)(a0 / TILE);                      // first of its RING_TILES tiles
-        const int ta_last = min(ta + RING_TILES, n_tiles) - 1;
+        const int ta = (int)(a0 / TILE);                      // first of its tiles
+        const int ta_last = min(ta + A_TILES, n_tiles) - 1;
         const int tb0 = (int)(item % n_chunks) * CHUNK;
         const int tb1 = min(tb0 + CHUNK, n_tiles);
         const int valid_a = (int)max((int64_t)0, min((int64_t)NT, p.n - a0));
@@ -428,24 +440,21 @@ __global__ void __launch_bounds__(RING_NT, 1) pair_ring_kernel(const PairParams 
                 if (tb >= tb_first && tb < tb1) {
                     const double4 bbox = p.tile_box[tb];
                     const double dmin = box_min_d2(abox, bbox);
-                    live = dmin * (1.0 - 1e-12) <= p.max_d2;
+                    live = dmin <= p.max_d2;
                     if (live) {
                         // every pair of the two boxes has dmin <= d2 <= dmax in the kernel's own arithmetic
+                        // (fp subtraction, multiplication and addition are monotone)
                         const double dxm = fmax(abox.z - bbox.x, bbox.z - abox.x);
                         const double dym = fmax(abox.w - bbox.y, bbox.w - abox.y);
                         const double dmax = __dadd_rn(__dmul_rn(dxm, dxm), __dmul_rn(dym, dym));
-                        int lo = 0, hi = 0;
-                        {   // first slot whose threshold is >= value (binary search over ascending thresholds)
-                            int a = 0, b = n_slots - 1;
-                            const long long v = __double_as_longlong(dmin);
-                            while (a < b) { const int mid = (a + b) >> 1; if (v <= s_upper[mid]) b = mid; else a = mid + 1; }
-                            lo = a;
-                            a = 0; b = n_slots - 1;
-                            const long long w = __double_as_longlong(dmax);
-                            while (a < b) { const int mid = (a + b) >> 1; if (w <= s_upper[mid]) b = mid; else a = mid + 1; }
-                            hi = a;
-                        }
-                        lo = max(lo, 1); hi = min(hi, n_lags);
+                        int a = 0, b = n_slots - 1;           // first slot whose threshold is >= dmin
+                        const long long v = __double_as_longlong(dmin);
+                        while (a < b) { const int mid = (a + b) >> 1; if (v <= s_upper[mid]) b = mid; else a = mid + 1; }
+                        const int lo = max(a, 1);
+                        a = 0; b = n_slots - 1;
+                        const long long w = __double_as_longlong(dmax);
+                        while (a < b) { const int mid = (a + b) >> 1; if (w <= s_upper[mid]) b = mid; else a = mid + 1; }
+                        const int hi = min(a, n_lags);
                         s_range[h * 32 + lane] = make_short2((short)lo, (short)hi);
                     }
                 }
@@ -466,8 +475,8 @@ __global__ void __launch_bounds__(RING_NT, 1) pair_ring_kernel(const PairParams 
         // fold the rings of my warp into its global partials (lane l owns ring slot l)
         auto fold = [&]() {
             __syncwarp();
-            if (win_hi >= win_lo) {
-                const int abs_slot = win_lo + ((lane - win_lo) & (RING - 1));       // the slot of the window that maps to ring `lane`
+            if (win_hi >= win_lo && lane < RING) {
+                const int abs_slot = win_lo + ((lane - win_lo) & (RING - 1));       // the window's slot that maps to ring `lane`
                 double v_sq = 0.0, v_prod = 0.0, v_val = 0.0;
                 unsigned long long v_cnt = 0;
                 const int row = lane * NT + warp * 32;
@@ -531,8 +540,7 @@ __global__ void __launch_bounds__(RING_NT, 1) pair_ring_kernel(const PairParams 
             const int jbase = tb * TILE;
             if (tid == 0) {
                 const long long vb = min((int64_t)TILE, p.n - (int64_t)tb * TILE), va = valid_a;
-                // pairs with j > i, i in [a0, a0+va), j in [jbase, jbase+vb)
-                unsigned long long np = 0;
+                unsigned long long np = 0;                    // pairs with j > i, i in [a0, a0+va), j in [jbase, jbase+vb)
                 if (!diagonal) np = (unsigned long long)(va * vb);
                 else
                     for (long long i = a0; i < a0 + va; ++i) {
@@ -544,32 +552,26 @@ __global__ void __launch_bounds__(RING_NT, 1) pair_ring_kernel(const PairParams 
 
             int wlo = 1;                                      // lag slots accepted by the ring: [wlo, wlo + wlen)
             unsigned wlen = (unsigned)n_lags;
-            auto compute = [&](int j0, int (&slot)[U], double (&dzv)[U]) {
+            auto ring_of = [&](int s, int trash) -> int {
+                return (((unsigned)(s - wlo) < wlen) ? (s & (RING - 1)) : trash) * NT;
+            };
+            // ---- stage 1: exact lag slot and dz of U consecutive pairs (independent chains) -------
+            auto compute = [&](int j0, int (&sl)[U], double (&dzv)[U]) {
                 double d2[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const double2 pj = bxy[j0 + u];
                     dzv[u] = __dsub_rn(zi, bz[j0 + u]);
-                    if (ELLIPSE) {
-                        const double dx = __dsub_rn(pj.x, xi), dy = __dsub_rn(pj.y, yi);
-                        const double n0 = __fma_rn(w01, dy, __dmul_rn(w00, dx));
-                        const double n1 = __fma_rn(w11, dy, __dmul_rn(w10, dx));
-                        d2[u] = __dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1));
-                    } else {
-                        const double dx = __dsub_rn(xi, pj.x), dy = __dsub_rn(yi, pj.y);
-                        d2[u] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                    }
+                    // scipy cdist euclidean: sqrt(dx*dx + dy*dy), nothing fused (distance/point.py:56)
+                    const double dx = __dsub_rn(xi, pj.x), dy = __dsub_rn(yi, pj.y);
+                    d2[u] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
                 }
-                int e[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    float r;
-                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__double2float_rn(d2[u])));
-                    e[u] = min(__float2int_rz(r * lut_scale), LUT_N - 1);
+                    int idx = (__double2hiint(d2[u]) - base_hi) >> LUT2_SHIFT;
+                    idx = min(max(idx, 0), lut_last);
+                    sl[u] = s_lut[idx];
                 }
-                int sl[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) sl[u] = s_lut[e[u]];
                 if (FIX > 0) {
 #pragma unroll
                     for (int t = 0; t < FIX; ++t) {
@@ -584,25 +586,58 @@ __global__ void __launch_bounds__(RING_NT, 1) pair_ring_kernel(const PairParams 
                     for (int u = 0; u < U; ++u)
                         while (__double_as_longlong(d2[u]) > s_upper[sl[u]]) ++sl[u];
                 }
+                if (diagonal) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (diagonal && !(jbase + j0 + u > ig)) sl[u] = 0;                 // keep i < j only
-                    // lag slots of the current window -> ring slot, everything else (d2 <= 0, masked, beyond
-                    // range, outside the window of a wide tile pair) -> trash slot RING
-                    const unsigned t = (unsigned)(sl[u] - wlo);
-                    slot[u] = ((t < wlen) ? (sl[u] & (RING - 1)) : RING) * NT;
+                    for (int u = 0; u < U; ++u)
+                        if (!(jbase + j0 + u > ig)) sl[u] = 0;                         // keep i < j only
                 }
             };
-            auto rmw = [&](const int (&slot)[U], const double (&dzv)[U]) {
+            // ---- stage 2: accumulate the group in registers, touch the ring twice ----------------
+            auto consume = [&](int (&sl)[U], double (&dzv)[U]) {
+                int lo = sl[0], mx = sl[0];
+#pragma unroll
+                for (int u = 1; u < U; ++u) { lo = min(lo, sl[u]); mx = max(mx, sl[u]); }
+                int n_out = 0;
+                if (__any_sync(0xffffffffu, mx > lo + 1)) {                            // rare: a pair outside {lo, lo+1}
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (sl[u] > lo + 1) {
+                            const int r = ring_of(sl[u], TRASH_HI);
+                            double2 a = acc[r];
+                            a.x += dzv[u];
+                            a.y = __fma_rn(dzv[u], dzv[u], a.y);
+                            acc[r] = a;
+                            cnt[r] += 1u;
+                            dzv[u] = 0.0; sl[u] = lo; ++n_out;
+                        }
+                    }
+                }
+                double dh[U];
+                int ch = 0;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    double2 a = acc[slot[u]];
-                    const uint32_t c = cnt[slot[u]];
-                    a.x += dzv[u];
-                    a.y = __fma_rn(dzv[u], dzv[u], a.y);
-                    acc[slot[u]] = a;
-                    cnt[slot[u]] = c + 1u;
+                    const bool is_hi = (sl[u] != lo);
+                    dh[u] = is_hi ? dzv[u] : 0.0;
+                    ch += is_hi ? 1 : 0;
                 }
+                // all-8 and lo+1-only sums, pairwise trees to keep the dependency chains short
+                const double a1 = ((dzv[0] + dzv[1]) + (dzv[2] + dzv[3])) + ((dzv[4] + dzv[5]) + (dzv[6] + dzv[7]));
+                const double h1 = ((dh[0] + dh[1]) + (dh[2] + dh[3])) + ((dh[4] + dh[5]) + (dh[6] + dh[7]));
+                double a2e = dzv[0] * dzv[0], a2o = dzv[1] * dzv[1], h2e = dh[0] * dh[0], h2o = dh[1] * dh[1];
+#pragma unroll
+                for (int u = 2; u < U; u += 2) {
+                    a2e = __fma_rn(dzv[u], dzv[u], a2e); a2o = __fma_rn(dzv[u + 1], dzv[u + 1], a2o);
+                    h2e = __fma_rn(dh[u], dh[u], h2e);   h2o = __fma_rn(dh[u + 1], dh[u + 1], h2o);
+                }
+                const double a2 = a2e + a2o, h2 = h2e + h2o;
+                const int r_lo = ring_of(lo, TRASH_LO), r_hi = ring_of(lo + 1, TRASH_HI);   // never equal
+                double2 v_lo = acc[r_lo], v_hi = acc[r_hi];
+                const uint32_t c_lo = cnt[r_lo], c_hi = cnt[r_hi];
+                v_lo.x += a1 - h1; v_lo.y += a2 - h2;
+                v_hi.x += h1;      v_hi.y += h2;
+                acc[r_lo] = v_lo; acc[r_hi] = v_hi;
+                cnt[r_lo] = c_lo + (uint32_t)(U - ch - n_out);
+                cnt[r_hi] = c_hi + (uint32_t)ch;
             };
             int sA[U], sB[U];
             double dA[U], dB[U];
@@ -611,13 +646,13 @@ __global__ void __launch_bounds__(RING_NT, 1) pair_ring_kernel(const PairParams 
 #pragma unroll 1
                 for (int j0 = 0; j0 < TILE - 2 * U; j0 += 2 * U) {
                     compute(j0 + U, sB, dB);
-                    rmw(sA, dA);
+                    consume(sA, dA);
                     compute(j0 + 2 * U, sA, dA);
-                    rmw(sB, dB);
+                    consume(sB, dB);
                 }
                 compute(TILE - U, sB, dB);
-                rmw(sA, dA);
-                rmw(sB, dB);
+                consume(sA, dA);
+                consume(sB, dB);
             };
             if (!wide) {
                 sweep();
@@ -631,15 +666,14 @@ __global__ void __launch_bounds__(RING_NT, 1) pair_ring_kernel(const PairParams 
                     win_lo = w0; win_hi = w0 + (int)wlen - 1;
                     fold();
                 }
-                if (tid == 0) evaluated += 0;                 // counted once above
             }
             __syncthreads();
             if (tb_next < 0) break;
             tb = tb_next;
         }
         fold();                                               // my z_i changes with the next item
-        cnt[RING * NT] = 0u;
-        acc[RING * NT] = make_double2(0.0, 0.0);
+        cnt[TRASH_LO * NT] = 0u; cnt[TRASH_HI * NT] = 0u;
+        acc[TRASH_LO * NT] = make_double2(0.0, 0.0); acc[TRASH_HI * NT] = make_double2(0.0, 0.0);
     }
     if (tid == 0 && evaluated) atomicAdd(p.pairs_evaluated, evaluated);
 }
@@ -860,13 +894,42 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             const char *force_ring = std::getenv("PIB_FORCE_RING");
             if (force_ring && force_ring[0] == '1') use_ring = true;
         }
-        if (use_ring) nt = RING_NT;
-        const int64_t a_tiles = use_ring ? (n_tiles + RING_TILES - 1) / RING_TILES : (int64_t)n_tiles * (TILE / nt);
+        constexpr int RING = 32, RING_NT = 256;
+        // ring kernel's slot table: indexed by (high word of d2 - base) >> 13, 128 cells per octave
+        std::vector<uint16_t> lut2;
+        int lut2_base = 0, fix2 = 0;
+        uint16_t *d_lut2 = nullptr;
+        if (use_ring) {
+            auto hiword = [](double v) { long long b; std::memcpy(&b, &v, 8); return (int)(b >> 32); };
+            auto from_hi = [](int hi) { long long b = (long long)hi << 32; double v; std::memcpy(&v, &b, 8); return v; };
+            const int cell = 1 << LUT2_SHIFT;
+            const int hi_max = hiword(up[n_slots - 2]);
+            lut2_base = hiword(up[1] / 4.0) & ~(cell - 1);
+            int n_cells = ((hi_max - lut2_base) >> LUT2_SHIFT) + 3;
+            if (n_cells > LUT2_MAX) {                          // very wide lag range: coarser start, more fix-up steps
+                n_cells = LUT2_MAX;
+                lut2_base = (hi_max & ~(cell - 1)) - (LUT2_MAX - 3) * cell;
+            }
+            lut2.resize(n_cells);
+            auto slot_of = [&](double v) { int q = 0; while (q < n_slots - 1 && v > up[q]) ++q; return q; };
+            for (int e = 0; e < n_cells; ++e) {
+                const double v_lo = e == 0 ? 0.0 : from_hi(lut2_base + e * cell);
+                const int q_lo = slot_of(v_lo);
+                const int q_hi = e == n_cells - 1 ? n_slots - 1
+                                                  : slot_of(std::nextafter(from_hi(lut2_base + (e + 1) * cell), 0.0));
+                lut2[e] = (uint16_t)q_lo;
+                fix2 = std::max(fix2, q_hi - q_lo);
+            }
+            PIB_TRY(ws.alloc(&d_lut2, lut2.size()));
+            PIB_CUDA(cudaMemcpyAsync(d_lut2, lut2.data(), lut2.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
+            nt = RING_NT;
+        }
+        const int64_t a_tiles = use_ring ? (n_tiles + RING_NT / TILE - 1) / (RING_NT / TILE) : (int64_t)n_tiles * (TILE / nt);
         const int64_t n_items = (a_tiles * n_chunks + shard_count - 1) / shard_count;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sm_count(), n_items));
         const int warps = nt / 32;
         double *d_partial;
-        const size_t part_n = ((size_t)grid * warps + 1) * n_slots * 4;       // + 1: overflow part of the ring kernel
+        const size_t part_n = ((size_t)grid * warps + 1) * n_slots * 4;
         PIB_TRY(ws.alloc(&d_partial, part_n));
 
         PairParams p;
@@ -874,6 +937,7 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         p.upper = d_upper; p.lut = d_lut; p.lut_scale = (float)scale; p.max_d2 = up_lag[n_lags - 1];
         p.shard_index = shard_index; p.shard_count = shard_count; p.partial = d_partial;
         p.pairs_evaluated = d_evaluated;
+        p.lut2 = d_lut2; p.lut2_base = lut2_base; p.lut2_n = (int)lut2.size();
         for (int t = 0; t < out_dirs; ++t) {
             PIB_CUDA(cudaMemsetAsync(d_partial, 0, part_n * sizeof(double), stream));
             int rc;
@@ -885,16 +949,16 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
                               : launch_pair_kernel<32, true>(p, fix_steps, grid, stream);
             } else if (use_ring) {
                 p.w00 = p.w01 = p.w10 = p.w11 = 0;
-                const size_t smem = (size_t)(RING + 1) * RING_NT * (sizeof(double2) + sizeof(uint32_t));
-                if (fix_steps <= 2) {
-                    PIB_CUDA(cudaFuncSetAttribute(pair_ring_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    pair_ring_kernel<false, 2><<<grid, RING_NT, smem, stream>>>(p);
-                } else if (fix_steps <= 4) {
-                    PIB_CUDA(cudaFuncSetAttribute(pair_ring_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    pair_ring_kernel<false, 4><<<grid, RING_NT, smem, stream>>>(p);
+                const size_t smem = (size_t)(RING + 2) * RING_NT * (sizeof(double2) + sizeof(uint32_t));
+                if (fix2 <= 1) {
+                    PIB_CUDA(cudaFuncSetAttribute(pair_ring_kernel<RING, RING_NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    pair_ring_kernel<RING, RING_NT, 1><<<grid, RING_NT, smem, stream>>>(p);
+                } else if (fix2 <= 2) {
+                    PIB_CUDA(cudaFuncSetAttribute(pair_ring_kernel<RING, RING_NT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    pair_ring_kernel<RING, RING_NT, 2><<<grid, RING_NT, smem, stream>>>(p);
                 } else {
-                    PIB_CUDA(cudaFuncSetAttribute(pair_ring_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    pair_ring_kernel<false, 0><<<grid, RING_NT, smem, stream>>>(p);
+                    PIB_CUDA(cudaFuncSetAttribute(pair_ring_kernel<RING, RING_NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    pair_ring_kernel<RING, RING_NT, 0><<<grid, RING_NT, smem, stream>>>(p);
                 }
                 rc = cudaGetLastError() == cudaSuccess ? PIB_OK : PIB_ERR_CUDA;
                 if (rc != PIB_OK) set_error("pair_ring_kernel launch failed");
