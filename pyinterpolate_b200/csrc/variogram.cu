@@ -874,7 +874,7 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
 
         // ring-window kernel or full-histogram kernel?  The ring needs a tile pair to span < 32 lags:
         // estimate the span from the tile bounding boxes (A sub-tile = 2 tiles, B tile = 1 tile).
-        bool use_ring = false;
+        bool use_ring = false, ring16_ok = false;
         const char *force_full = std::getenv("PIB_FORCE_FULL");
         if (n_dirs == 0 && n_lags <= MAX_SLOTS - 2 && !(force_full && force_full[0] == '1')) {
             std::vector<double4> boxes(n_tiles);
@@ -890,11 +890,18 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
                 std::sort(diag.begin(), diag.end());
                 const double d90 = diag[(size_t)(0.9 * (diag.size() - 1))];
                 use_ring = (2.5 * d90 / min_width + 2.0) <= 24.0;
+                ring16_ok = (3.0 * d90 / min_width + 2.0) <= 15.0;       // A sub-tile = 4 tiles (~2x the diagonal)
             }
             const char *force_ring = std::getenv("PIB_FORCE_RING");
             if (force_ring && force_ring[0] == '1') use_ring = true;
+            if (force_ring && force_ring[0] == '1' && force_ring[1] == '6') ring16_ok = true;    // "16"
+            const char *ring_env = std::getenv("PIB_RING");
+            if (ring_env) ring16_ok = (ring_env[0] == '1' && ring_env[1] == '6');
         }
-        constexpr int RING = 32, RING_NT = 256;
+        // two instantiations: 32-slot ring / 256 threads, or 16-slot ring / 512 threads (more warps to hide
+        // latency) when tile pairs are narrow enough
+        int ring = 32, ring_nt = 256;
+        if (use_ring && ring16_ok) { ring = 16; ring_nt = 512; }
         // ring kernel's slot table: indexed by (high word of d2 - base) >> 13, 128 cells per octave
         std::vector<uint16_t> lut2;
         int lut2_base = 0, fix2 = 0;
@@ -922,9 +929,9 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             }
             PIB_TRY(ws.alloc(&d_lut2, lut2.size()));
             PIB_CUDA(cudaMemcpyAsync(d_lut2, lut2.data(), lut2.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
-            nt = RING_NT;
+            nt = ring_nt;
         }
-        const int64_t a_tiles = use_ring ? (n_tiles + RING_NT / TILE - 1) / (RING_NT / TILE) : (int64_t)n_tiles * (TILE / nt);
+        const int64_t a_tiles = use_ring ? (n_tiles + ring_nt / TILE - 1) / (ring_nt / TILE) : (int64_t)n_tiles * (TILE / nt);
         const int64_t n_items = (a_tiles * n_chunks + shard_count - 1) / shard_count;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sm_count(), n_items));
         const int warps = nt / 32;
@@ -949,17 +956,22 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
                               : launch_pair_kernel<32, true>(p, fix_steps, grid, stream);
             } else if (use_ring) {
                 p.w00 = p.w01 = p.w10 = p.w11 = 0;
-                const size_t smem = (size_t)(RING + 2) * RING_NT * (sizeof(double2) + sizeof(uint32_t));
-                if (fix2 <= 1) {
-                    PIB_CUDA(cudaFuncSetAttribute(pair_ring_kernel<RING, RING_NT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    pair_ring_kernel<RING, RING_NT, 1><<<grid, RING_NT, smem, stream>>>(p);
-                } else if (fix2 <= 2) {
-                    PIB_CUDA(cudaFuncSetAttribute(pair_ring_kernel<RING, RING_NT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    pair_ring_kernel<RING, RING_NT, 2><<<grid, RING_NT, smem, stream>>>(p);
+                const size_t smem = (size_t)(ring + 2) * ring_nt * (sizeof(double2) + sizeof(uint32_t));
+#define PIB_LAUNCH_RING(R, T, F)                                                                                     \
+    do {                                                                                                             \
+        PIB_CUDA(cudaFuncSetAttribute(pair_ring_kernel<R, T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        pair_ring_kernel<R, T, F><<<grid, T, smem, stream>>>(p);                                                    \
+    } while (0)
+                if (ring == 16) {
+                    if (fix2 <= 1) PIB_LAUNCH_RING(16, 512, 1);
+                    else if (fix2 <= 2) PIB_LAUNCH_RING(16, 512, 2);
+                    else PIB_LAUNCH_RING(16, 512, 0);
                 } else {
-                    PIB_CUDA(cudaFuncSetAttribute(pair_ring_kernel<RING, RING_NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    pair_ring_kernel<RING, RING_NT, 0><<<grid, RING_NT, smem, stream>>>(p);
+                    if (fix2 <= 1) PIB_LAUNCH_RING(32, 256, 1);
+                    else if (fix2 <= 2) PIB_LAUNCH_RING(32, 256, 2);
+                    else PIB_LAUNCH_RING(32, 256, 0);
                 }
+#undef PIB_LAUNCH_RING
                 rc = cudaGetLastError() == cudaSuccess ? PIB_OK : PIB_ERR_CUDA;
                 if (rc != PIB_OK) set_error("pair_ring_kernel launch failed");
             } else {

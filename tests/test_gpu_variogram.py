@@ -161,16 +161,19 @@ def test_generic_kernel_matches_tiled_kernel(pib, monkeypatch):
         np.testing.assert_allclose(a["sum_sq"], b["sum_sq"], rtol=1e-12)
 
 
+@pytest.mark.parametrize("ring", ["32", "16"])
 @pytest.mark.parametrize("n,step,maxr", [(30000, 2000.0, 40500.0), (5000, 250.0, 30000.0), (1000, 500.0, 40500.0)])
-def test_ring_kernel_vs_oracle(pib, oracle, monkeypatch, n, step, maxr):
+def test_ring_kernel_vs_oracle(pib, oracle, monkeypatch, n, step, maxr, ring):
     """The ring-window kernel (the 1M-point fast path) forced onto sizes the oracle can check:
     coarse lags (ring slots only), fine lags (tile pairs wider than the ring -> overflow path)."""
     from pyinterpolate_b200 import _lib
     pts = dem_like_field(n, seed=31)
     lags = np.arange(step, maxr, step)
     monkeypatch.setenv("PIB_FORCE_RING", "1")
+    monkeypatch.setenv("PIB_RING", ring)                    # 32-slot ring x 256 threads or 16-slot ring x 512 threads
     got = _lib.variogram_host(pts, lags)
     monkeypatch.delenv("PIB_FORCE_RING")
+    monkeypatch.delenv("PIB_RING")
     want = oracle.variogram_sums(pts, lags)
     np.testing.assert_array_equal(got["count"], want["count"])
     np.testing.assert_allclose(got["sum_sq"], want["sum_sq"], rtol=RTOL)
@@ -185,7 +188,12 @@ def test_ring_and_full_kernels_agree_300k(pib, monkeypatch):
     lags = np.arange(500.0, 40500.0, 500.0)
     monkeypatch.setenv("PIB_FORCE_RING", "1")
     ring = _lib.variogram_host(pts, lags)
+    monkeypatch.setenv("PIB_RING", "16")
+    ring16 = _lib.variogram_host(pts, lags)
+    monkeypatch.delenv("PIB_RING")
     monkeypatch.delenv("PIB_FORCE_RING")
+    np.testing.assert_array_equal(ring16["count"], ring["count"])
+    np.testing.assert_allclose(ring16["sum_sq"], ring["sum_sq"], rtol=1e-12)
     monkeypatch.setenv("PIB_FORCE_FULL", "1")
     full = _lib.variogram_host(pts, lags)
     monkeypatch.delenv("PIB_FORCE_FULL")
