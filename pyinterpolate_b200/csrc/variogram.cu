@@ -890,7 +890,7 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
                 std::sort(diag.begin(), diag.end());
                 const double d90 = diag[(size_t)(0.9 * (diag.size() - 1))];
                 use_ring = (2.5 * d90 / min_width + 2.0) <= 24.0;
-                ring16_ok = (3.0 * d90 / min_width + 2.0) <= 15.0;       // A sub-tile = 4 tiles (~2x the diagonal)
+                ring16_ok = (3.0 * d90 / min_width + 2.0) <= 16.0;       // A sub-tile = 4 tiles (~2x the diagonal)
             }
             const char *force_ring = std::getenv("PIB_FORCE_RING");
             if (force_ring && force_ring[0] == '1') use_ring = true;
