@@ -18,6 +18,7 @@
 //                 partial pivoting like dgesv, so the pivot sequence follows the reference.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -356,6 +357,251 @@ __global__ void solve_kernel(const SolveParams p)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Register-resident solver (k <= 64): the system never touches shared memory during elimination.
+//
+// solve_kernel above keeps the matrix in shared memory, so every DFMA of the trailing update is an
+// LDS + STS and the kernel is shared-memory bound (2-3 % of the FP64 peak).  Here ONE THREAD OWNS ONE
+// ROW of Gamma in registers (K doubles + border column + right-hand side); K = 8/16/32/64 is a template
+// parameter and the whole LU is unrolled, so every register index is static.  Per elimination step
+// the threads of a system agree on the pivot (partial pivoting = argmax over the rows not yet used,
+// like dgetf2), the pivot row is broadcast through shared memory (one LDS.128 per two DFMAs) and every
+// other row updates itself.  Rows are never swapped: a row simply retires when it is chosen as pivot,
+// which is the same elimination order as LAPACK's explicit swaps.  The ones border of ordinary kriging
+// is the (K+1)-th row; it lives in shared memory, one element per thread (thread c owns column c).
+// Systems with fewer than K neighbours are padded with identity rows / columns.
+// ---------------------------------------------------------------------------------------------
+template <int TPS>
+static __device__ __forceinline__ void sys_sync(int sid)
+{
+    if (TPS <= 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(sid + 1), "n"(TPS) : "memory");
+}
+
+template <int K, bool ORD>
+struct RegSysSmem {
+    double prow[K + 4];        // pivot row: columns 0..K-1, [K] border column, [K+1] right-hand side
+    double brow[K + 4];        // border row (ORD): columns 0..K-1, [K] corner, [K+1] its right-hand side
+    double xs[K + 4];          // solution
+    double2 nxy[K];
+    double G[K * (K + 1)];     // Gamma, row stride K + 1 (odd: column reads are conflict free); each entry computed once
+    double redv[4];
+    long long redk[2];
+    int redi[4];
+};
+
+template <int K, bool ORD>
+__global__ void __launch_bounds__(256) solve_reg_kernel(const SolveParams p)
+{
+    constexpr int TPS = K < 32 ? 32 : K;          // threads per system
+    constexpr int SPC = 256 / TPS;                // systems per CTA
+    constexpr int NSTEP = ORD ? K + 1 : K;
+    constexpr int WARPS = TPS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RegSysSmem<K, ORD> *smem = reinterpret_cast<RegSysSmem<K, ORD> *>(smem_raw);
+    const int sid = threadIdx.x / TPS, t = threadIdx.x % TPS, lane = threadIdx.x & 31, wis = t >> 5;
+    const int64_t slot = (int64_t)blockIdx.x * SPC + sid;
+    if (slot >= p.count) return;                   // whole systems leave together (barriers are per system)
+    RegSysSmem<K, ORD> &S = smem[sid];
+    const GridIndex &g = p.g;
+    const int kk = p.kk;
+
+    const int32_t q = p.order[slot];
+    const double ux = p.unknown[2 * (int64_t)q], uy = p.unknown[2 * (int64_t)q + 1];
+    int my_pos = -1;
+    double my_d = 0.0;
+    if (t < kk) {
+        my_pos = p.nbr_pos[slot * kk + t];
+        my_d = p.nbr_d[slot * kk + t];
+        S.nxy[t] = make_double2(g.x[my_pos], g.y[my_pos]);
+    } else if (t < K) {
+        S.nxy[t] = make_double2(0.0, 0.0);
+    }
+    sys_sync<TPS>(sid);
+    const double2 me = (t < K) ? S.nxy[t] : make_double2(0.0, 0.0);
+
+    for (int set = 0; set < p.n_sets; ++set) {
+        const double nugget = p.params[3 * set], sill = p.params[3 * set + 1], rang = p.params[3 * set + 2];
+        // ---- my row of [Gamma | 1 | k] (ordinary.py:108-115 row order: neighbours by ascending distance) ----
+        // Gamma is symmetric: thread t evaluates the K/2 entries (t, t+1 .. t+K/2) cyclically and writes both
+        // (t, c) and (c, t) into shared memory; afterwards every thread loads its row with static indices
+        if (t < K) {
+            for (int i = 0; i < K / 2; ++i) {
+                int c = t + 1 + i;
+                if (c >= K) c -= K;
+                double v;
+                if (t < kk && c < kk) {
+                    const double2 o = S.nxy[c];
+                    const double dx = __dsub_rn(me.x, o.x), dy = __dsub_rn(me.y, o.y);
+                    v = gamma_model(p.model, sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))), nugget, sill, rang);
+                } else v = 0.0;                                                 // identity padding (off diagonal)
+                S.G[t * (K + 1) + c] = v;
+                S.G[c * (K + 1) + t] = v;
+            }
+            S.G[t * (K + 1) + t] = (t < kk) ? nugget : 1.0;                     // gamma(0) / identity padding
+        }
+        sys_sync<TPS>(sid);
+        double a[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) a[c] = (t < K) ? S.G[t * (K + 1) + c] : 0.0;
+        const double rhs0 = (t < kk) ? gamma_model(p.model, my_d, nugget, sill, rang) : 0.0;
+        double rhs = rhs0;
+        double ab = (ORD && t < kk) ? 1.0 : 0.0;                                // border column entry of my row
+        if (ORD) {
+            if (t < K) S.brow[t] = (t < kk) ? 1.0 : 0.0;
+            if (t == 0) { S.brow[K] = 0.0; S.brow[K + 1] = 1.0; }
+        }
+        bool row_active = (t < K);
+        bool border_active = ORD;
+        int my_step = -1, border_step = -1;
+        double my_inv = 0.0, border_inv = 0.0;
+        bool singular = false;
+        sys_sync<TPS>(sid);
+
+        // ---- LU with partial pivoting, fully unrolled (column j) ------------------------------------
+#pragma unroll
+        for (int j = 0; j < NSTEP; ++j) {
+            if (singular) break;
+            // candidates: my row's entry in column j, and (ORD) the border row's entry offered by its owner
+            double bv = row_active ? fabs(j < K ? a[j < K ? j : 0] : ab) : -1.0;
+            int bi = t;
+            if (ORD && border_active) {
+                const int owner = (j < K) ? j : 0;
+                if (t == owner) {
+                    const double v = fabs(S.brow[j]);
+                    if (v > bv) { bv = v; bi = K; }                             // ties keep the smaller row id
+                }
+            }
+            {
+                // warp argmax with the hardware integer reductions: |v| >= 0, so the fp64 order is the order of
+                // the bit pattern; first the high words, then the low words among the leaders, then the lowest lane
+                // (NaN candidates have the largest pattern and are caught by the check below)
+                const long long key = __double_as_longlong(bv < 0.0 ? -1.0 : bv);
+                const unsigned hi = (bv < 0.0) ? 0u : (unsigned)(key >> 32) + 1u, lo = (unsigned)key;
+                const unsigned hmax = __reduce_max_sync(0xffffffffu, hi);
+                const unsigned lmax = __reduce_max_sync(0xffffffffu, hi == hmax ? lo : 0u);
+                const unsigned lead = __ballot_sync(0xffffffffu, hi == hmax && lo == lmax);
+                const int src = __ffs(lead) - 1;
+                bi = __shfl_sync(0xffffffffu, bi, src);
+                bv = (hmax == 0u) ? -1.0 : __longlong_as_double(((long long)(hmax - 1u) << 32) | lmax);
+            }
+            if (WARPS > 1) {
+                if (lane == 0) { S.redv[wis] = bv; S.redi[wis] = bi; }
+                sys_sync<TPS>(sid);
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) {
+                    const double ov = S.redv[w];
+                    const int oi = S.redi[w];
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+            }
+            if (!(bv > 0.0) || isinf(bv)) { singular = true; break; }           // zero / NaN pivot column
+            // publish the pivot row
+            if (bi < K) {
+                if (t == bi) {
+#pragma unroll
+                    for (int c = 0; c < K; ++c)
+                        if (c >= j) S.prow[c] = a[c];
+                    S.prow[K] = ab; S.prow[K + 1] = rhs;
+                    row_active = false; my_step = j;
+                }
+            } else {
+                if (t < K) S.prow[t] = S.brow[t];
+                if (t == 0) { S.prow[K] = S.brow[K]; S.prow[K + 1] = S.brow[K + 1]; }
+                border_active = false; border_step = j;
+            }
+            sys_sync<TPS>(sid);
+            const double inv = __drcp_rn(S.prow[j]);
+            if (my_step == j) my_inv = inv;
+            if (border_step == j) border_inv = inv;
+            {
+                // retired rows update with l = 0 (an exact no-op): no divergent branch around the DFMAs
+                const double l = row_active ? (j < K ? a[j < K ? j : 0] : ab) * inv : 0.0;   // dgetf2 scales by the reciprocal
+#pragma unroll
+                for (int c = 0; c < K; ++c)
+                    if (c > j) a[c] = __fma_rn(-l, S.prow[c], a[c]);
+                if (ORD && j < K) ab = __fma_rn(-l, S.prow[K], ab);
+                rhs = __fma_rn(-l, S.prow[K + 1], rhs);
+            }
+            if (ORD && border_active) {
+                const double lb = S.brow[j] * inv;
+                if (t < K && t > j) S.brow[t] = __fma_rn(-lb, S.prow[t], S.brow[t]);
+                if (t == 0) {
+                    if (j < K) S.brow[K] = __fma_rn(-lb, S.prow[K], S.brow[K]);
+                    S.brow[K + 1] = __fma_rn(-lb, S.prow[K + 1], S.brow[K + 1]);
+                }
+            }
+            if (WARPS == 1) __syncwarp();
+        }
+        sys_sync<TPS>(sid);
+
+        double zhat = nan(""), sigma = nan("");
+        uint8_t stat = PIB_STATUS_SINGULAR;
+        if (!singular) {
+            // ---- back substitution: column j of U belongs to the rows that retired before step j ----
+#pragma unroll
+            for (int j = NSTEP - 1; j >= 0; --j) {
+                if (my_step == j) S.xs[j] = rhs * my_inv;
+                if (ORD && border_step == j && t == 0) S.xs[j] = S.brow[K + 1] * border_inv;
+                sys_sync<TPS>(sid);
+                const double x = S.xs[j];
+                if (my_step >= 0 && my_step < j) rhs = __fma_rn(-(j < K ? a[j < K ? j : 0] : ab), x, rhs);
+                if (ORD && border_step >= 0 && border_step < j && t == 0)
+                    S.brow[K + 1] = __fma_rn(-S.brow[j], x, S.brow[K + 1]);
+            }
+            sys_sync<TPS>(sid);
+            // zhat = z . w (ordinary.py:121) or (z - mean) . w + mean (simple.py:114-116); sigma = w . k (+ mu)
+            double zs = 0.0, ss = 0.0;
+            if (t < kk) {
+                const double w = S.xs[t];
+                double zv = p.values ? p.values[(size_t)set * p.n + g.orig[my_pos]] : g.z[my_pos];
+                if (!ORD) zv -= p.process_mean;
+                zs = zv * w;
+                ss = w * rhs0;
+            }
+            if (ORD && t == 0) ss += S.xs[K];                                   // mu * 1
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                zs += __shfl_xor_sync(0xffffffffu, zs, o);
+                ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            }
+            if (WARPS > 1) {
+                if (lane == 0) { S.redv[wis] = zs; S.redv[2 + wis] = ss; }
+                sys_sync<TPS>(sid);
+                zs = S.redv[0] + S.redv[1]; ss = S.redv[2] + S.redv[3];
+            }
+            zhat = ORD ? zs : zs + p.process_mean;
+            sigma = ss;
+            stat = PIB_STATUS_OK;
+            if (sigma < 0.0) { sigma = nan(""); stat = PIB_STATUS_NEGATIVE_VARIANCE; }   // ordinary.py:125-126
+        }
+        if (t == 0) {
+            double *o = p.out + ((size_t)set * p.m + q) * 4;
+            o[0] = zhat; o[1] = sigma; o[2] = ux; o[3] = uy;
+            if (p.status) p.status[(size_t)set * p.m + q] = stat;
+        }
+        sys_sync<TPS>(sid);
+    }
+}
+
+template <int K>
+static int launch_solve_reg(const SolveParams &sp, int mode, cudaStream_t stream)
+{
+    constexpr int SPC = 256 / (K < 32 ? 32 : K);
+    const int grid = (int)((sp.count + SPC - 1) / SPC);
+    if (mode == PIB_KRIGE_ORDINARY) {
+        const size_t bytes = sizeof(RegSysSmem<K, true>) * SPC;
+        PIB_CUDA(cudaFuncSetAttribute(solve_reg_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        solve_reg_kernel<K, true><<<grid, 256, bytes, stream>>>(sp);
+    } else {
+        const size_t bytes = sizeof(RegSysSmem<K, false>) * SPC;
+        PIB_CUDA(cudaFuncSetAttribute(solve_reg_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        solve_reg_kernel<K, false><<<grid, 256, bytes, stream>>>(sp);
+    }
+    PIB_CUDA(cudaGetLastError());
+    return PIB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
 int krige_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
@@ -397,6 +643,8 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
     const size_t knn_smem = (size_t)KNN_WARPS * 2 * k2 * sizeof(Cand);
     PIB_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem));
 
+    const char *force_smem = std::getenv("PIB_FORCE_SMEM_SOLVE");
+    const bool use_reg = kk <= 64 && !(force_smem && force_smem[0] == '1');
     const int64_t chunk = std::min<int64_t>(m, (int64_t)1 << 21);
     int32_t *nbr_pos;
     double *nbr_d;
@@ -418,9 +666,17 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
         sp.model = model; sp.mode = mode; sp.process_mean = process_mean; sp.out = d_out; sp.status = d_status;
         sp.warps = solve_warps; sp.stride = stride;
         timing_begin(PIB_T_SOLVE, stream);
-        solve_kernel<<<(int)((count + solve_warps - 1) / solve_warps), solve_warps * 32, per_warp * solve_warps, stream>>>(sp);
+        int rc = PIB_OK;
+        if (use_reg && kk <= 8) rc = launch_solve_reg<8>(sp, mode, stream);
+        else if (use_reg && kk <= 16) rc = launch_solve_reg<16>(sp, mode, stream);
+        else if (use_reg && kk <= 32) rc = launch_solve_reg<32>(sp, mode, stream);
+        else if (use_reg && kk <= 64) rc = launch_solve_reg<64>(sp, mode, stream);
+        else {
+            solve_kernel<<<(int)((count + solve_warps - 1) / solve_warps), solve_warps * 32, per_warp * solve_warps, stream>>>(sp);
+            if (cudaGetLastError() != cudaSuccess) { set_error("solve_kernel launch failed"); rc = PIB_ERR_CUDA; }
+        }
         timing_end(PIB_T_SOLVE, stream);
-        PIB_CUDA(cudaGetLastError());
+        PIB_TRY(rc);
     }
     return PIB_OK;
 }

@@ -16,7 +16,7 @@ only = os.environ.get("QP_ONLY", "")
 pts = dem_like_field(n, seed=2)
 lags = np.arange(500.0, 40500.0, 500.0)
 d = torch.from_numpy(pts).cuda()
-for rep in range(3):
+for rep in range(0 if only == "krige" else 3):
     torch.cuda.synchronize(); t0 = time.time()
     r = _lib.variogram_device(d, lags, want_pairs=True)
     torch.cuda.synchronize(); dt = time.time() - t0
@@ -24,16 +24,18 @@ for rep in range(3):
     kms, _ = _lib.last_kernel_ms(_lib.KERNEL_PAIR)
     print(f"variogram n={n}: {dt*1e3:.1f} ms (pair kernel {kms:.1f} ms) evaluated={ev:.3e} pairs -> {ev/dt:.3e} pairs/s evaluated, "
           f"{n*(n-1)/2/dt:.3e} equivalent pairs/s, {13*ev/dt/1e12:.2f} TFLOP/s algorithmic")
-W = np.array([[1, 0, 0, 2.23606797749979]])
-torch.cuda.synchronize(); t0 = time.time()
-r = _lib.variogram_device(d[: n // 5].contiguous(), lags, W=W, want_pairs=True)
-torch.cuda.synchronize(); dt = time.time() - t0
-print(f"ellipse 1 dir n={n//5}: {dt*1e3:.1f} ms evaluated={r['pairs_evaluated']:.3e}")
+if only != "krige":
+    W = np.array([[1, 0, 0, 2.23606797749979]])
+    torch.cuda.synchronize(); t0 = time.time()
+    r = _lib.variogram_device(d[: n // 5].contiguous(), lags, W=W, want_pairs=True)
+    torch.cuda.synchronize(); dt = time.time() - t0
+    print(f"ellipse 1 dir n={n//5}: {dt*1e3:.1f} ms evaluated={r['pairs_evaluated']:.3e}")
 
 if only == "variogram":
     sys.exit(0)
 known = d
-for k, m in ((32, 1_000_000), (64, 1_000_000)):
+M = int(os.environ.get("QP_M", "1000000"))
+for k, m in ((32, M), (64, M)):
     unk = torch.from_numpy(uniform_locations(m, seed=5)).cuda()
     params = np.array([[1.0, float(np.var(pts[:, 2])), 20000.0]])
     for mode in (0, 1):
@@ -41,4 +43,5 @@ for k, m in ((32, 1_000_000), (64, 1_000_000)):
             torch.cuda.synchronize(); t0 = time.time()
             out, _, st = _lib.krige_device(known, unk, 6, params, mode, k)
             torch.cuda.synchronize(); dt = time.time() - t0
-        print(f"krige mode={mode} k={k} n={n} m={m}: {dt*1e3:.1f} ms -> {m/dt:.3e} pts/s")
+        kn, _ = _lib.last_kernel_ms(_lib.KERNEL_KNN); so, _ = _lib.last_kernel_ms(_lib.KERNEL_SOLVE)
+        print(f"krige mode={mode} k={k} n={n} m={m}: {dt*1e3:.1f} ms (knn {kn:.1f} solve {so:.1f}) -> {m/dt:.3e} pts/s")
