@@ -5,6 +5,7 @@ Same call signatures as the reference (src/pyinterpolate/__init__.py:15-24); the
 internals are replaced by libpyinterp_b200.so (hand-written CUDA, C ABI in include/pyinterp_b200.h).
 There is no CPU fallback: without the CUDA library or a GPU every compute call raises.
 """
+from .indicator import ExperimentalIndicatorVariogram, IndicatorKriging, IndicatorVariogramData
 from .kriging import indicator_kriging, interpolate_points, ordinary_kriging, simple_kriging
 from .models import TheoreticalVariogram
 from .variogram import (DirectionalVariogram, ExperimentalVariogram, build_experimental_variogram,
@@ -13,4 +14,5 @@ from .variogram import (DirectionalVariogram, ExperimentalVariogram, build_exper
 __version__ = "0.1.0"
 __all__ = ["ExperimentalVariogram", "DirectionalVariogram", "build_experimental_variogram",
            "calculate_semivariance", "calculate_covariance", "TheoreticalVariogram",
-           "ordinary_kriging", "simple_kriging", "interpolate_points", "indicator_kriging"]
+           "ordinary_kriging", "simple_kriging", "interpolate_points", "indicator_kriging",
+           "ExperimentalIndicatorVariogram", "IndicatorVariogramData", "IndicatorKriging"]
