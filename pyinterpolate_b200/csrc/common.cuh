@@ -82,6 +82,7 @@ struct SortedPoints {
     int32_t *orig = nullptr;                           // [n_pad] original row, -1 for padding
     double4 *tile_box = nullptr;                       // [n_pad / tile]  (xmin, ymin, xmax, ymax)
     int tile = 0;
+    double box[4] = {0, 0, 0, 0};                      // xmin, ymin, xmax, ymax of all points
 };
 int build_sorted_points(const double *d_xyz, int64_t n, int tile, int pad_to, Scratch &ws,
                         cudaStream_t stream, SortedPoints *out);

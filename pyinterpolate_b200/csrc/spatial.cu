@@ -172,6 +172,7 @@ int build_sorted_points(const double *d_xyz, int64_t n, int tile, int pad_to, Sc
 
     SortedPoints sp;
     sp.n = n; sp.tile = tile;
+    for (int i = 0; i < 4; ++i) sp.box[i] = box[i];
     sp.n_pad = (n + pad_to - 1) / pad_to * pad_to;
     PIB_TRY(ws.alloc(&sp.xy, sp.n_pad)); PIB_TRY(ws.alloc(&sp.z, sp.n_pad));
     PIB_TRY(ws.alloc(&sp.orig, sp.n_pad));

@@ -50,6 +50,7 @@ struct PairParams {
     float lut_scale;
     const uint16_t *lut2;        // [lut2_n] ring kernel: (hi word of d2 - lut2_base) >> 13 -> first candidate slot
     int lut2_base, lut2_n;
+    double box_slack;            // ellipse ring kernel: slack on the whitened bounding boxes
     double max_d2;               // T(edges[n_lags-1])
     double w00, w01, w10, w11;   // whitening matrix (ellipse)
     int shard_index, shard_count;
@@ -174,8 +175,11 @@ __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
                 bool live = false;
                 if (tb >= tb_first && tb < tb1) {
                     const double4 bbox = p.tile_box[tb];
-                    // margin: ellipse norms are >= the plain distance up to rounding of the rotation
-                    live = box_min_d2(abox, bbox) * (1.0 - 1e-12) <= p.max_d2;
+                    if (ELLIPSE) {                      // whitened boxes + slack (see pair_ring_kernel)
+                        const double gx = fmax(0.0, fmax(abox.x - bbox.z, bbox.x - abox.z) - p.box_slack);
+                        const double gy = fmax(0.0, fmax(abox.y - bbox.w, bbox.y - abox.w) - p.box_slack);
+                        live = (gx * gx + gy * gy) * (1.0 - 1e-12) <= p.max_d2;
+                    } else live = box_min_d2(abox, bbox) <= p.max_d2;
                 }
                 m |= (uint64_t)__ballot_sync(0xffffffffu, live) << (32 * h);
             }
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
 constexpr int LUT2_MAX = 4096;
 constexpr int LUT2_SHIFT = 13;                 // keep 7 of the 20 mantissa bits of the high word: 128 cells per octave
 
-template <int RING, int NT, int FIX>
+template <int RING, int NT, int FIX, bool ELLIPSE>
 __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
 {
     constexpr int U = 8;
@@ -412,6 +416,10 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
     unsigned long long evaluated = 0;
     double *my_partial = p.partial + ((size_t)blockIdx.x * (NT / 32) + warp) * n_slots * 4;
     const int base_hi = p.lut2_base, lut_last = p.lut2_n - 1;
+    const double w00 = p.w00, w01 = p.w01, w10 = p.w10, w11 = p.w11;
+    // ELLIPSE: p.tile_box holds the boxes of the WHITENED coordinates W p; box_slack covers the rounding
+    // difference between W (p_j - p_i) as the pairs compute it and W p_j - W p_i
+    const double slack = p.box_slack;
 
     for (int64_t item = ((int64_t)blockIdx.x) * p.shard_count + p.shard_index; item < n_items;
          item += (int64_t)gridDim.x * p.shard_count) {
@@ -439,14 +447,20 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
                 bool live = false;
                 if (tb >= tb_first && tb < tb1) {
                     const double4 bbox = p.tile_box[tb];
-                    const double dmin = box_min_d2(abox, bbox);
+                    double dmin;
+                    if (ELLIPSE) {
+                        const double gx = fmax(0.0, fmax(abox.x - bbox.z, bbox.x - abox.z) - slack);
+                        const double gy = fmax(0.0, fmax(abox.y - bbox.w, bbox.y - abox.w) - slack);
+                        dmin = (gx * gx + gy * gy) * (1.0 - 1e-12);
+                    } else dmin = box_min_d2(abox, bbox);
                     live = dmin <= p.max_d2;
                     if (live) {
                         // every pair of the two boxes has dmin <= d2 <= dmax in the kernel's own arithmetic
-                        // (fp subtraction, multiplication and addition are monotone)
-                        const double dxm = fmax(abox.z - bbox.x, bbox.z - abox.x);
-                        const double dym = fmax(abox.w - bbox.y, bbox.w - abox.y);
-                        const double dmax = __dadd_rn(__dmul_rn(dxm, dxm), __dmul_rn(dym, dym));
+                        // (fp subtraction, multiplication and addition are monotone; the ellipse bounds carry slack)
+                        const double dxm = fmax(abox.z - bbox.x, bbox.z - abox.x) + (ELLIPSE ? slack : 0.0);
+                        const double dym = fmax(abox.w - bbox.y, bbox.w - abox.y) + (ELLIPSE ? slack : 0.0);
+                        const double dmax = ELLIPSE ? (dxm * dxm + dym * dym) * (1.0 + 1e-12)
+                                                    : __dadd_rn(__dmul_rn(dxm, dxm), __dmul_rn(dym, dym));
                         int a = 0, b = n_slots - 1;           // first slot whose threshold is >= dmin
                         const long long v = __double_as_longlong(dmin);
                         while (a < b) { const int mid = (a + b) >> 1; if (v <= s_upper[mid]) b = mid; else a = mid + 1; }
@@ -562,9 +576,18 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
                 for (int u = 0; u < U; ++u) {
                     const double2 pj = bxy[j0 + u];
                     dzv[u] = __dsub_rn(zi, bz[j0 + u]);
-                    // scipy cdist euclidean: sqrt(dx*dx + dy*dy), nothing fused (distance/point.py:56)
-                    const double dx = __dsub_rn(xi, pj.x), dy = __dsub_rn(yi, pj.y);
-                    d2[u] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                    if (ELLIPSE) {
+                        // vector_distance = other - centre (angular.py:448); W @ d as OpenBLAS dgemm evaluates it:
+                        // fma(W[r][1], dy, W[r][0]*dx); einsum: n0*n0 + n1*n1 un-fused (angular.py:666-668)
+                        const double dx = __dsub_rn(pj.x, xi), dy = __dsub_rn(pj.y, yi);
+                        const double n0 = __fma_rn(w01, dy, __dmul_rn(w00, dx));
+                        const double n1 = __fma_rn(w11, dy, __dmul_rn(w10, dx));
+                        d2[u] = __dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1));
+                    } else {
+                        // scipy cdist euclidean: sqrt(dx*dx + dy*dy), nothing fused (distance/point.py:56)
+                        const double dx = __dsub_rn(xi, pj.x), dy = __dsub_rn(yi, pj.y);
+                        d2[u] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -676,6 +699,32 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
         acc[TRASH_LO * NT] = make_double2(0.0, 0.0); acc[TRASH_HI * NT] = make_double2(0.0, 0.0);
     }
     if (tid == 0 && evaluated) atomicAdd(p.pairs_evaluated, evaluated);
+}
+
+// bounding boxes of the whitened coordinates (u, v) = W p of every tile (one warp per tile)
+__global__ void tile_box_whitened_kernel(const double2 *__restrict__ xy, int64_t n, int64_t n_tiles,
+                                         double w00, double w01, double w10, double w11, double4 *__restrict__ box)
+{
+    const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= n_tiles) return;
+    double umin = INFINITY, vmin = INFINITY, umax = -INFINITY, vmax = -INFINITY;
+    for (int k = lane; k < TILE; k += 32) {
+        const int64_t i = t * TILE + k;
+        if (i < n) {
+            const double2 q = xy[i];
+            const double u = w00 * q.x + w01 * q.y, v = w10 * q.x + w11 * q.y;
+            umin = fmin(umin, u); umax = fmax(umax, u);
+            vmin = fmin(vmin, v); vmax = fmax(vmax, v);
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        umin = fmin(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+        vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    if (lane == 0) box[t] = make_double4(umin, vmin, umax, vmax);
 }
 
 // Fixed-order sum of the per-warp partials -> outputs (one thread per lag)
@@ -876,7 +925,13 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         // estimate the span from the tile bounding boxes (A sub-tile = 2 tiles, B tile = 1 tile).
         bool use_ring = false, ring16_ok = false;
         const char *force_full = std::getenv("PIB_FORCE_FULL");
-        if (n_dirs == 0 && n_lags <= MAX_SLOTS - 2 && !(force_full && force_full[0] == '1')) {
+        double stretch = 1.0;                      // largest singular value of the whitening matrices
+        for (int t = 0; t < n_dirs; ++t) {
+            const double *w = W + 4 * t;
+            const double frob = w[0] * w[0] + w[1] * w[1] + w[2] * w[2] + w[3] * w[3], det = w[0] * w[3] - w[1] * w[2];
+            stretch = std::max(stretch, std::sqrt(0.5 * (frob + std::sqrt(std::max(0.0, frob * frob - 4.0 * det * det)))));
+        }
+        if (n_lags <= MAX_SLOTS - 2 && !(force_full && force_full[0] == '1')) {
             std::vector<double4> boxes(n_tiles);
             PIB_CUDA(cudaMemcpyAsync(boxes.data(), sp.tile_box, sizeof(double4) * n_tiles, cudaMemcpyDeviceToHost, stream));
             PIB_CUDA(cudaStreamSynchronize(stream));
@@ -888,7 +943,7 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             for (int b = 1; b < n_lags; ++b) min_width = std::min(min_width, edges[b] - edges[b - 1]);
             if (!diag.empty()) {
                 std::sort(diag.begin(), diag.end());
-                const double d90 = diag[(size_t)(0.9 * (diag.size() - 1))];
+                const double d90 = stretch * diag[(size_t)(0.9 * (diag.size() - 1))];
                 use_ring = (2.5 * d90 / min_width + 2.0) <= 24.0;
                 ring16_ok = (3.0 * d90 / min_width + 2.0) <= 16.0;       // A sub-tile = 4 tiles (~2x the diagonal)
             }
@@ -945,35 +1000,52 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         p.shard_index = shard_index; p.shard_count = shard_count; p.partial = d_partial;
         p.pairs_evaluated = d_evaluated;
         p.lut2 = d_lut2; p.lut2_base = lut2_base; p.lut2_n = (int)lut2.size();
+        p.box_slack = 0.0;
+        double4 *d_boxw = nullptr;                 // ellipse: bounding boxes of the whitened coordinates, per direction
+        if (n_dirs > 0) PIB_TRY(ws.alloc(&d_boxw, n_tiles));
         for (int t = 0; t < out_dirs; ++t) {
             PIB_CUDA(cudaMemsetAsync(d_partial, 0, part_n * sizeof(double), stream));
             int rc;
-            timing_begin(PIB_T_PAIR, stream);
             if (n_dirs > 0) {
                 p.w00 = W[4 * t]; p.w01 = W[4 * t + 1]; p.w10 = W[4 * t + 2]; p.w11 = W[4 * t + 3];
-                rc = nt == 128 ? launch_pair_kernel<128, true>(p, fix_steps, grid, stream)
-                   : nt == 64 ? launch_pair_kernel<64, true>(p, fix_steps, grid, stream)
-                              : launch_pair_kernel<32, true>(p, fix_steps, grid, stream);
-            } else if (use_ring) {
-                p.w00 = p.w01 = p.w10 = p.w11 = 0;
+                tile_box_whitened_kernel<<<(int)(((int64_t)n_tiles * 32 + 255) / 256), 256, 0, stream>>>(
+                    sp.xy, n, n_tiles, p.w00, p.w01, p.w10, p.w11, d_boxw);
+                PIB_CUDA(cudaGetLastError());
+                p.tile_box = d_boxw;
+                // |W (p_j - p_i) as computed  -  (W p_j - W p_i) as boxed| <= a few ulps of |W| |p|; 1e-12 relative is ample
+                const double pmax = std::fabs(sp.box[0]) + std::fabs(sp.box[1]) + std::fabs(sp.box[2]) + std::fabs(sp.box[3]);
+                p.box_slack = 1e-12 * pmax * (std::fabs(p.w00) + std::fabs(p.w01) + std::fabs(p.w10) + std::fabs(p.w11));
+            } else p.w00 = p.w01 = p.w10 = p.w11 = 0;
+            timing_begin(PIB_T_PAIR, stream);
+            if (use_ring) {
                 const size_t smem = (size_t)(ring + 2) * ring_nt * (sizeof(double2) + sizeof(uint32_t));
-#define PIB_LAUNCH_RING(R, T, F)                                                                                     \
-    do {                                                                                                             \
-        PIB_CUDA(cudaFuncSetAttribute(pair_ring_kernel<R, T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        pair_ring_kernel<R, T, F><<<grid, T, smem, stream>>>(p);                                                    \
+#define PIB_LAUNCH_RING(R, T, F, E)                                                                                     \
+    do {                                                                                                                \
+        PIB_CUDA(cudaFuncSetAttribute(pair_ring_kernel<R, T, F, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        pair_ring_kernel<R, T, F, E><<<grid, T, smem, stream>>>(p);                                                    \
+    } while (0)
+#define PIB_LAUNCH_RING_E(R, T, F)                        \
+    do {                                                  \
+        if (n_dirs > 0) PIB_LAUNCH_RING(R, T, F, true);   \
+        else PIB_LAUNCH_RING(R, T, F, false);             \
     } while (0)
                 if (ring == 16) {
-                    if (fix2 <= 1) PIB_LAUNCH_RING(16, 512, 1);
-                    else if (fix2 <= 2) PIB_LAUNCH_RING(16, 512, 2);
-                    else PIB_LAUNCH_RING(16, 512, 0);
+                    if (fix2 <= 1) PIB_LAUNCH_RING_E(16, 512, 1);
+                    else if (fix2 <= 2) PIB_LAUNCH_RING_E(16, 512, 2);
+                    else PIB_LAUNCH_RING_E(16, 512, 0);
                 } else {
-                    if (fix2 <= 1) PIB_LAUNCH_RING(32, 256, 1);
-                    else if (fix2 <= 2) PIB_LAUNCH_RING(32, 256, 2);
-                    else PIB_LAUNCH_RING(32, 256, 0);
+                    if (fix2 <= 1) PIB_LAUNCH_RING_E(32, 256, 1);
+                    else if (fix2 <= 2) PIB_LAUNCH_RING_E(32, 256, 2);
+                    else PIB_LAUNCH_RING_E(32, 256, 0);
                 }
+#undef PIB_LAUNCH_RING_E
 #undef PIB_LAUNCH_RING
                 rc = cudaGetLastError() == cudaSuccess ? PIB_OK : PIB_ERR_CUDA;
                 if (rc != PIB_OK) set_error("pair_ring_kernel launch failed");
+            } else if (n_dirs > 0) {
+                rc = nt == 128 ? launch_pair_kernel<128, true>(p, fix_steps, grid, stream)
+                   : nt == 64 ? launch_pair_kernel<64, true>(p, fix_steps, grid, stream)
+                              : launch_pair_kernel<32, true>(p, fix_steps, grid, stream);
             } else {
                 p.w00 = p.w01 = p.w10 = p.w11 = 0;
                 rc = nt == 128 ? launch_pair_kernel<128, false>(p, fix_steps, grid, stream)

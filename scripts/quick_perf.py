@@ -25,11 +25,20 @@ for rep in range(0 if only == "krige" else 3):
     print(f"variogram n={n}: {dt*1e3:.1f} ms (pair kernel {kms:.1f} ms) evaluated={ev:.3e} pairs -> {ev/dt:.3e} pairs/s evaluated, "
           f"{n*(n-1)/2/dt:.3e} equivalent pairs/s, {13*ev/dt/1e12:.2f} TFLOP/s algorithmic")
 if only != "krige":
-    W = np.array([[1, 0, 0, 2.23606797749979]])
-    torch.cuda.synchronize(); t0 = time.time()
-    r = _lib.variogram_device(d[: n // 5].contiguous(), lags, W=W, want_pairs=True)
-    torch.cuda.synchronize(); dt = time.time() - t0
-    print(f"ellipse 1 dir n={n//5}: {dt*1e3:.1f} ms evaluated={r['pairs_evaluated']:.3e}")
+    from pyinterpolate_b200 import core
+    W = np.stack([core.define_whitening_matrix(a, 0.2) for a in (90, 0, 45, 135)]).reshape(-1, 4)
+    d5 = torch.from_numpy(dem_like_field(n // 5, seed=3)).cuda()
+    for rep in range(2):
+        torch.cuda.synchronize(); t0 = time.time()
+        r = _lib.variogram_device(d5, lags, lower=core.ellipse_lower_limits(lags), W=W, want_pairs=True)
+        torch.cuda.synchronize(); dt = time.time() - t0
+    kms, nl = _lib.last_kernel_ms(_lib.KERNEL_PAIR)
+    print(f"ellipse 4 dirs n={n//5} (config 3): {dt*1e3:.1f} ms (pair kernels {kms:.1f} ms, {nl} launches) evaluated={r['pairs_evaluated']:.3e}")
+    for rep in range(2):
+        torch.cuda.synchronize(); t0 = time.time()
+        r = _lib.variogram_device(d, lags, lower=core.ellipse_lower_limits(lags), W=W[:1], want_pairs=True)
+        torch.cuda.synchronize(); dt = time.time() - t0
+    print(f"ellipse 1 dir n={n}: {dt*1e3:.1f} ms evaluated={r['pairs_evaluated']:.3e}")
 
 if only == "variogram":
     sys.exit(0)

@@ -182,6 +182,28 @@ def test_ring_kernel_vs_oracle(pib, oracle, monkeypatch, n, step, maxr, ring):
     assert got["pairs_evaluated"] <= n * (n - 1) // 2
 
 
+@pytest.mark.parametrize("ring", ["32", "16"])
+def test_ring_kernel_ellipse_vs_oracle(pib, oracle, monkeypatch, ring):
+    """Ellipse directions through the ring kernel (whitened bounding boxes for culling and lag windows)."""
+    from pyinterpolate_b200 import _lib, core
+    pts = dem_like_field(12000, seed=35)
+    lags = np.arange(3000.0, 40500.0, 3000.0)
+    angles = [90, 0, 45, 135, 15]
+    W = np.stack([core.define_whitening_matrix(a, 0.2) for a in angles]).reshape(-1, 4)
+    monkeypatch.setenv("PIB_FORCE_RING", "1")
+    monkeypatch.setenv("PIB_RING", ring)
+    got = _lib.variogram_host(pts, lags, lower=core.ellipse_lower_limits(lags), W=W)
+    monkeypatch.delenv("PIB_FORCE_RING")
+    monkeypatch.delenv("PIB_RING")
+    want = oracle.variogram_sums(pts, lags, angles, 0.2)
+    np.testing.assert_array_equal(got["count"], want["count"])
+    np.testing.assert_allclose(got["sum_sq"], want["sum_sq"], rtol=RTOL)
+    np.testing.assert_allclose(got["sum_prod"], want["sum_prod"], rtol=RTOL)
+    full = _lib.variogram_host(pts, lags, lower=core.ellipse_lower_limits(lags), W=W)     # default kernel choice
+    np.testing.assert_array_equal(full["count"], want["count"])
+    assert got["pairs_evaluated"] < 5 * len(pts) * (len(pts) - 1) // 2
+
+
 def test_ring_and_full_kernels_agree_300k(pib, monkeypatch):
     from pyinterpolate_b200 import _lib
     pts = dem_like_field(300_000, seed=33)
