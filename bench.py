@@ -269,7 +269,7 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (pair kernel) --------------------------------------------
     evaluated_per_rank = evaluated / world                              # evaluated is the all-reduced total
     achieved = FLOP_PER_PAIR * evaluated_per_rank / (pair_kernel_ms * 1e-3) / 1e12
-    roofline = {"bound": "fp64", "kernel": "pair_ring_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+    roofline = {"bound": "fp64", "kernel": "pair_ring_kernel<16,512>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak,
                 "peak_source": "DFMA-saturation probe run in this process (pib_fp64_peak_tflops); MEASURED_PEAKS.json "
                                "has no FP64 figure (its HBM %.0f GB/s / bf16 figures do not bound this kernel)"
@@ -284,6 +284,25 @@ def run_b200(args):
     if rank == 0:
         v, cores, sample = cpu_variogram_sample(pts, lags)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    # ---- BASELINE config 3 (directional, 4 ellipse directions, tolerance 0.2, 200k points), rank 0 only ----
+    if not args.no_extra and rank == 0:
+        from pyinterpolate_b200 import core
+        p3 = torch.from_numpy(dem_like_field(200_000, extent=EXTENT, seed=3)).to(dev)
+        W = np.stack([core.define_whitening_matrix(a, 0.2) for a in (90, 0, 45, 135)]).reshape(-1, 4)
+        lower = core.ellipse_lower_limits(lags)
+        r3 = _lib.variogram_device(p3, lags, lower=lower, W=W, want_pairs=True)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            r3 = _lib.variogram_device(p3, lags, lower=lower, W=W, want_pairs=True)
+        c1.record()
+        torch.cuda.synchronize()
+        ms3 = c0.elapsed_time(c1) / 3
+        extra["directional_config3"] = {"points": 200_000, "directions": 4, "tolerance": 0.2, "ms": ms3,
+                                        "direction_pairs_per_s": 4 * (200_000 * 199_999 / 2) / (ms3 * 1e-3),
+                                        "pairs_evaluated": r3["pairs_evaluated"]}
 
     # ---- kriging half of the metric (outside the timed region; every rank kriges its own locations) ----
     if not args.no_extra:
