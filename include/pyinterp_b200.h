@@ -110,6 +110,20 @@ PIB_API int pib_variogram_host(const double *xyz, int64_t n,
                        int64_t *pairs_evaluated);
 
 /* ------------------------------------------------------------------------------------------
+ * Variogram point cloud: per lag, (z_i - z_j)^2 of every ORDERED pair in the lag, in the reference's
+ * order (row i ascending, then j ascending = np.where on the N x N mask).  Replaces
+ *   semivariogram/experimental/functions/general.py:13-75, :150-233   omnidirectional_semivariogram_cloud
+ *   semivariogram/experimental/functions/directional.py:83-134, :468-530   from_ellipse_cloud (n_dirs == 1)
+ * lag_offsets [n_lags + 1] (HOST): start of each lag's block in `values`; lag b holds
+ * lag_offsets[b+1] - lag_offsets[b] = 2 * count[b] values (count from pib_variogram_host).
+ * values [lag_offsets[n_lags]] (HOST, out).  Output is O(pairs): meant for small N.
+ * ---------------------------------------------------------------------------------------- */
+PIB_API int pib_variogram_cloud_host(const double *xyz, int64_t n,
+                             const double *edges, const double *lower, int n_lags,
+                             const double *W, int n_dirs,
+                             const int64_t *lag_offsets, double *values);
+
+/* ------------------------------------------------------------------------------------------
  * Point kriging — batched neighbour search + system assembly + solve.
  *
  * Replaces the per-location Python loop of

@@ -8,11 +8,12 @@ There is no CPU fallback: without the CUDA library or a GPU every compute call r
 from .indicator import ExperimentalIndicatorVariogram, IndicatorKriging, IndicatorVariogramData
 from .kriging import indicator_kriging, interpolate_points, ordinary_kriging, simple_kriging
 from .models import TheoreticalVariogram
-from .variogram import (DirectionalVariogram, ExperimentalVariogram, build_experimental_variogram,
-                        calculate_covariance, calculate_semivariance)
+from .variogram import (DirectionalVariogram, ExperimentalVariogram, VariogramCloud, build_experimental_variogram,
+                        calculate_covariance, calculate_semivariance, point_cloud_semivariance)
 
 __version__ = "0.1.0"
 __all__ = ["ExperimentalVariogram", "DirectionalVariogram", "build_experimental_variogram",
-           "calculate_semivariance", "calculate_covariance", "TheoreticalVariogram",
+           "calculate_semivariance", "calculate_covariance", "point_cloud_semivariance", "VariogramCloud",
+           "TheoreticalVariogram",
            "ordinary_kriging", "simple_kriging", "interpolate_points", "indicator_kriging",
            "ExperimentalIndicatorVariogram", "IndicatorVariogramData", "IndicatorKriging"]

@@ -18,7 +18,7 @@ STATUS_OK, STATUS_SINGULAR, STATUS_NEGATIVE_VARIANCE = 0, 1, 2
 
 EXPORTS = ("pib_last_error", "pib_version", "pib_device_sm_count", "pib_variogram_device",
            "pib_variogram_host", "pib_krige_device", "pib_krige_host", "pib_gamma_host",
-           "pib_fp64_peak_tflops", "pib_last_kernel_ms")
+           "pib_fp64_peak_tflops", "pib_last_kernel_ms", "pib_variogram_cloud_host")
 
 _lib = None
 
@@ -50,6 +50,7 @@ def load():
     L.pib_gamma_host.argtypes = [i32, f64, f64, f64, dp, i64, dp]
     L.pib_fp64_peak_tflops.argtypes = [dp]
     L.pib_last_kernel_ms.argtypes = [i32, dp, dp]
+    L.pib_variogram_cloud_host.argtypes = [dp, i64, dp, dp, i32, dp, i32, dp, dp]
     for name in EXPORTS:
         getattr(L, name).restype = getattr(L, name).restype or i32
     L.pib_last_error.restype = ctypes.c_char_p
@@ -89,6 +90,24 @@ def variogram_host(xyz, edges, lower=None, W=None, shard=(0, 1)):
                               _host_ptr(cnt), ctypes.cast(ctypes.byref(evaluated), ctypes.c_void_p))
     check(rc, "pib_variogram_host")
     return dict(sum_sq=ssq, sum_prod=spr, sum_val=sva, count=cnt, pairs_evaluated=int(evaluated.value))
+
+
+def variogram_cloud_host(xyz, edges, lower=None, W=None):
+    """Per-lag lists of (z_i - z_j)^2 over ordered pairs, in the reference's (i, j) order.
+    One direction at most (``W`` = 4 doubles).  Returns a list of float64 arrays, one per lag."""
+    L = load()
+    xyz, edges = _f64(xyz), _f64(edges)
+    n, n_lags = xyz.shape[0], edges.shape[0]
+    Wc = None if W is None else _f64(np.asarray(W).reshape(1, 4))
+    lower_c = None if lower is None else _f64(lower)
+    counts = variogram_host(xyz, edges, lower=lower_c, W=Wc)["count"].reshape(-1)
+    offsets = np.zeros(n_lags + 1, dtype=np.int64)
+    np.cumsum(2 * counts, out=offsets[1:])
+    values = np.empty(int(offsets[-1]), dtype=np.float64)
+    rc = L.pib_variogram_cloud_host(_host_ptr(xyz), n, _host_ptr(edges), _host_ptr(lower_c), n_lags, _host_ptr(Wc),
+                                    0 if W is None else 1, _host_ptr(offsets), _host_ptr(values))
+    check(rc, "pib_variogram_cloud_host")
+    return [values[offsets[b]:offsets[b + 1]] for b in range(n_lags)]
 
 
 def variogram_device(xyz_t, edges, lower=None, W=None, shard=(0, 1), want_pairs=False):

@@ -67,6 +67,9 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
                      const double *W, int n_dirs, int shard_index, int shard_count,
                      double *d_sum_sq, double *d_sum_prod, double *d_sum_val, int64_t *d_count,
                      int64_t *pairs_evaluated, cudaStream_t stream);
+int variogram_cloud_device(const double *d_xyz, int64_t n, const double *edges, const double *lower, int n_lags,
+                           const double *W, int n_dirs, const int64_t *lag_offsets, double *d_values,
+                           cudaStream_t stream);
 int krige_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
                  const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
                  double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, cudaStream_t stream);
@@ -140,6 +143,35 @@ int pib_variogram_host(const double *xyz, int64_t n, const double *edges, const 
             if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
             if (e != cudaSuccess) { set_error(std::string("variogram: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; }
         }
+    }
+    cudaStreamSynchronize(stream);
+    cudaStreamDestroy(stream);
+    return rc;
+}
+
+int pib_variogram_cloud_host(const double *xyz, int64_t n, const double *edges, const double *lower, int n_lags,
+                             const double *W, int n_dirs, const int64_t *lag_offsets, double *values)
+{
+    PIB_CHECK((xyz || n == 0) && edges && lag_offsets, PIB_ERR_INVALID, "cloud: NULL pointer");
+    PIB_CHECK(n >= 0 && n_lags >= 1, PIB_ERR_INVALID, "cloud: need n >= 0 and at least one lag");
+    const int64_t total = lag_offsets[n_lags];
+    PIB_CHECK(total >= 0 && (values || total == 0), PIB_ERR_INVALID, "cloud: values is NULL");
+    if (n < 2 || total == 0) return PIB_OK;
+    cudaStream_t stream;
+    PIB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    int rc;
+    {
+        Scratch ws(stream);
+        double *d_xyz, *d_values;
+        rc = ws.alloc(&d_xyz, (size_t)n * 3);
+        if (rc == PIB_OK) rc = ws.alloc(&d_values, (size_t)total);
+        cudaError_t e = cudaSuccess;
+        if (rc == PIB_OK) e = cudaMemcpyAsync(d_xyz, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, stream);
+        if (rc == PIB_OK && e == cudaSuccess)
+            rc = variogram_cloud_device(d_xyz, n, edges, lower, n_lags, W, n_dirs, lag_offsets, d_values, stream);
+        if (rc == PIB_OK && e == cudaSuccess) e = cudaMemcpyAsync(values, d_values, sizeof(double) * total, cudaMemcpyDeviceToHost, stream);
+        if (rc == PIB_OK && e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { set_error(std::string("cloud: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; }
     }
     cudaStreamSynchronize(stream);
     cudaStreamDestroy(stream);

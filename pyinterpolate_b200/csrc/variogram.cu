@@ -1069,4 +1069,117 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
     return PIB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Variogram point cloud: per lag, the squared differences (z_i - z_j)^2 of the ORDERED
+// pairs in the reference's order — rows i ascending, within a row j ascending, i.e. np.where on the
+// N x N mask (semivariogram/experimental/functions/general.py:13-75, :150-233; ellipse:
+// functions/directional.py:83-134, :468-530).  Output is O(pairs), so this is for small N; it works on the
+// points in the caller's order with one thread per row i (no tiling, no culling).
+//   pass 1: counts[b][i] = ordered pairs of row i in lag b;  exclusive scan along i per lag
+//   pass 2: values[lag_offset[b] + scan[b][i] + k] = (z_i - z_j)^2 for the k-th j of row i in lag b
+// ---------------------------------------------------------------------------------------------
+template <bool WRITE>
+__global__ void cloud_kernel(const double *__restrict__ xyz, int64_t n, const double *__restrict__ up_d2,
+                             const double *__restrict__ low_d2, int n_lags, bool ellipse, double w00, double w01,
+                             double w10, double w11, unsigned long long *__restrict__ cursor /* [n_lags][n] */,
+                             double *__restrict__ values)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double xi = xyz[3 * i], yi = xyz[3 * i + 1], zi = xyz[3 * i + 2];
+    for (int64_t j = 0; j < n; ++j) {
+        if (j == i) continue;
+        double d2;
+        if (ellipse) {
+            const double dx = __dsub_rn(xyz[3 * j], xi), dy = __dsub_rn(xyz[3 * j + 1], yi);
+            const double n0 = __fma_rn(w01, dy, __dmul_rn(w00, dx));
+            const double n1 = __fma_rn(w11, dy, __dmul_rn(w10, dx));
+            d2 = __dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1));
+        } else {
+            const double dx = __dsub_rn(xi, xyz[3 * j]), dy = __dsub_rn(yi, xyz[3 * j + 1]);
+            d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        }
+        if (!(d2 > 0.0)) continue;
+        for (int b = 0; b < n_lags; ++b) {
+            if (d2 <= up_d2[b] && d2 > low_d2[b]) {
+                unsigned long long *c = cursor + (size_t)b * n + i;
+                if (WRITE) {
+                    const double dz = zi - xyz[3 * j + 2];
+                    values[(*c)++] = dz * dz;
+                } else ++(*c);
+            }
+        }
+    }
+}
+
+// exclusive scan of each lag's row counts, shifted by the lag's global offset (one CTA per lag)
+__global__ void cloud_scan_kernel(unsigned long long *cursor, int64_t n, const int64_t *__restrict__ lag_offsets)
+{
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    unsigned long long *row = cursor + (size_t)blockIdx.x * n;
+    if (threadIdx.x == 0) s_carry = (unsigned long long)lag_offsets[blockIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = 0; base < n; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        const unsigned long long v = i < n ? row[i] : 0ull;
+        unsigned long long incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0ull, wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            s_warp[lane] = wi - w;                               // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const unsigned long long carry = s_carry;
+        if (i < n) row[i] = carry + s_warp[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + s_warp[warp] + incl;
+        __syncthreads();
+    }
+}
+
+int variogram_cloud_device(const double *d_xyz, int64_t n, const double *edges, const double *lower, int n_lags,
+                           const double *W, int n_dirs, const int64_t *lag_offsets, double *d_values,
+                           cudaStream_t stream)
+{
+    PIB_CHECK(n >= 0 && n_lags >= 1 && edges && lag_offsets, PIB_ERR_INVALID, "cloud: bad arguments");
+    PIB_CHECK(n_dirs == 0 || (n_dirs == 1 && W), PIB_ERR_INVALID, "cloud: one direction at a time");
+    if (n < 2) return PIB_OK;
+    Scratch ws(stream);
+    std::vector<double> up(n_lags), low(n_lags);
+    for (int b = 0; b < n_lags; ++b) {
+        up[b] = sq_threshold(edges[b]);
+        low[b] = sq_threshold((n_dirs > 0 && lower) ? lower[b] : (b ? edges[b - 1] : 0.0));
+    }
+    double *d_up, *d_low;
+    int64_t *d_off;
+    unsigned long long *d_cursor;
+    PIB_TRY(ws.alloc(&d_up, n_lags)); PIB_TRY(ws.alloc(&d_low, n_lags)); PIB_TRY(ws.alloc(&d_off, n_lags));
+    PIB_TRY(ws.alloc(&d_cursor, (size_t)n_lags * n));
+    PIB_CUDA(cudaMemcpyAsync(d_up, up.data(), n_lags * sizeof(double), cudaMemcpyHostToDevice, stream));
+    PIB_CUDA(cudaMemcpyAsync(d_low, low.data(), n_lags * sizeof(double), cudaMemcpyHostToDevice, stream));
+    PIB_CUDA(cudaMemcpyAsync(d_off, lag_offsets, n_lags * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+    PIB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long) * n_lags * n, stream));
+    const double w00 = n_dirs ? W[0] : 0, w01 = n_dirs ? W[1] : 0, w10 = n_dirs ? W[2] : 0, w11 = n_dirs ? W[3] : 0;
+    const int grid = (int)((n + 127) / 128);
+    cloud_kernel<false><<<grid, 128, 0, stream>>>(d_xyz, n, d_up, d_low, n_lags, n_dirs > 0, w00, w01, w10, w11, d_cursor, nullptr);
+    PIB_CUDA(cudaGetLastError());
+    cloud_scan_kernel<<<n_lags, 1024, 0, stream>>>(d_cursor, n, d_off);
+    PIB_CUDA(cudaGetLastError());
+    cloud_kernel<true><<<grid, 128, 0, stream>>>(d_xyz, n, d_up, d_low, n_lags, n_dirs > 0, w00, w01, w10, w11, d_cursor, d_values);
+    PIB_CUDA(cudaGetLastError());
+    return PIB_OK;
+}
+
 }  // namespace pib

@@ -9,9 +9,13 @@ Mirrors (file:line relative to /root/reference/src/pyinterpolate/):
 
 One kernel pass yields semivariance, covariance and pair counts together, so the class computes
 both curves from a single launch where the reference runs its whole pipeline twice.
+The point cloud (``as_cloud=True`` / ``point_cloud_semivariance`` / ``VariogramCloud``) comes from a
+second kernel that writes (z_i - z_j)^2 per ordered pair in the reference's order.
 Not built yet (raise NotImplementedError, there is no CPU fallback): the triangle selection
-method ('t'), custom_weights, and the point-cloud output (as_cloud).
+method ('t') and custom_weights.
 """
+from collections import OrderedDict
+
 import numpy as np
 
 from . import _lib, core
@@ -111,6 +115,31 @@ def calculate_covariance(ds, step_size=None, max_range=None, direction=None, tol
     return np.column_stack([lags, cov, npairs])
 
 
+def point_cloud_semivariance(ds, step_size=None, max_range=None, direction=None, tolerance=None,
+                             dir_neighbors_selection_method="t", custom_bins=None, custom_weights=None):
+    """``{lag: [(z_i - z_j)^2 for every ordered pair in the lag]}`` — experimental_semivariogram.py
+    (point_cloud_semivariance) -> functions/general.py:13-75 / functions/directional.py:83-134.
+    Values come in the reference's order (i ascending, then j ascending); an empty lag maps to ``[]``.
+    ``custom_weights`` are ignored for clouds, like in the reference."""
+    points = core.variogram_points(ds)
+    core.validate_bins(step_size, max_range, custom_bins)
+    core.validate_semivariance_weights(points, custom_weights)
+    core.validate_direction_and_tolerance(direction, tolerance)
+    lags = core.get_lags(step_size, max_range, custom_bins)
+    lags64 = np.ascontiguousarray(lags, dtype=np.float64)
+    xyz = np.ascontiguousarray(points, dtype=np.float64)
+    if direction is not None and tolerance is not None:
+        _check_method(direction, dir_neighbors_selection_method, None)
+        W = core.define_whitening_matrix(direction, tolerance).reshape(4)
+        clouds = _lib.variogram_cloud_host(xyz, lags64, lower=core.ellipse_lower_limits(lags64), W=W)
+    else:
+        clouds = _lib.variogram_cloud_host(xyz, lags64)
+    out = OrderedDict()
+    for lag, values in zip(lags, clouds):
+        out[lag] = values if len(values) else []
+    return out
+
+
 class ExperimentalVariogram:
     """classes/experimental_variogram.py:16-402: attributes ``lags``, ``semivariances``,
     ``covariances``, ``points_per_lag``, ``variance``, ``direction``, ``tolerance``, ``step_size``,
@@ -119,9 +148,6 @@ class ExperimentalVariogram:
     def __init__(self, ds, step_size=None, max_range=None, direction=None, tolerance=None,
                  dir_neighbors_selection_method="t", custom_bins=None, custom_weights=None,
                  is_semivariance=True, is_covariance=True, as_cloud=False):
-        if as_cloud:
-            raise NotImplementedError("as_cloud=True (variogram point cloud) is not implemented in "
-                                      "pyinterpolate_b200 yet (SURVEY.md §8f-2)")
         self.ds = core.variogram_points(ds)
         self.lags = None if custom_bins is None else custom_bins
         self.points_per_lag = None
@@ -146,6 +172,12 @@ class ExperimentalVariogram:
                 self.semivariances = sem
             if is_covariance:
                 self.covariances = cov
+        if as_cloud:
+            self.point_cloud_semivariances = point_cloud_semivariance(
+                self.ds, step_size, max_range, direction, tolerance, dir_neighbors_selection_method,
+                self.lags, custom_weights)
+            if self.lags is None:
+                self.lags = core.get_lags(step_size, max_range, custom_bins)
         self.model = self.get_model_params()
 
     def get_model_params(self):
@@ -223,3 +255,44 @@ class DirectionalVariogram:
         raise KeyError(f'Given direction is not possible to retrieve, pass one direction from a '
                        f'possible_variograms: {self.possible_variograms} or leave None to get a dictionary with all '
                        f'possible variograms.')
+
+
+class VariogramCloud:
+    """classes/variogram_cloud.py:82-504 (data side: ``semivariances``, ``lags``, ``points_per_lag``,
+    ``average_semivariance``, ``describe``, ``experimental_semivariances``, ``remove_outliers``); plots stay
+    with the reference."""
+
+    def __init__(self, ds, step_size=None, max_range=None, direction=None, tolerance=None,
+                 dir_neighbors_selection_method='t', custom_bins=None, custom_weights=None):
+        self._experimental_variogram = ExperimentalVariogram(
+            ds=ds, step_size=step_size, max_range=max_range, direction=direction, tolerance=tolerance,
+            dir_neighbors_selection_method=dir_neighbors_selection_method, custom_bins=custom_bins,
+            custom_weights=custom_weights, is_semivariance=True, is_covariance=False, as_cloud=True)
+        self.semivariances = self._experimental_variogram.point_cloud_semivariances
+        self.lags = self._experimental_variogram.lags
+        self.direction = direction
+        self.tolerance = tolerance
+        self.points_per_lag = [len(self.semivariances[lag]) for lag in self.lags]
+
+    def experimental_semivariances(self):
+        return self._experimental_variogram
+
+    def average_semivariance(self):
+        """``[lag, mean(cloud) / 2, count]`` per lag (variogram_cloud.py:213-232)."""
+        return np.array([[lag, np.mean(self.semivariances[lag]) / 2, len(self.semivariances[lag])]
+                         for lag in self.lags])
+
+    def describe(self, as_dataframe=False):
+        """variogram_cloud.py:234-294."""
+        from scipy.stats import kurtosis, skew
+        stats = {}
+        for lag in self.lags:
+            data = self.semivariances[lag]
+            stats[lag] = {'count': len(data), 'mean': np.mean(data) / 2, 'std': np.std(data), 'min': np.min(data),
+                          'max': np.max(data), '25%': np.quantile(data, q=0.25), 'median': np.median(data),
+                          '75%': np.quantile(data, q=0.75), 'skewness': skew(data), 'kurtosis': kurtosis(data),
+                          'lag': lag}
+        if as_dataframe:
+            import pandas as pd
+            return pd.DataFrame(stats)
+        return stats
