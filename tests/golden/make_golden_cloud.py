@@ -30,9 +30,9 @@ def main():
     g["arm_lags"], g["arm_sizes"], g["arm_values"] = pack(point_cloud_semivariance(arm, step_size=1, max_range=6))
     g["arm_e_lags"], g["arm_e_sizes"], g["arm_e_values"] = pack(point_cloud_semivariance(
         arm, step_size=1.5, max_range=6, direction=15, tolerance=0.25, dir_neighbors_selection_method="e"))
-    pts = dem_like_field(700, seed=51)
-    g["f700_lags"], g["f700_sizes"], g["f700_values"] = pack(point_cloud_semivariance(pts, step_size=4000, max_range=40000))
-    g["f700_e_lags"], g["f700_e_sizes"], g["f700_e_values"] = pack(point_cloud_semivariance(
+    pts = dem_like_field(350, seed=51)
+    g["f350_lags"], g["f350_sizes"], g["f350_values"] = pack(point_cloud_semivariance(pts, step_size=4000, max_range=40000))
+    g["f350_e_lags"], g["f350_e_sizes"], g["f350_e_values"] = pack(point_cloud_semivariance(
         pts, step_size=4000, max_range=40000, direction=45, tolerance=0.3, dir_neighbors_selection_method="e"))
     sparse = dem_like_field(30, extent=1000.0, seed=52)          # has empty lags
     g["sparse_lags"], g["sparse_sizes"], g["sparse_values"] = pack(point_cloud_semivariance(sparse, step_size=5.0, max_range=100.0))

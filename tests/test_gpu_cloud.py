@@ -38,10 +38,10 @@ def test_cloud_golden(pib, golden, gold):
     _check(pib.point_cloud_semivariance(arm, step_size=1, max_range=6), gold, "arm")
     _check(pib.point_cloud_semivariance(arm, step_size=1.5, max_range=6, direction=15, tolerance=0.25,
                                         dir_neighbors_selection_method="e"), gold, "arm_e")
-    pts = dem_like_field(700, seed=51)
-    _check(pib.point_cloud_semivariance(pts, step_size=4000, max_range=40000), gold, "f700")
+    pts = dem_like_field(350, seed=51)
+    _check(pib.point_cloud_semivariance(pts, step_size=4000, max_range=40000), gold, "f350")
     _check(pib.point_cloud_semivariance(pts, step_size=4000, max_range=40000, direction=45, tolerance=0.3,
-                                        dir_neighbors_selection_method="e"), gold, "f700_e")
+                                        dir_neighbors_selection_method="e"), gold, "f350_e")
     sparse = dem_like_field(30, extent=1000.0, seed=52)
     cloud = pib.point_cloud_semivariance(sparse, step_size=5.0, max_range=100.0)
     _check(cloud, gold, "sparse")
