@@ -16,7 +16,9 @@ MODEL_IDS = {"circular": 0, "cubic": 1, "exponential": 2, "gaussian": 3,
 KRIGE_ORDINARY, KRIGE_SIMPLE = 0, 1
 STATUS_OK, STATUS_SINGULAR, STATUS_NEGATIVE_VARIANCE = 0, 1, 2
 
-EXPORTS = ("pib_last_error", "pib_version", "pib_device_sm_count", "pib_variogram_device",
+STATUS_TOO_MANY_NEIGHBORS = 3
+
+EXPORTS = ("pib_krige_ex_device", "pib_krige_ex_host", "pib_last_error", "pib_version", "pib_device_sm_count", "pib_variogram_device",
            "pib_variogram_host", "pib_krige_device", "pib_krige_host", "pib_gamma_host",
            "pib_fp64_peak_tflops", "pib_last_kernel_ms", "pib_variogram_cloud_host")
 
@@ -47,6 +49,9 @@ def load():
     kr_args = [dp, i64, dp, i32, dp, dp, i64, i32, i32, f64, i32, dp, dp, dp]
     L.pib_krige_device.argtypes = kr_args + [ctypes.c_void_p]
     L.pib_krige_host.argtypes = kr_args
+    kr_ex = kr_args[:11] + [f64, f64, f64, i32] + kr_args[11:]
+    L.pib_krige_ex_device.argtypes = kr_ex + [ctypes.c_void_p]
+    L.pib_krige_ex_host.argtypes = kr_ex
     L.pib_gamma_host.argtypes = [i32, f64, f64, f64, dp, i64, dp]
     L.pib_fp64_peak_tflops.argtypes = [dp]
     L.pib_last_kernel_ms.argtypes = [i32, dp, dp]
@@ -137,8 +142,9 @@ def variogram_device(xyz_t, edges, lower=None, W=None, shard=(0, 1), want_pairs=
 
 
 def krige_host(known, unknown, model, params, mode, k, process_mean=0.0, values=None,
-               want_neighbors=False):
-    """Host-buffer call. ``params`` is ``[n_sets, 3]`` (nugget, sill, rang).
+               want_neighbors=False, neighbors_range=0.0, direction=None, max_tick=5.0, use_all=False):
+    """Host-buffer call. ``params`` is ``[n_sets, 3]`` (nugget, sill, rang).  ``direction`` (degrees) switches to
+    the directional neighbour selection within ``neighbors_range``.
     Returns (out[n_sets, m, 4], nbr_idx[m, k] or None, status[n_sets, m])."""
     L = load()
     known, unknown = _f64(known), _f64(unknown).reshape(-1, 2)
@@ -148,10 +154,11 @@ def krige_host(known, unknown, model, params, mode, k, process_mean=0.0, values=
     out = np.zeros((n_sets, m, 4))
     status = np.zeros((n_sets, m), dtype=np.uint8)
     idx = np.full((m, k), -1, dtype=np.int32) if want_neighbors else None
-    rc = L.pib_krige_host(_host_ptr(known), n, _host_ptr(values_c), n_sets, _host_ptr(params), _host_ptr(unknown), m,
-                          int(model), int(mode), float(process_mean), int(k), _host_ptr(out), _host_ptr(idx),
-                          _host_ptr(status))
-    check(rc, "pib_krige_host")
+    rc = L.pib_krige_ex_host(_host_ptr(known), n, _host_ptr(values_c), n_sets, _host_ptr(params), _host_ptr(unknown), m,
+                             int(model), int(mode), float(process_mean), int(k), float(neighbors_range),
+                             float("nan") if direction is None else float(direction), float(max_tick),
+                             1 if use_all else 0, _host_ptr(out), _host_ptr(idx), _host_ptr(status))
+    check(rc, "pib_krige_ex_host")
     return out, idx, status
 
 

@@ -1,4 +1,5 @@
 // extern "C" surface of libpyinterp_b200.so — see include/pyinterp_b200.h for the contract.
+#include <cmath>
 #include <mutex>
 #include <string>
 
@@ -72,6 +73,7 @@ int variogram_cloud_device(const double *d_xyz, int64_t n, const double *edges, 
                            cudaStream_t stream);
 int krige_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
                  const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
+                 double neighbors_range, double direction, double max_tick, int use_all,
                  double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, cudaStream_t stream);
 int gamma_device(int model, double nugget, double sill, double rang, const double *d_h, int64_t n, double *d_out,
                  cudaStream_t stream);
@@ -178,18 +180,37 @@ int pib_variogram_cloud_host(const double *xyz, int64_t n, const double *edges, 
     return rc;
 }
 
+int pib_krige_ex_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
+                        const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
+                        double neighbors_range, double direction, double max_tick, int use_all,
+                        double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, void *stream)
+{
+    PIB_CHECK(d_known && (d_unknown || m == 0) && (d_out || m == 0), PIB_ERR_INVALID, "krige: NULL pointer");
+    return krige_device(d_known, n, d_values, n_sets, params, d_unknown, m, model, mode, process_mean, k,
+                        neighbors_range, direction, max_tick, use_all, d_out, d_nbr_idx, d_status,
+                        static_cast<cudaStream_t>(stream));
+}
+
 int pib_krige_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
                      const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
                      double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, void *stream)
 {
-    PIB_CHECK(d_known && (d_unknown || m == 0) && (d_out || m == 0), PIB_ERR_INVALID, "krige: NULL pointer");
-    return krige_device(d_known, n, d_values, n_sets, params, d_unknown, m, model, mode, process_mean, k, d_out,
-                        d_nbr_idx, d_status, static_cast<cudaStream_t>(stream));
+    return pib_krige_ex_device(d_known, n, d_values, n_sets, params, d_unknown, m, model, mode, process_mean, k, 0.0,
+                               nan(""), 0.0, 0, d_out, d_nbr_idx, d_status, stream);
 }
 
 int pib_krige_host(const double *known, int64_t n, const double *values, int n_sets, const double *params,
                    const double *unknown, int64_t m, int model, int mode, double process_mean, int k, double *out,
                    int32_t *nbr_idx, uint8_t *status)
+{
+    return pib_krige_ex_host(known, n, values, n_sets, params, unknown, m, model, mode, process_mean, k, 0.0, nan(""),
+                             0.0, 0, out, nbr_idx, status);
+}
+
+int pib_krige_ex_host(const double *known, int64_t n, const double *values, int n_sets, const double *params,
+                      const double *unknown, int64_t m, int model, int mode, double process_mean, int k,
+                      double neighbors_range, double direction, double max_tick, int use_all, double *out,
+                      int32_t *nbr_idx, uint8_t *status)
 {
     PIB_CHECK(known && (unknown || m == 0) && (out || m == 0), PIB_ERR_INVALID, "krige: NULL pointer");
     PIB_CHECK(n >= 1 && m >= 0 && k >= 1 && n_sets >= 1, PIB_ERR_INVALID, "krige: need n >= 1, m >= 0, k >= 1");
@@ -217,8 +238,8 @@ int pib_krige_host(const double *known, int64_t n, const double *values, int n_s
             if (e != cudaSuccess) { set_error(std::string("krige: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; }
         }
         if (rc == PIB_OK)
-            rc = krige_device(d_known, n, d_values, n_sets, params, d_unknown, m, model, mode, process_mean, k, d_out,
-                              d_idx, d_status, stream);
+            rc = krige_device(d_known, n, d_values, n_sets, params, d_unknown, m, model, mode, process_mean, k,
+                              neighbors_range, direction, max_tick, use_all, d_out, d_idx, d_status, stream);
         if (rc == PIB_OK) {
             e = cudaMemcpyAsync(out, d_out, sizeof(double) * 4 * n_sets * m, cudaMemcpyDeviceToHost, stream);
             if (e == cudaSuccess && nbr_idx) e = cudaMemcpyAsync(nbr_idx, d_idx, sizeof(int32_t) * m * k, cudaMemcpyDeviceToHost, stream);

@@ -58,19 +58,85 @@ static __device__ void warp_bitonic_sort(Cand *buf, int n2, int lane)
     __syncwarp();
 }
 
+// Running "k smallest by (distance, original index)" of one warp: best[0, k2) sorted, best[k2, 2 k2) staging.
+struct TopK {
+    Cand *best;
+    int k2, kk, staged;
+    Cand thr;                       // current kk-th best
+};
+
+static __device__ __forceinline__ Cand cand_inf()
+{
+    Cand c; c.d = INFINITY; c.orig = 0x7fffffff; c.pos = -1;
+    return c;
+}
+
+static __device__ void topk_init(TopK &t, Cand *buf, int k2, int kk, int lane)
+{
+    t.best = buf; t.k2 = k2; t.kk = kk; t.staged = 0; t.thr = cand_inf();
+    for (int i = lane; i < 2 * k2; i += 32) buf[i] = cand_inf();
+    __syncwarp();
+}
+
+static __device__ void topk_merge(TopK &t, int lane)
+{
+    warp_bitonic_sort(t.best, 2 * t.k2, lane);
+    for (int i = t.k2 + lane; i < 2 * t.k2; i += 32) t.best[i] = cand_inf();
+    __syncwarp();
+    t.staged = 0;
+    t.thr = t.best[t.kk - 1];
+}
+
+// warp-collective: every lane offers one candidate (valid = false for idle lanes)
+static __device__ void topk_offer(TopK &t, const Cand &c, bool valid, int lane)
+{
+    bool pass = valid && cand_less(c, t.thr);
+    unsigned mask = __ballot_sync(0xffffffffu, pass);
+    if (mask == 0u) return;
+    if (t.staged + __popc(mask) > t.k2) {                       // staging full: merge, then re-test
+        topk_merge(t, lane);
+        pass = pass && cand_less(c, t.thr);
+        mask = __ballot_sync(0xffffffffu, pass);
+    }
+    if (pass) t.best[t.k2 + t.staged + __popc(mask & ((1u << lane) - 1u))] = c;
+    t.staged += __popc(mask);
+    __syncwarp();
+}
+
+static __device__ void topk_finish(TopK &t, int lane)
+{
+    if (t.staged > 0) topk_merge(t, lane);
+}
+
 struct KnnParams {
     GridIndex g;
     const double *unknown;      // [m][2]
     const int32_t *order;       // [count] location ids to process (cell-sorted)
     int64_t count;
-    int kk;                     // min(k, n)
-    int k2;                     // power of two >= kk
+    int kk;                     // min(k, n) (row stride of nbr_pos / nbr_d)
+    int k2;                     // power of two >= max(kk, 32)
     int r0;                     // first ring radius in cells
     int32_t *nbr_pos;           // [count][kk]
     double *nbr_d;              // [count][kk]
     int32_t *nbr_idx;           // optional [m][k] (original rows, -1 padded), indexed by location id
     int k;
+    // directional / range-limited selection (transform/select_points.py:104-257)
+    int32_t *nbr_count;         // [count] neighbours found (directional kernel)
+    double range, direction;
+    int last_tol;               // largest angular tolerance tried (degrees)
+    int use_all;
 };
+
+static __device__ __forceinline__ Cand make_cand(const GridIndex &g, int pos, double ux, double uy)
+{
+    // cdist: sqrt(dx*dx + dy*dy), nothing fused (transform/select_points.py:85)
+    Cand c;
+    const double dx = __dsub_rn(ux, g.x[pos]), dy = __dsub_rn(uy, g.y[pos]);
+    c.d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    c.orig = g.orig[pos];
+    c.pos = pos;
+    return c;
+}
 
 __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const KnnParams p)
 {
@@ -79,20 +145,15 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const KnnParams p)
     const int64_t slot = (int64_t)blockIdx.x * KNN_WARPS + warp;
     if (slot >= p.count) return;
     const int k2 = p.k2, kk = p.kk;
-    Cand *best = reinterpret_cast<Cand *>(smem_raw) + (size_t)warp * 2 * k2;   // [0,k2) sorted best, [k2,2k2) staging
     const GridIndex &g = p.g;
+    TopK top;
+    topk_init(top, reinterpret_cast<Cand *>(smem_raw) + (size_t)warp * 2 * k2, k2, kk, lane);
 
     const int32_t q = p.order[slot];
     const double ux = p.unknown[2 * (int64_t)q], uy = p.unknown[2 * (int64_t)q + 1];
     const int cx = clampi((int)floor((ux - g.x0) * g.inv_h), 0, g.gx - 1);
     const int cy = clampi((int)floor((uy - g.y0) * g.inv_h), 0, g.gy - 1);
 
-    Cand inf_c; inf_c.d = INFINITY; inf_c.orig = 0x7fffffff; inf_c.pos = -1;
-    for (int t = lane; t < 2 * k2; t += 32) best[t] = inf_c;
-    __syncwarp();
-
-    int staged = 0;                 // entries in the staging half
-    Cand thr = inf_c;               // current k-th best (best[kk-1])
     int r_done = -1;                // rings [0, r_done] scanned
     int r = p.r0;
     const double slack = 1e-9 * (fabs(ux) + fabs(uy) + fabs(g.x0) + fabs(g.y0) + g.h * (g.gx + g.gy));
@@ -112,45 +173,14 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const KnnParams p)
                 const int s0 = g.cell_start[yy * g.gx + xa], s1 = g.cell_start[yy * g.gx + xb + 1];
                 for (int base = s0; base < s1; base += 32) {
                     const int pos = base + lane;
-                    Cand c = inf_c;
-                    if (pos < s1) {
-                        // cdist: sqrt(dx*dx + dy*dy), nothing fused (transform/select_points.py:85)
-                        const double dx = __dsub_rn(ux, g.x[pos]), dy = __dsub_rn(uy, g.y[pos]);
-                        c.d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-                        c.orig = g.orig[pos];
-                        c.pos = pos;
-                    }
-                    const bool pass = (pos < s1) && cand_less(c, thr);
-                    const unsigned mask = __ballot_sync(0xffffffffu, pass);
-                    const int n_pass = __popc(mask);
-                    if (n_pass == 0) continue;
-                    if (staged + n_pass > k2) {                      // staging full: merge first
-                        warp_bitonic_sort(best, 2 * k2, lane);
-                        for (int t = k2 + lane; t < 2 * k2; t += 32) best[t] = inf_c;
-                        __syncwarp();
-                        staged = 0;
-                        thr = best[kk - 1];
-                        // re-test against the tighter threshold
-                        const bool pass2 = pass && cand_less(c, thr);
-                        const unsigned mask2 = __ballot_sync(0xffffffffu, pass2);
-                        if (pass2) best[k2 + __popc(mask2 & ((1u << lane) - 1u))] = c;
-                        staged = __popc(mask2);
-                    } else {
-                        if (pass) best[k2 + staged + __popc(mask & ((1u << lane) - 1u))] = c;
-                        staged += n_pass;
-                    }
-                    __syncwarp();
+                    Cand c = cand_inf();
+                    if (pos < s1) c = make_cand(g, pos, ux, uy);
+                    topk_offer(top, c, pos < s1, lane);
                 }
             }
         }
         r_done = r;
-        if (staged > 0) {
-            warp_bitonic_sort(best, 2 * k2, lane);
-            for (int t = k2 + lane; t < 2 * k2; t += 32) best[t] = inf_c;
-            __syncwarp();
-            staged = 0;
-            thr = best[kk - 1];
-        }
+        topk_finish(top, lane);
         const bool whole_grid = (x_lo == 0 && y_lo == 0 && x_hi == g.gx - 1 && y_hi == g.gy - 1);
         if (whole_grid) break;
         // radius around the location that the scanned square is guaranteed to cover
@@ -160,17 +190,127 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const KnnParams p)
         if (cy - r > 0) rho = fmin(rho, uy - (g.y0 + (cy - r) * g.h));
         if (cy + r < g.gy - 1) rho = fmin(rho, (g.y0 + (cy + r + 1) * g.h) - uy);
         rho -= slack;
-        if (thr.d <= rho) break;                                 // k-th neighbour is inside the covered disc
-        if (isinf(thr.d)) r = 2 * r + 1;                          // fewer than k found so far
-        else r = max(r + 1, min((int)ceil(thr.d * g.inv_h) + 1, 2 * r + 1));
+        if (top.thr.d <= rho) break;                             // k-th neighbour is inside the covered disc
+        if (isinf(top.thr.d)) r = 2 * r + 1;                      // fewer than k found so far
+        else r = max(r + 1, min((int)ceil(top.thr.d * g.inv_h) + 1, 2 * r + 1));
     }
 
     for (int t = lane; t < kk; t += 32) {
-        p.nbr_pos[slot * kk + t] = best[t].pos;
-        p.nbr_d[slot * kk + t] = best[t].d;
+        p.nbr_pos[slot * kk + t] = top.best[t].pos;
+        p.nbr_d[slot * kk + t] = top.best[t].d;
     }
     if (p.nbr_idx)
-        for (int t = lane; t < p.k; t += 32) p.nbr_idx[(int64_t)q * p.k + t] = t < kk ? best[t].orig : -1;
+        for (int t = lane; t < p.k; t += 32) p.nbr_idx[(int64_t)q * p.k + t] = t < kk ? top.best[t].orig : -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Directional neighbour selection (models fitted on a directional variogram carry a direction):
+//   transform/select_points.py:104-168  select_kriging_data_from_direction
+//   transform/select_points.py:171-257  select_possible_neighbors_angular
+//   distance/angular.py:106-185         calc_angles, calculate_angular_difference
+// Points within `range` are kept, sorted by distance, and filtered by their angular difference to the
+// model direction; the tolerance starts at 1 degree and is widened by 1 degree until at least k
+// points qualify or it exceeds max_tick.  The result has min(k, qualifying) rows (all qualifying rows
+// with use_all), possibly none.  Two passes over the cells that intersect the range disc:
+// pass 1 histograms the smallest integer tolerance each in-range point needs, pass 2 selects.
+// ---------------------------------------------------------------------------------------------
+static __device__ __forceinline__ double py_mod_2pi(double x)
+{
+    const double two_pi = 2.0 * 3.141592653589793;
+    double m = fmod(x, two_pi);
+    if (m != 0.0 && m < 0.0) m += two_pi;                       // numpy's floored modulo
+    return m;
+}
+
+static __device__ __forceinline__ double angular_difference(double ux, double uy, double kx, double ky, double direction)
+{
+    const double rad2deg = 180.0 / 3.141592653589793, deg2rad = 3.141592653589793 / 180.0;
+    const double ang = py_mod_2pi(atan2(ky - uy, kx - ux)) * rad2deg;            // _calc_angle_from_origin
+    const double e = direction * deg2rad, r = ang * deg2rad;                       // calculate_angular_difference
+    const double a = fabs(py_mod_2pi(r - e) * rad2deg), b = fabs(py_mod_2pi(e - r) * rad2deg);
+    return fmin(a, b);
+}
+
+constexpr int MAX_TOL = 64;
+
+__global__ void __launch_bounds__(KNN_WARPS * 32) knn_dir_kernel(const KnnParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_hist[KNN_WARPS][MAX_TOL + 2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t slot = (int64_t)blockIdx.x * KNN_WARPS + warp;
+    if (slot >= p.count) return;
+    const int k2 = p.k2, kk = p.kk;
+    const GridIndex &g = p.g;
+    const int32_t q = p.order[slot];
+    const double ux = p.unknown[2 * (int64_t)q], uy = p.unknown[2 * (int64_t)q + 1];
+    // cells that can hold a point within the range (one extra cell of margin for rounding)
+    const int x_lo = clampi((int)floor((ux - p.range - g.x0) * g.inv_h) - 1, 0, g.gx - 1);
+    const int x_hi = clampi((int)floor((ux + p.range - g.x0) * g.inv_h) + 1, 0, g.gx - 1);
+    const int y_lo = clampi((int)floor((uy - p.range - g.y0) * g.inv_h) - 1, 0, g.gy - 1);
+    const int y_hi = clampi((int)floor((uy + p.range - g.y0) * g.inv_h) + 1, 0, g.gy - 1);
+    int *hist = s_hist[warp];
+    for (int t = lane; t < MAX_TOL + 2; t += 32) hist[t] = 0;
+    __syncwarp();
+
+    TopK top;
+    topk_init(top, reinterpret_cast<Cand *>(smem_raw) + (size_t)warp * 2 * k2, k2, kk, lane);
+    int tol = p.last_tol;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int yy = y_lo; yy <= y_hi; ++yy) {
+            const int s0 = g.cell_start[yy * g.gx + x_lo], s1 = g.cell_start[yy * g.gx + x_hi + 1];
+            for (int base = s0; base < s1; base += 32) {
+                const int pos = base + lane;
+                Cand c = cand_inf();
+                bool ok = false;
+                double ad = 0.0;
+                if (pos < s1) {
+                    c = make_cand(g, pos, ux, uy);
+                    if (c.d <= p.range) {                        // distances <= max_range (select_points.py:201)
+                        ad = angular_difference(ux, uy, g.x[pos], g.y[pos], p.direction);
+                        ok = true;
+                    }
+                }
+                if (pass == 0) {
+                    if (ok) {                                    // smallest integer tolerance with ad <= tolerance
+                        int need = max(1, (int)ceil(ad));
+                        if ((double)need < ad) ++need;
+                        if (need <= p.last_tol) atomicAdd(&hist[need], 1);
+                    }
+                } else {
+                    topk_offer(top, c, ok && ad <= (double)tol, lane);
+                }
+            }
+        }
+        __syncwarp();
+        if (pass == 0) {
+            // widen 1, 2, ... until >= k qualify or the tolerance passes max_tick (select_points.py:232-240)
+            int cum = 0;
+            tol = p.last_tol;
+            for (int t = 1; t <= p.last_tol; ++t) {
+                cum += hist[t];
+                if (cum >= p.k) { tol = t; break; }
+            }
+        }
+    }
+    topk_finish(top, lane);
+    int found = 0;
+    for (int t = lane; t < kk; t += 32) {
+        const Cand c = top.best[t];
+        p.nbr_pos[slot * kk + t] = c.pos;
+        p.nbr_d[slot * kk + t] = c.d;
+        found += (c.pos >= 0) ? 1 : 0;
+    }
+    for (int o = 16; o; o >>= 1) found += __shfl_xor_sync(0xffffffffu, found, o);
+    if (p.use_all) {                                             // all qualifying rows are wanted: did they fit?
+        int qualifying = 0;
+        for (int t = 1; t <= tol; ++t) qualifying += hist[t];
+        if (qualifying > kk) found = -1;
+        else if (qualifying < p.k) found = min(found, qualifying);
+    } else found = min(found, p.k);
+    if (lane == 0) p.nbr_count[slot] = found;
+    if (p.nbr_idx)
+        for (int t = lane; t < p.k; t += 32) p.nbr_idx[(int64_t)q * p.k + t] = (t < kk && top.best[t].pos >= 0) ? top.best[t].orig : -1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -228,6 +368,7 @@ struct SolveParams {
     uint8_t *status;            // NULL or [n_sets][m]
     int warps;                  // warps per CTA
     int stride;                 // row stride of the augmented matrix in doubles (odd)
+    const int32_t *nbr_count;   // NULL, or [count] neighbours actually selected (<= kk; directional selection)
 };
 
 // per-warp shared memory: A[dim][stride] | rhs0[dim] | dinv[dim] | nx[kk] ny[kk] nd[kk] | npos[kk] (int)
@@ -243,22 +384,33 @@ __global__ void solve_kernel(const SolveParams p)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t slot = (int64_t)blockIdx.x * p.warps + warp;
     if (slot >= p.count) return;
-    const int kk = p.kk, mode = p.mode;
-    const int dim = (mode == PIB_KRIGE_ORDINARY) ? kk + 1 : kk;
+    const int kmax = p.kk, mode = p.mode;                       // shared-memory layout is sized for kmax neighbours
+    const int dmax = (mode == PIB_KRIGE_ORDINARY) ? kmax + 1 : kmax;
     const int st = p.stride;
-    const size_t per_warp = ((size_t)dim * st * 8 + (size_t)dim * 16 + (size_t)kk * 24 + (size_t)((kk + 1) / 2 * 2) * 4 + 15) / 16 * 16;
+    const size_t per_warp = ((size_t)dmax * st * 8 + (size_t)dmax * 16 + (size_t)kmax * 24 + (size_t)((kmax + 1) / 2 * 2) * 4 + 15) / 16 * 16;
     double *A = reinterpret_cast<double *>(smem_raw + per_warp * warp);
-    double *rhs0 = A + (size_t)dim * st;
-    double *dinv = rhs0 + dim;
-    double *nx = dinv + dim, *ny = nx + kk, *nd = ny + kk;
-    int32_t *npos = reinterpret_cast<int32_t *>(nd + kk);
+    double *rhs0 = A + (size_t)dmax * st;
+    double *dinv = rhs0 + dmax;
+    double *nx = dinv + dmax, *ny = nx + kmax, *nd = ny + kmax;
+    int32_t *npos = reinterpret_cast<int32_t *>(nd + kmax);
     const GridIndex &g = p.g;
 
     const int32_t q = p.order[slot];
     const double ux = p.unknown[2 * (int64_t)q], uy = p.unknown[2 * (int64_t)q + 1];
+    const int kk = p.nbr_count ? p.nbr_count[slot] : kmax;      // neighbours of THIS location
+    const int dim = (mode == PIB_KRIGE_ORDINARY) ? kk + 1 : kk;
+    if (kk <= 0) {                       // 0: no neighbour qualified, the reference kriges a NaN row; -1: too many
+        if (lane == 0)
+            for (int set = 0; set < p.n_sets; ++set) {
+                double *o = p.out + ((size_t)set * p.m + q) * 4;
+                o[0] = nan(""); o[1] = nan(""); o[2] = ux; o[3] = uy;
+                if (p.status) p.status[(size_t)set * p.m + q] = kk < 0 ? PIB_STATUS_TOO_MANY_NEIGHBORS : PIB_STATUS_OK;
+            }
+        return;
+    }
     for (int t = lane; t < kk; t += 32) {
-        const int pos = p.nbr_pos[slot * kk + t];
-        npos[t] = pos; nx[t] = g.x[pos]; ny[t] = g.y[pos]; nd[t] = p.nbr_d[slot * kk + t];
+        const int pos = p.nbr_pos[slot * kmax + t];
+        npos[t] = pos; nx[t] = g.x[pos]; ny[t] = g.y[pos]; nd[t] = p.nbr_d[slot * kmax + t];
     }
     __syncwarp();
 
@@ -403,15 +555,24 @@ __global__ void __launch_bounds__(256) solve_reg_kernel(const SolveParams p)
     if (slot >= p.count) return;                   // whole systems leave together (barriers are per system)
     RegSysSmem<K, ORD> &S = smem[sid];
     const GridIndex &g = p.g;
-    const int kk = p.kk;
+    const int kk = p.nbr_count ? p.nbr_count[slot] : p.kk;      // neighbours of THIS location (<= p.kk <= K)
 
     const int32_t q = p.order[slot];
     const double ux = p.unknown[2 * (int64_t)q], uy = p.unknown[2 * (int64_t)q + 1];
+    if (kk <= 0) {                       // 0: no neighbour qualified, the reference kriges a NaN row; -1: too many
+        if (t == 0)
+            for (int set = 0; set < p.n_sets; ++set) {
+                double *o = p.out + ((size_t)set * p.m + q) * 4;
+                o[0] = nan(""); o[1] = nan(""); o[2] = ux; o[3] = uy;
+                if (p.status) p.status[(size_t)set * p.m + q] = kk < 0 ? PIB_STATUS_TOO_MANY_NEIGHBORS : PIB_STATUS_OK;
+            }
+        return;
+    }
     int my_pos = -1;
     double my_d = 0.0;
     if (t < kk) {
-        my_pos = p.nbr_pos[slot * kk + t];
-        my_d = p.nbr_d[slot * kk + t];
+        my_pos = p.nbr_pos[slot * p.kk + t];
+        my_d = p.nbr_d[slot * p.kk + t];
         S.nxy[t] = make_double2(g.x[my_pos], g.y[my_pos]);
     } else if (t < K) {
         S.nxy[t] = make_double2(0.0, 0.0);
@@ -606,15 +767,26 @@ static int launch_solve_reg(const SolveParams &sp, int mode, cudaStream_t stream
 // ---------------------------------------------------------------------------------------------
 int krige_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
                  const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
+                 double neighbors_range, double direction, double max_tick, int use_all,
                  double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, cudaStream_t stream)
 {
+    const bool directional = !std::isnan(direction);
+    PIB_CHECK(directional || !use_all, PIB_ERR_UNSUPPORTED,
+              "krige: use_all_neighbors_in_range is only implemented for directional models");
+    PIB_CHECK(!directional || (neighbors_range > 0 && std::isfinite(neighbors_range)), PIB_ERR_INVALID,
+              "krige: directional selection needs a positive neighbors_range");
     PIB_CHECK(n >= 1 && m >= 0 && k >= 1, PIB_ERR_INVALID, "krige: need n >= 1, m >= 0, k >= 1");
     PIB_CHECK(n_sets >= 1 && params != nullptr, PIB_ERR_INVALID, "krige: need at least one parameter set");
     PIB_CHECK(model >= 0 && model <= 6, PIB_ERR_INVALID, "krige: unknown model id");
     PIB_CHECK(mode == PIB_KRIGE_ORDINARY || mode == PIB_KRIGE_SIMPLE, PIB_ERR_INVALID, "krige: unknown mode");
     PIB_CHECK(m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31), PIB_ERR_UNSUPPORTED, "krige: more than 2^31-1 rows");
-    const int kk = (int)std::min<int64_t>(k, n);
-    PIB_CHECK(kk <= MAX_K, PIB_ERR_UNSUPPORTED, "krige: no_neighbors above 128 is not supported");
+    PIB_CHECK(std::min<int64_t>(k, n) <= MAX_K, PIB_ERR_UNSUPPORTED, "krige: no_neighbors above 128 is not supported");
+    const int kk = use_all ? (int)std::min<int64_t>(MAX_K, n) : (int)std::min<int64_t>(k, n);
+    int last_tol = 0;
+    if (directional) {
+        last_tol = std::max(2, (int)std::floor(max_tick) + 1);   // 1, 2, ... until the tolerance exceeds max_tick
+        PIB_CHECK(last_tol <= MAX_TOL, PIB_ERR_UNSUPPORTED, "krige: max_tick above 63 degrees is not supported");
+    }
     timing_reset(PIB_T_KNN);
     timing_reset(PIB_T_SOLVE);
     if (m == 0) return PIB_OK;
@@ -642,6 +814,7 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
     PIB_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * solve_warps)));
     const size_t knn_smem = (size_t)KNN_WARPS * 2 * k2 * sizeof(Cand);
     PIB_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem));
+    PIB_CUDA(cudaFuncSetAttribute(knn_dir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem));
 
     const char *force_smem = std::getenv("PIB_FORCE_SMEM_SOLVE");
     const bool use_reg = kk <= 64 && !(force_smem && force_smem[0] == '1');
@@ -650,21 +823,28 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
     double *nbr_d;
     PIB_TRY(ws.alloc(&nbr_pos, (size_t)chunk * kk));
     PIB_TRY(ws.alloc(&nbr_d, (size_t)chunk * kk));
+    int32_t *nbr_count = nullptr;
+    if (directional) PIB_TRY(ws.alloc(&nbr_count, (size_t)chunk));
 
     for (int64_t begin = 0; begin < m; begin += chunk) {
         const int64_t count = std::min(chunk, m - begin);
         KnnParams kp;
         kp.g = g; kp.unknown = d_unknown; kp.order = order + begin; kp.count = count; kp.kk = kk; kp.k2 = k2; kp.r0 = r0;
         kp.nbr_pos = nbr_pos; kp.nbr_d = nbr_d; kp.nbr_idx = d_nbr_idx; kp.k = k;
+        kp.nbr_count = nbr_count; kp.range = neighbors_range; kp.direction = direction; kp.last_tol = last_tol;
+        kp.use_all = use_all;
         timing_begin(PIB_T_KNN, stream);
-        knn_kernel<<<(int)((count + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, knn_smem, stream>>>(kp);
+        if (directional)
+            knn_dir_kernel<<<(int)((count + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, knn_smem, stream>>>(kp);
+        else
+            knn_kernel<<<(int)((count + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, knn_smem, stream>>>(kp);
         timing_end(PIB_T_KNN, stream);
         PIB_CUDA(cudaGetLastError());
         SolveParams sp;
         sp.g = g; sp.unknown = d_unknown; sp.order = order + begin; sp.count = count; sp.m = m; sp.n = n; sp.kk = kk; sp.k = k;
         sp.nbr_pos = nbr_pos; sp.nbr_d = nbr_d; sp.values = d_values; sp.params = d_params; sp.n_sets = n_sets;
         sp.model = model; sp.mode = mode; sp.process_mean = process_mean; sp.out = d_out; sp.status = d_status;
-        sp.warps = solve_warps; sp.stride = stride;
+        sp.warps = solve_warps; sp.stride = stride; sp.nbr_count = nbr_count;
         timing_begin(PIB_T_SOLVE, stream);
         int rc = PIB_OK;
         if (use_reg && kk <= 8) rc = launch_solve_reg<8>(sp, mode, stream);

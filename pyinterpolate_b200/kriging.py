@@ -7,9 +7,10 @@ Mirrors (file:line relative to /root/reference/src/pyinterpolate/):
   * kriging/point/indicator.py:200-325    IndicatorKriging._estimate (batched: one neighbour search,
                                           one solve per threshold)
 
-Not built yet (NotImplementedError, there is no CPU fallback): models with a ``direction``
-(angular neighbour selection, transform/select_points.py:104-257), ``use_all_neighbors_in_range=True``
-(variable-size systems) and ``allow_approximate_solutions=True`` (lstsq fallback).
+Models that carry a ``direction`` use the reference's angular neighbour selection
+(transform/select_points.py:104-257) inside ``neighbors_range`` (default: the model range).
+Not built yet (NotImplementedError, there is no CPU fallback): ``use_all_neighbors_in_range=True`` for
+isotropic models or with more than 128 rows in range, and ``allow_approximate_solutions=True`` (lstsq fallback).
 """
 import warnings
 
@@ -27,13 +28,11 @@ _SINGULAR_MSG = ("Singular matrix in Kriging system detected, "
 
 
 def _prepare(theoretical_model, known_locations, unknown_locations, use_all_neighbors_in_range,
-             allow_approximate_solutions):
+             allow_approximate_solutions, neighbors_range=None, max_tick=5.):
     mid, nugget, sill, rang, direction = model_parameters(theoretical_model)
-    if direction is not None:
-        raise NotImplementedError("kriging with a directional theoretical model is not implemented in "
-                                  "pyinterpolate_b200 yet (SURVEY.md §8f-3)")
-    if use_all_neighbors_in_range:
-        raise NotImplementedError("use_all_neighbors_in_range=True is not implemented in pyinterpolate_b200 yet")
+    if use_all_neighbors_in_range and direction is None:
+        raise NotImplementedError("use_all_neighbors_in_range=True is only implemented for directional models "
+                                  "in pyinterpolate_b200")
     if allow_approximate_solutions:
         raise NotImplementedError("allow_approximate_solutions=True (least-squares fallback) is not implemented "
                                   "in pyinterpolate_b200 yet")
@@ -43,13 +42,19 @@ def _prepare(theoretical_model, known_locations, unknown_locations, use_all_neig
         raise ValueError("known_locations must be rows of [x, y, value]")
     if unknown.ndim != 2 or unknown.shape[1] != 2:
         raise ValueError("unknown_locations must be rows of [x, y]")
-    return mid, np.array([[nugget, sill, rang]]), known, unknown
+    # neighbors_range defaults to the model range (kriging/utils/point_kriging_solve.py:68-69)
+    selection = dict(neighbors_range=rang if neighbors_range is None else float(neighbors_range),
+                     direction=direction, max_tick=max_tick, use_all=bool(use_all_neighbors_in_range))
+    return mid, np.array([[nugget, sill, rang]]), known, unknown, selection
 
 
 def _raise_on_singular(status):
     if (status == _lib.STATUS_SINGULAR).any():
         # kriging/utils/errors.py:1-15 via ordinary.py:130-131
         raise RuntimeError(_SINGULAR_MSG)
+    if (status == _lib.STATUS_TOO_MANY_NEIGHBORS).any():
+        raise NotImplementedError("use_all_neighbors_in_range selected more than 128 neighbours for a location; "
+                                  "pyinterpolate_b200 solves systems of at most 128 neighbours")
 
 
 def ordinary_kriging(theoretical_model, known_locations, unknown_locations=None, neighbors_range=None,
@@ -58,16 +63,18 @@ def ordinary_kriging(theoretical_model, known_locations, unknown_locations=None,
                      return_neighbors=False):
     """``[predicted value, variance error, x, y]`` rows — kriging/point/ordinary.py:134-221.
 
-    ``neighbors_range`` does not change the result when ``use_all_neighbors_in_range`` is False
-    (transform/select_points.py:95-101: the k nearest are used either way), ``max_tick`` only applies to
-    directional models and ``progress_bar`` has nothing to show: one batched launch replaces the loop.
+    For isotropic models ``neighbors_range`` does not change the result when ``use_all_neighbors_in_range`` is
+    False (transform/select_points.py:95-101: the k nearest are used either way); for models with a
+    ``direction`` it bounds the angular search and ``max_tick`` caps the tolerance widening.
+    ``progress_bar`` has nothing to show: one batched launch replaces the loop.
     ``unknown_location=`` (the README's spelling) is accepted as an alias."""
     if unknown_locations is None:
         unknown_locations = unknown_location
-    mid, params, known, unknown = _prepare(theoretical_model, known_locations, unknown_locations,
-                                           use_all_neighbors_in_range, allow_approximate_solutions)
+    mid, params, known, unknown, sel = _prepare(theoretical_model, known_locations, unknown_locations,
+                                                use_all_neighbors_in_range, allow_approximate_solutions,
+                                                neighbors_range, max_tick)
     out, idx, status = _lib.krige_host(known, unknown, mid, params, _lib.KRIGE_ORDINARY, int(no_neighbors),
-                                       want_neighbors=return_neighbors)
+                                       want_neighbors=return_neighbors, **sel)
     _raise_on_singular(status)
     return (out[0], idx) if return_neighbors else out[0]
 
@@ -81,10 +88,11 @@ def simple_kriging(theoretical_model, known_locations, unknown_locations=None, p
         unknown_locations = unknown_location
     if process_mean is None:
         raise TypeError("simple_kriging() missing required argument: 'process_mean'")
-    mid, params, known, unknown = _prepare(theoretical_model, known_locations, unknown_locations,
-                                           use_all_neighbors_in_range, allow_approximate_solutions)
+    mid, params, known, unknown, sel = _prepare(theoretical_model, known_locations, unknown_locations,
+                                                use_all_neighbors_in_range, allow_approximate_solutions,
+                                                neighbors_range, max_tick)
     out, idx, status = _lib.krige_host(known, unknown, mid, params, _lib.KRIGE_SIMPLE, int(no_neighbors),
-                                       process_mean=float(process_mean), want_neighbors=return_neighbors)
+                                       process_mean=float(process_mean), want_neighbors=return_neighbors, **sel)
     _raise_on_singular(status)
     return (out[0], idx) if return_neighbors else out[0]
 

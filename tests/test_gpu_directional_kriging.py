@@ -1,0 +1,48 @@
+"""GPU parity for kriging with directional models: angular neighbour selection with
+tolerance widening, fewer-than-k and empty neighbour sets — against the unmodified reference
+(tests/golden/make_golden_directional_kriging.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from pyinterpolate_b200.synthetic import dem_like_field, uniform_locations
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def pib():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pyinterpolate_b200 as pib
+    return pib
+
+
+@pytest.mark.parametrize("case", range(5))
+def test_directional_kriging_golden(pib, case):
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_directional_kriging.npz"))
+    known = dem_like_field(20000, seed=61)
+    unk = uniform_locations(120, seed=62)
+    name = "abcde"[case]
+    direction, rang, k, tick, use_all = gold["cases"][case]
+    k = int(k)
+    mdl = {"variogram_model_type": "spherical", "nugget": 1.0, "sill": float(gold["var"]), "rang": float(rang),
+           "direction": float(direction)}
+    ok, idx = pib.ordinary_kriging(mdl, known, unk, no_neighbors=k, max_tick=float(tick),
+                                   use_all_neighbors_in_range=bool(use_all), return_neighbors=True)
+    sk = pib.simple_kriging(mdl, known, unk, process_mean=float(known[:, 2].mean()), no_neighbors=k,
+                            max_tick=float(tick), use_all_neighbors_in_range=bool(use_all))
+    counts, want_idx = gold[f"{name}_counts"], gold[f"{name}_idx"]
+    # neighbour sets bit-exact (the ABI reports at most k indices per location)
+    width = min(k, want_idx.shape[1])
+    np.testing.assert_array_equal(idx[:, :width], want_idx[:, :width])
+    assert ((idx >= 0).sum(axis=1) == np.minimum(counts, k)).all()
+    for got, want in ((ok, gold[f"{name}_ok"]), (sk, gold[f"{name}_sk"])):
+        np.testing.assert_array_equal(np.isnan(got[:, 0]), np.isnan(want[:, 0]))
+        np.testing.assert_array_equal(np.isnan(got[:, 1]), np.isnan(want[:, 1]))
+        np.testing.assert_allclose(got[:, :2], want[:, :2], rtol=1e-9, equal_nan=True)
+        np.testing.assert_array_equal(got[:, 2:], want[:, 2:])
+    assert (counts == 0).any() and (counts < k).any()            # the fixture really exercises short / empty sets
