@@ -403,7 +403,10 @@ __global__ void solve_kernel(const SolveParams p)
         if (lane == 0)
             for (int set = 0; set < p.n_sets; ++set) {
                 double *o = p.out + ((size_t)set * p.m + q) * 4;
-                o[0] = nan(""); o[1] = nan(""); o[2] = ux; o[3] = uy;
+                // the reference solves a 1-row system built from a NaN row: zhat = NaN and sigma^2 = gamma(NaN),
+                // i.e. nugget + sill for the models written with `lags <= rang` masks, NaN for the exponential ones
+                o[0] = nan(""); o[2] = ux; o[3] = uy;
+                o[1] = kk < 0 ? nan("") : gamma_model(p.model, nan(""), p.params[3 * set], p.params[3 * set + 1], p.params[3 * set + 2]);
                 if (p.status) p.status[(size_t)set * p.m + q] = kk < 0 ? PIB_STATUS_TOO_MANY_NEIGHBORS : PIB_STATUS_OK;
             }
         return;
@@ -563,7 +566,10 @@ __global__ void __launch_bounds__(256) solve_reg_kernel(const SolveParams p)
         if (t == 0)
             for (int set = 0; set < p.n_sets; ++set) {
                 double *o = p.out + ((size_t)set * p.m + q) * 4;
-                o[0] = nan(""); o[1] = nan(""); o[2] = ux; o[3] = uy;
+                // the reference solves a 1-row system built from a NaN row: zhat = NaN and sigma^2 = gamma(NaN),
+                // i.e. nugget + sill for the models written with `lags <= rang` masks, NaN for the exponential ones
+                o[0] = nan(""); o[2] = ux; o[3] = uy;
+                o[1] = kk < 0 ? nan("") : gamma_model(p.model, nan(""), p.params[3 * set], p.params[3 * set + 1], p.params[3 * set + 2]);
                 if (p.status) p.status[(size_t)set * p.m + q] = kk < 0 ? PIB_STATUS_TOO_MANY_NEIGHBORS : PIB_STATUS_OK;
             }
         return;

@@ -110,8 +110,11 @@ def test_edge_cases_golden(pib, golden):
     with pytest.raises(KeyError):
         pib.ordinary_kriging({"variogram_model_type": "matern", "nugget": 0, "sill": 1, "rang": 1}, arm, unk)
     with pytest.raises(NotImplementedError):
-        pib.ordinary_kriging({"variogram_model_type": "linear", "nugget": 0, "sill": 1, "rang": 1, "direction": 45},
-                             arm, unk)
+        pib.ordinary_kriging({"variogram_model_type": "linear", "nugget": 0, "sill": 1, "rang": 1}, arm, unk,
+                             use_all_neighbors_in_range=True)          # isotropic use_all is not built
+    with pytest.raises(NotImplementedError):
+        pib.ordinary_kriging({"variogram_model_type": "linear", "nugget": 0, "sill": 1, "rang": 1}, arm, unk,
+                             allow_approximate_solutions=True)
 
 
 def test_exact_interpolation_at_known_points(pib):
