@@ -111,6 +111,21 @@ PIB_API int pib_variogram_host(const double *xyz, int64_t n,
                        int64_t *pairs_evaluated);
 
 /* ------------------------------------------------------------------------------------------
+ * Weighted semivariance (custom_weights).  Replaces
+ *   semivariogram/weights/experimental/weighting.py:4-54          (omnidirectional, n_dirs == 0)
+ *   semivariogram/experimental/functions/directional.py:276-392   (directional = ellipse, n_dirs == 1)
+ * weights [n] per-point weights (non-zero).  sums [4][n_lags] (out), over UNORDERED pairs in the lag, with
+ * w_p = w_i w_j / (w_i + w_j):
+ *   omni:        sum w_p (z_i/w_i - z_j/w_j)^2,  sum w_p,  sum (z_i/w_i + z_j/w_j),  sum (w_i + w_j)
+ *   directional: sum w_p (z_i - z_j)^2,          sum w_p,  sum (w_i z_i + w_j z_j),  sum (w_i + w_j)
+ * count [n_lags] unordered pairs.  Small-data path (global atomics; sums are not bit-reproducible run to run).
+ * ---------------------------------------------------------------------------------------- */
+PIB_API int pib_variogram_weighted_host(const double *xyz, const double *weights, int64_t n,
+                                const double *edges, const double *lower, int n_lags,
+                                const double *W, int n_dirs,
+                                double *sums, int64_t *count);
+
+/* ------------------------------------------------------------------------------------------
  * Variogram point cloud: per lag, (z_i - z_j)^2 of every ORDERED pair in the lag, in the reference's
  * order (row i ascending, then j ascending = np.where on the N x N mask).  Replaces
  *   semivariogram/experimental/functions/general.py:13-75, :150-233   omnidirectional_semivariogram_cloud

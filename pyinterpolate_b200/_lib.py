@@ -20,7 +20,8 @@ STATUS_TOO_MANY_NEIGHBORS = 3
 
 EXPORTS = ("pib_krige_ex_device", "pib_krige_ex_host", "pib_last_error", "pib_version", "pib_device_sm_count", "pib_variogram_device",
            "pib_variogram_host", "pib_krige_device", "pib_krige_host", "pib_gamma_host",
-           "pib_fp64_peak_tflops", "pib_last_kernel_ms", "pib_variogram_cloud_host")
+           "pib_fp64_peak_tflops", "pib_last_kernel_ms", "pib_variogram_cloud_host",
+           "pib_variogram_weighted_host")
 
 _lib = None
 
@@ -56,6 +57,7 @@ def load():
     L.pib_fp64_peak_tflops.argtypes = [dp]
     L.pib_last_kernel_ms.argtypes = [i32, dp, dp]
     L.pib_variogram_cloud_host.argtypes = [dp, i64, dp, dp, i32, dp, i32, dp, dp]
+    L.pib_variogram_weighted_host.argtypes = [dp, dp, i64, dp, dp, i32, dp, i32, dp, dp]
     for name in EXPORTS:
         getattr(L, name).restype = getattr(L, name).restype or i32
     L.pib_last_error.restype = ctypes.c_char_p
@@ -97,6 +99,21 @@ def variogram_host(xyz, edges, lower=None, W=None, shard=(0, 1)):
     return dict(sum_sq=ssq, sum_prod=spr, sum_val=sva, count=cnt, pairs_evaluated=int(evaluated.value))
 
 
+def variogram_weighted_host(xyz, weights, edges, lower=None, W=None):
+    """Weighted pair sums (see the header).  Returns (sums[4, L], count[L]) over unordered pairs."""
+    L = load()
+    xyz, edges, weights = _f64(xyz), _f64(edges), _f64(weights)
+    n, n_lags = xyz.shape[0], edges.shape[0]
+    Wc = None if W is None else _f64(np.asarray(W).reshape(1, 4))
+    lower_c = None if lower is None else _f64(lower)
+    sums = np.zeros((4, n_lags))
+    cnt = np.zeros(n_lags, dtype=np.int64)
+    rc = L.pib_variogram_weighted_host(_host_ptr(xyz), _host_ptr(weights), n, _host_ptr(edges), _host_ptr(lower_c),
+                                       n_lags, _host_ptr(Wc), 0 if W is None else 1, _host_ptr(sums), _host_ptr(cnt))
+    check(rc, "pib_variogram_weighted_host")
+    return sums, cnt
+
+
 def variogram_cloud_host(xyz, edges, lower=None, W=None):
     """Per-lag lists of (z_i - z_j)^2 over ordered pairs, in the reference's (i, j) order.
     One direction at most (``W`` = 4 doubles).  Returns a list of float64 arrays, one per lag."""
@@ -111,7 +128,8 @@ def variogram_cloud_host(xyz, edges, lower=None, W=None):
     values = np.empty(int(offsets[-1]), dtype=np.float64)
     rc = L.pib_variogram_cloud_host(_host_ptr(xyz), n, _host_ptr(edges), _host_ptr(lower_c), n_lags, _host_ptr(Wc),
                                     0 if W is None else 1, _host_ptr(offsets), _host_ptr(values))
-    check(rc, "pib_variogram_cloud_host")
+    check(rc, "pib_variogram_cloud_host",
+           "pib_variogram_weighted_host")
     return [values[offsets[b]:offsets[b + 1]] for b in range(n_lags)]
 
 

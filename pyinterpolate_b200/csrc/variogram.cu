@@ -1182,4 +1182,83 @@ int variogram_cloud_device(const double *d_xyz, int64_t n, const double *edges, 
     return PIB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Weighted semivariance (custom_weights):
+//   semivariogram/weights/experimental/weighting.py:4-54        omnidirectional (u = z / w)
+//   semivariogram/experimental/functions/directional.py:276-392 directional, always ellipse selection
+// Per lag, over unordered pairs (the reference's ordered sums are twice these):
+//   s1 = sum w_p q       w_p = w_i w_j / (w_i + w_j);  q = (u_i - u_j)^2 (omni) or (z_i - z_j)^2 (directional)
+//   s2 = sum w_p
+//   s3 = sum (f_i + f_j) f = u (omni) or w z (directional)
+//   s4 = sum (w_i + w_j)
+// One thread per point i over all j > i, global fp64 REDs (this path serves small areal data sets).
+// ---------------------------------------------------------------------------------------------
+__global__ void weighted_pair_kernel(const double *__restrict__ xyz, const double *__restrict__ wts, int64_t n,
+                                     const double *__restrict__ up_d2, const double *__restrict__ low_d2, int n_lags,
+                                     bool ellipse, double w00, double w01, double w10, double w11,
+                                     double *__restrict__ sums /* [4][n_lags] */, unsigned long long *__restrict__ count)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double xi = xyz[3 * i], yi = xyz[3 * i + 1], zi = xyz[3 * i + 2], wi = wts[i];
+        const double ui = zi / wi;
+        for (int64_t j = i + 1; j < n; ++j) {
+            double d2;
+            if (ellipse) {
+                const double dx = __dsub_rn(xyz[3 * j], xi), dy = __dsub_rn(xyz[3 * j + 1], yi);
+                const double n0 = __fma_rn(w01, dy, __dmul_rn(w00, dx));
+                const double n1 = __fma_rn(w11, dy, __dmul_rn(w10, dx));
+                d2 = __dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1));
+            } else {
+                const double dx = __dsub_rn(xi, xyz[3 * j]), dy = __dsub_rn(yi, xyz[3 * j + 1]);
+                d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            }
+            if (!(d2 > 0.0)) continue;
+            for (int b = 0; b < n_lags; ++b) {
+                if (d2 <= up_d2[b] && d2 > low_d2[b]) {
+                    const double zj = xyz[3 * j + 2], wj = wts[j];
+                    const double wp = (wi * wj) / (wi + wj);
+                    double q, f;
+                    if (ellipse) { const double dz = zj - zi; q = dz * dz; f = wi * zi + wj * zj; }
+                    else { const double du = ui - zj / wj; q = du * du; f = ui + zj / wj; }
+                    atomicAdd(&sums[b], wp * q);
+                    atomicAdd(&sums[n_lags + b], wp);
+                    atomicAdd(&sums[2 * n_lags + b], f);
+                    atomicAdd(&sums[3 * n_lags + b], wi + wj);
+                    atomicAdd(&count[b], 1ull);
+                }
+            }
+        }
+    }
+}
+
+int variogram_weighted_device(const double *d_xyz, const double *d_weights, int64_t n, const double *edges,
+                              const double *lower, int n_lags, const double *W, int n_dirs, double *d_sums,
+                              int64_t *d_count, cudaStream_t stream)
+{
+    PIB_CHECK(n >= 0 && n_lags >= 1 && edges && d_sums && d_count, PIB_ERR_INVALID, "weighted variogram: bad arguments");
+    PIB_CHECK(n_dirs == 0 || (n_dirs == 1 && W), PIB_ERR_INVALID, "weighted variogram: one direction at a time");
+    PIB_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * 4 * n_lags, stream));
+    PIB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t) * n_lags, stream));
+    if (n < 2) return PIB_OK;
+    Scratch ws(stream);
+    std::vector<double> up(n_lags), low(n_lags);
+    for (int b = 0; b < n_lags; ++b) {
+        up[b] = sq_threshold(edges[b]);
+        low[b] = sq_threshold((n_dirs > 0 && lower) ? lower[b] : (b ? edges[b - 1] : 0.0));
+    }
+    double *d_up, *d_low;
+    PIB_TRY(ws.alloc(&d_up, n_lags)); PIB_TRY(ws.alloc(&d_low, n_lags));
+    PIB_CUDA(cudaMemcpyAsync(d_up, up.data(), n_lags * sizeof(double), cudaMemcpyHostToDevice, stream));
+    PIB_CUDA(cudaMemcpyAsync(d_low, low.data(), n_lags * sizeof(double), cudaMemcpyHostToDevice, stream));
+    const int grid = (int)std::min<int64_t>((n + 127) / 128, 8 * sm_count());
+    weighted_pair_kernel<<<grid, 128, 0, stream>>>(d_xyz, d_weights, n, d_up, d_low, n_lags, n_dirs > 0,
+                                                   n_dirs ? W[0] : 0, n_dirs ? W[1] : 0, n_dirs ? W[2] : 0,
+                                                   n_dirs ? W[3] : 0, d_sums,
+                                                   reinterpret_cast<unsigned long long *>(d_count));
+    PIB_CUDA(cudaGetLastError());
+    return PIB_OK;
+}
+
 }  // namespace pib

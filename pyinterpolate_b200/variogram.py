@@ -46,8 +46,7 @@ def _finalize(sums, directional):
 
 def _check_method(direction, method, custom_weights):
     if custom_weights is not None:
-        raise NotImplementedError("custom_weights are not implemented in pyinterpolate_b200 yet "
-                                  "(weighted semivariance, SURVEY.md §8f-4)")
+        return                              # the weighted directional path always selects with the ellipse
     if direction is not None and method not in ("e", "ellipse"):
         raise NotImplementedError("only dir_neighbors_selection_method='e' (ellipse) is implemented in "
                                   "pyinterpolate_b200; the triangle method 't' is not built yet")
@@ -99,9 +98,54 @@ def experimental_curves(ds, step_size=None, max_range=None, direction=None, tole
     return lags, sem, cov, npairs
 
 
+def weighted_semivariance(ds, custom_weights, step_size=None, max_range=None, direction=None, tolerance=None,
+                          custom_bins=None):
+    """``[lag, weighted semivariance, number of point pairs]`` for ``custom_weights``:
+    omnidirectional — semivariogram/weights/experimental/weighting.py:4-54 through
+    functions/general.py:292-301; directional — functions/directional.py:276-392 (ellipse selection
+    whatever ``dir_neighbors_selection_method`` says, like the reference)."""
+    points = core.variogram_points(ds)
+    core.validate_bins(step_size, max_range, custom_bins)
+    core.validate_semivariance_weights(points, custom_weights)
+    core.validate_direction_and_tolerance(direction, tolerance)
+    lags = core.get_lags(step_size, max_range, custom_bins)
+    lags64 = np.ascontiguousarray(lags, dtype=np.float64)
+    xyz = np.ascontiguousarray(points, dtype=np.float64)
+    w = np.ascontiguousarray(custom_weights, dtype=np.float64)
+    directional = direction is not None and tolerance is not None
+    if directional:
+        W = core.define_whitening_matrix(direction, tolerance).reshape(4)
+        sums, cnt = _lib.variogram_weighted_host(xyz, w, lags64, lower=core.ellipse_lower_limits(lags64), W=W)
+    else:
+        sums, cnt = _lib.variogram_weighted_host(xyz, w, lags64)
+    s1, s2, s3, s4 = sums
+    out = np.zeros((len(lags), 3))
+    out[:, 0] = lags
+    for b in range(len(lags)):
+        if cnt[b] == 0:
+            if directional:
+                if b == 0:
+                    out[b] = [lags[b], 0, 0]
+                    continue
+                raise RuntimeError(f'There are no neighbors for a lag {lags[b]}, the process has been stopped.')
+            out[b, 1:] = (0, 0) if b == 0 else (np.nan, np.nan)        # functions/general.py:283-287
+            continue
+        if directional:
+            # gamma = sum w_h (dz^2 - avg) / sum w_h, avg = weighted mean of the neighbour values (:377-383)
+            out[b, 1] = 0.5 * (s1[b] / s2[b] - s3[b] / s4[b])
+        else:
+            # sum(w sem - m') / (2 sum w) over ordered pairs, m' = mean of the weighted values (weighting.py:40-50)
+            value = (2.0 * s1[b] - s3[b]) / (4.0 * s2[b])
+            out[b, 1] = 0 if value < 0 else value
+        out[b, 2] = 2 * cnt[b]
+    return out
+
+
 def calculate_semivariance(ds, step_size=None, max_range=None, direction=None, tolerance=None,
                            dir_neighbors_selection_method="t", custom_bins=None, custom_weights=None):
     """``[lag, semivariance, number of point pairs]`` — experimental_semivariogram.py:19-229."""
+    if custom_weights is not None:
+        return weighted_semivariance(ds, custom_weights, step_size, max_range, direction, tolerance, custom_bins)
     lags, sem, _, npairs = experimental_curves(ds, step_size, max_range, direction, tolerance,
                                                dir_neighbors_selection_method, custom_bins, custom_weights)
     return np.column_stack([lags, sem, npairs])
@@ -162,10 +206,19 @@ class ExperimentalVariogram:
         self.tolerance = tolerance
         self.method = dir_neighbors_selection_method
         self.as_cloud = as_cloud
-        if is_semivariance or is_covariance:
+        if custom_weights is not None and is_semivariance:
+            # weighted semivariance first (classes/experimental_variogram.py:284-307); the covariance call
+            # below takes no weights in the reference either (:240-262)
+            wtab = weighted_semivariance(self.ds, custom_weights, step_size, max_range, direction, tolerance, self.lags)
+            self.lags, self.semivariances, self.points_per_lag = wtab[:, 0], wtab[:, 1], wtab[:, 2]
+            if is_covariance:
+                _, _, cov, _ = experimental_curves(self.ds, step_size, max_range, direction, tolerance,
+                                                   dir_neighbors_selection_method, custom_bins)
+                self.covariances = cov
+        elif is_semivariance or is_covariance:
             lags, sem, cov, npairs = experimental_curves(
                 self.ds, step_size, max_range, direction, tolerance, dir_neighbors_selection_method,
-                self.lags, custom_weights)
+                self.lags, None)
             self.lags = lags
             self.points_per_lag = npairs
             if is_semivariance:
