@@ -128,8 +128,7 @@ def variogram_cloud_host(xyz, edges, lower=None, W=None):
     values = np.empty(int(offsets[-1]), dtype=np.float64)
     rc = L.pib_variogram_cloud_host(_host_ptr(xyz), n, _host_ptr(edges), _host_ptr(lower_c), n_lags, _host_ptr(Wc),
                                     0 if W is None else 1, _host_ptr(offsets), _host_ptr(values))
-    check(rc, "pib_variogram_cloud_host",
-           "pib_variogram_weighted_host")
+    check(rc, "pib_variogram_cloud_host")
     return [values[offsets[b]:offsets[b + 1]] for b in range(n_lags)]
 
 
