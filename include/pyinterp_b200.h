@@ -126,6 +126,24 @@ PIB_API int pib_variogram_weighted_host(const double *xyz, const double *weights
                                 double *sums, int64_t *count);
 
 /* ------------------------------------------------------------------------------------------
+ * Triangle ("t") directional selection, the reference's default directional method.  Replaces
+ *   semivariogram/experimental/functions/directional.py:137-210, :536-565   from_triangle
+ *   distance/angular.py:9-64, :188-218, :283-339, :375-409, :459-494        triangle masks
+ * tri_lags [n_lags][9] (HOST), per lag h with a = radians(direction), made with numpy like the reference
+ * (distance/angular.py:283-339, :599-617):  h, h cos a, h sin a, (-h) cos a, (-h) sin a,
+ *   (h tol) cos(a + pi/2), (h tol) sin(a + pi/2), (h tol) cos(a - pi/2), (h tol) sin(a - pi/2)
+ * cos_t, sin_t = cos a, sin a (only used to locate a pair between the lag edges; membership near an edge is
+ * decided with the reference's own operation sequence).
+ * sums [3][n_lags] (out) over ORDERED pairs (centre p, neighbour q) of the cleaned masks:
+ *   sum (z_p - z_q)^2, sum z_p z_q, sum z_q;   count [n_lags] ordered pairs (the reference includes q == p
+ *   in the first lag).  Small-data path (one thread per centre, global atomics).
+ * ---------------------------------------------------------------------------------------- */
+PIB_API int pib_variogram_triangle_host(const double *xyz, int64_t n,
+                                const double *tri_lags, int n_lags,
+                                double cos_t, double sin_t, double tolerance,
+                                double *sums, int64_t *count);
+
+/* ------------------------------------------------------------------------------------------
  * Variogram point cloud: per lag, (z_i - z_j)^2 of every ORDERED pair in the lag, in the reference's
  * order (row i ascending, then j ascending = np.where on the N x N mask).  Replaces
  *   semivariogram/experimental/functions/general.py:13-75, :150-233   omnidirectional_semivariogram_cloud

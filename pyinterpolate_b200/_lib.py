@@ -21,7 +21,7 @@ STATUS_TOO_MANY_NEIGHBORS = 3
 EXPORTS = ("pib_krige_ex_device", "pib_krige_ex_host", "pib_last_error", "pib_version", "pib_device_sm_count", "pib_variogram_device",
            "pib_variogram_host", "pib_krige_device", "pib_krige_host", "pib_gamma_host",
            "pib_fp64_peak_tflops", "pib_last_kernel_ms", "pib_variogram_cloud_host",
-           "pib_variogram_weighted_host")
+           "pib_variogram_weighted_host", "pib_variogram_triangle_host")
 
 _lib = None
 
@@ -58,6 +58,7 @@ def load():
     L.pib_last_kernel_ms.argtypes = [i32, dp, dp]
     L.pib_variogram_cloud_host.argtypes = [dp, i64, dp, dp, i32, dp, i32, dp, dp]
     L.pib_variogram_weighted_host.argtypes = [dp, dp, i64, dp, dp, i32, dp, i32, dp, dp]
+    L.pib_variogram_triangle_host.argtypes = [dp, i64, dp, i32, f64, f64, f64, dp, dp]
     for name in EXPORTS:
         getattr(L, name).restype = getattr(L, name).restype or i32
     L.pib_last_error.restype = ctypes.c_char_p
@@ -111,6 +112,19 @@ def variogram_weighted_host(xyz, weights, edges, lower=None, W=None):
     rc = L.pib_variogram_weighted_host(_host_ptr(xyz), _host_ptr(weights), n, _host_ptr(edges), _host_ptr(lower_c),
                                        n_lags, _host_ptr(Wc), 0 if W is None else 1, _host_ptr(sums), _host_ptr(cnt))
     check(rc, "pib_variogram_weighted_host")
+    return sums, cnt
+
+
+def variogram_triangle_host(xyz, tri_lags, cos_t, sin_t, tolerance):
+    """Triangle-method pair sums over ordered pairs (see the header).  Returns (sums[3, L], count[L])."""
+    L = load()
+    xyz, tri_lags = _f64(xyz), _f64(tri_lags).reshape(-1, 9)
+    n, n_lags = xyz.shape[0], tri_lags.shape[0]
+    sums = np.zeros((3, n_lags))
+    cnt = np.zeros(n_lags, dtype=np.int64)
+    rc = L.pib_variogram_triangle_host(_host_ptr(xyz), n, _host_ptr(tri_lags), n_lags, float(cos_t), float(sin_t),
+                                       float(tolerance), _host_ptr(sums), _host_ptr(cnt))
+    check(rc, "pib_variogram_triangle_host")
     return sums, cnt
 
 

@@ -74,6 +74,8 @@ int variogram_cloud_device(const double *d_xyz, int64_t n, const double *edges, 
 int variogram_weighted_device(const double *d_xyz, const double *d_weights, int64_t n, const double *edges,
                               const double *lower, int n_lags, const double *W, int n_dirs, double *d_sums,
                               int64_t *d_count, cudaStream_t stream);
+int variogram_triangle_device(const double *d_xyz, int64_t n, const double *tri_lags, int n_lags, double cos_t,
+                              double sin_t, double tolerance, double *d_sums, int64_t *d_count, cudaStream_t stream);
 int krige_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
                  const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
                  double neighbors_range, double direction, double max_tick, int use_all,
@@ -182,6 +184,35 @@ int pib_variogram_weighted_host(const double *xyz, const double *weights, int64_
         if (rc == PIB_OK && e == cudaSuccess) e = cudaMemcpyAsync(count, d_count, sizeof(int64_t) * n_lags, cudaMemcpyDeviceToHost, stream);
         if (rc == PIB_OK && e == cudaSuccess) e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) { set_error(std::string("weighted variogram: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; }
+    }
+    cudaStreamSynchronize(stream);
+    cudaStreamDestroy(stream);
+    return rc;
+}
+
+int pib_variogram_triangle_host(const double *xyz, int64_t n, const double *tri_lags, int n_lags, double cos_t,
+                                double sin_t, double tolerance, double *sums, int64_t *count)
+{
+    PIB_CHECK(xyz || n == 0, PIB_ERR_INVALID, "triangle variogram: NULL pointer");
+    PIB_CHECK(tri_lags && sums && count && n >= 0 && n_lags >= 1, PIB_ERR_INVALID, "triangle variogram: bad arguments");
+    cudaStream_t stream;
+    PIB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    int rc;
+    {
+        Scratch ws(stream);
+        double *d_xyz, *d_sums;
+        int64_t *d_count;
+        rc = ws.alloc(&d_xyz, (size_t)n * 3);
+        if (rc == PIB_OK) rc = ws.alloc(&d_sums, (size_t)3 * n_lags);
+        if (rc == PIB_OK) rc = ws.alloc(&d_count, (size_t)n_lags);
+        cudaError_t e = cudaSuccess;
+        if (rc == PIB_OK && n > 0) e = cudaMemcpyAsync(d_xyz, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, stream);
+        if (rc == PIB_OK && e == cudaSuccess)
+            rc = variogram_triangle_device(d_xyz, n, tri_lags, n_lags, cos_t, sin_t, tolerance, d_sums, d_count, stream);
+        if (rc == PIB_OK && e == cudaSuccess) e = cudaMemcpyAsync(sums, d_sums, sizeof(double) * 3 * n_lags, cudaMemcpyDeviceToHost, stream);
+        if (rc == PIB_OK && e == cudaSuccess) e = cudaMemcpyAsync(count, d_count, sizeof(int64_t) * n_lags, cudaMemcpyDeviceToHost, stream);
+        if (rc == PIB_OK && e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { set_error(std::string("triangle variogram: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; }
     }
     cudaStreamSynchronize(stream);
     cudaStreamDestroy(stream);

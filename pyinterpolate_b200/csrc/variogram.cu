@@ -1261,4 +1261,139 @@ int variogram_weighted_device(const double *d_xyz, const double *d_weights, int6
     return PIB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Triangle ("t") directional selection — the reference's DEFAULT method:
+//   semivariogram/experimental/functions/directional.py:137-210 (from_triangle), :536-565
+//   distance/angular.py:283-339 generate_triangles / get_triangles_vertices, :375-409 select_points_within_triangle,
+//   :459-494 triangle_mask, :9-64 build_mask_indices, :188-218 clean_mask_indices
+// For a centre p and lag h the reference tests every q against two triangles sharing the base through p
+// (half width h*tol, perpendicular to the direction) with apexes at p +- h*(cos, sin): together a rhombus
+//   R_h(p) = { q : |u| + |v| / tol <= h },  (u, v) = (q - p) in the rotated frame.
+// The raw mask of lag k is "q in R_{h_k}(p)"; the cleaned mask is raw_k XOR raw_{k-1} (raw_0 for the first lag).
+// Exact arithmetic would put q into the single lag k* with h_{k*-1} < rho <= h_{k*}; the reference decides with
+// floating-point sign tests, so here
+//   * rho = |u| + |v|/tol is computed per ordered pair; when rho is farther than `band` from every lag edge the
+//     raw masks are certain (0 below k*, 1 from k* on) and the pair counts once, in lag k*;
+//   * otherwise (and always for q == p, which sits on the shared base edge of every triangle) the raw masks of
+//     the neighbouring lags are evaluated with the reference's own operation sequence (every +, -, * rounded
+//     separately, vertices p + offset with the offsets h*cos(..) computed on the host by numpy like the
+//     reference), so the cleaned masks are bit-identical.
+// One thread per centre point p (caller order), all q; per-lag sums through global fp64 REDs.
+// ---------------------------------------------------------------------------------------------
+struct TriLag {                   // per lag, host-computed with the reference's numpy calls
+    double h;
+    double apex_x, apex_y;        // h * cos(a), h * sin(a)
+    double inv_x, inv_y;          // (-h) * cos(a), (-h) * sin(a)
+    double a_x, a_y;              // (h tol) * cos(a + pi/2), (h tol) * sin(a + pi/2)
+    double c_x, c_y;              // (h tol) * cos(a - pi/2), (h tol) * sin(a - pi/2)
+};
+
+static __device__ __forceinline__ bool in_triangle_ref(double ax, double ay, double bx, double by, double cx, double cy,
+                                                       double qx, double qy)
+{
+    // distance/angular.py:393-407, operation for operation
+    const double s1 = __dsub_rn(__dmul_rn(__dsub_rn(qx, bx), __dsub_rn(ay, by)), __dmul_rn(__dsub_rn(ax, bx), __dsub_rn(qy, by)));
+    const double s2 = __dsub_rn(__dmul_rn(__dsub_rn(qx, cx), __dsub_rn(by, cy)), __dmul_rn(__dsub_rn(bx, cx), __dsub_rn(qy, cy)));
+    const double s3 = __dsub_rn(__dmul_rn(__dsub_rn(qx, ax), __dsub_rn(cy, ay)), __dmul_rn(__dsub_rn(cx, ax), __dsub_rn(qy, ay)));
+    const bool t1 = s1 < 0, t2 = s2 < 0, t3 = s3 < 0;
+    return (t1 && t2 && t3) || (!t1 && !t2 && !t3);
+}
+
+static __device__ __forceinline__ bool raw_mask_ref(const TriLag &L, double px, double py, double qx, double qy)
+{
+    const double ax = __dadd_rn(px, L.a_x), ay = __dadd_rn(py, L.a_y);          // base_a
+    const double cx = __dadd_rn(px, L.c_x), cy = __dadd_rn(py, L.c_y);          // base_b
+    const double bx = __dadd_rn(px, L.apex_x), by = __dadd_rn(py, L.apex_y);    // apex
+    const double ix = __dadd_rn(px, L.inv_x), iy = __dadd_rn(py, L.inv_y);      // inverted apex
+    return in_triangle_ref(ax, ay, bx, by, cx, cy, qx, qy) || in_triangle_ref(ax, ay, ix, iy, cx, cy, qx, qy);
+}
+
+__global__ void triangle_kernel(const double *__restrict__ xyz, int64_t n, const TriLag *__restrict__ lags, int n_lags,
+                                double cos_t, double sin_t, double inv_tol, double band_rel,
+                                double *__restrict__ sums /* [3][n_lags]: sq, prod, neighbour values */,
+                                unsigned long long *__restrict__ count)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const double h_max = lags[n_lags - 1].h;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+        for (int64_t j = 0; j < n; ++j) {
+            const double qx = xyz[3 * j], qy = xyz[3 * j + 1];
+            const double dx = qx - px, dy = qy - py;
+            const double u = dx * cos_t + dy * sin_t, v = dy * cos_t - dx * sin_t;
+            const double rho = fabs(u) + fabs(v) * inv_tol;
+            const double band = band_rel * (fabs(px) + fabs(py) + fabs(qx) + fabs(qy) + h_max) * (1.0 + inv_tol);
+            if (rho > h_max + band) continue;                       // outside every rhombus for certain
+            // k* = first lag with rho <= h_k
+            int lo = 0, hi = n_lags;                                // hi == n_lags: beyond the last lag
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (rho <= lags[mid].h) hi = mid; else lo = mid + 1; }
+            const int ks = lo;
+            // lags whose edge is within the band of rho need the reference's own test; q == p needs it everywhere
+            int k_first = ks, k_last = ks - 1;                      // empty range = everything certain
+            if (j == i) { k_first = 0; k_last = n_lags - 1; }
+            else {
+                if (ks < n_lags && lags[ks].h - rho <= band) k_last = ks;
+                if (ks > 0 && rho - lags[ks - 1].h <= band) { k_first = ks - 1; if (k_last < k_first) k_last = ks - 1; }
+                // (edges farther away than the neighbours of k* are farther than the band too: lags ascend)
+                while (k_first > 0 && rho - lags[k_first - 1].h <= band) --k_first;
+                while (k_last + 1 < n_lags && lags[k_last + 1].h - rho <= band) ++k_last;
+            }
+            const double qz = xyz[3 * j + 2];
+            const double dz = pz - qz;
+            if (k_last < k_first) {
+                if (ks < n_lags) {                                  // certain: counted once, in lag k*
+                    atomicAdd(&sums[ks], dz * dz);
+                    atomicAdd(&sums[n_lags + ks], pz * qz);
+                    atomicAdd(&sums[2 * n_lags + ks], qz);
+                    atomicAdd(&count[ks], 1ull);
+                }
+                continue;
+            }
+            // uncertain range [k_first, k_last]: raw masks from the reference's arithmetic, certain outside it
+            bool prev = (k_first > 0) ? (k_first - 1 >= ks) : false;           // raw_{k_first-1}: certain
+            for (int k = k_first; k <= min(k_last + 1, n_lags - 1); ++k) {
+                const bool raw = (k <= k_last) ? raw_mask_ref(lags[k], px, py, qx, qy) : (k >= ks);
+                const bool in_lag = (k == 0) ? raw : (raw != prev);            // clean_mask_indices: XOR with the previous lag
+                if (in_lag) {
+                    atomicAdd(&sums[k], dz * dz);
+                    atomicAdd(&sums[n_lags + k], pz * qz);
+                    atomicAdd(&sums[2 * n_lags + k], qz);
+                    atomicAdd(&count[k], 1ull);
+                }
+                prev = raw;
+            }
+            // lags beyond k_last + 1 are certain and equal to their predecessor (both 0 or both 1): nothing to add,
+            // except when k* lies beyond the uncertain range
+            if (ks > k_last + 1 && ks < n_lags) {
+                atomicAdd(&sums[ks], dz * dz);
+                atomicAdd(&sums[n_lags + ks], pz * qz);
+                atomicAdd(&sums[2 * n_lags + ks], qz);
+                atomicAdd(&count[ks], 1ull);
+            }
+        }
+    }
+}
+
+int variogram_triangle_device(const double *d_xyz, int64_t n, const double *tri_lags /* host [n_lags][9] */, int n_lags,
+                              double cos_t, double sin_t, double tolerance, double *d_sums, int64_t *d_count,
+                              cudaStream_t stream)
+{
+    PIB_CHECK(n >= 0 && n_lags >= 1 && tri_lags && d_sums && d_count, PIB_ERR_INVALID, "triangle variogram: bad arguments");
+    PIB_CHECK(tolerance > 0, PIB_ERR_INVALID, "triangle variogram: tolerance must be positive");
+    static_assert(sizeof(TriLag) == 9 * sizeof(double), "TriLag is nine doubles");
+    PIB_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * 3 * n_lags, stream));
+    PIB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t) * n_lags, stream));
+    if (n < 1) return PIB_OK;
+    Scratch ws(stream);
+    TriLag *d_lags;
+    PIB_TRY(ws.alloc(&d_lags, n_lags));
+    PIB_CUDA(cudaMemcpyAsync(d_lags, tri_lags, sizeof(TriLag) * n_lags, cudaMemcpyHostToDevice, stream));
+    const int grid = (int)std::min<int64_t>((n + 127) / 128, 8 * sm_count());
+    triangle_kernel<<<grid, 128, 0, stream>>>(d_xyz, n, d_lags, n_lags, cos_t, sin_t, 1.0 / tolerance, 1e-9, d_sums,
+                                              reinterpret_cast<unsigned long long *>(d_count));
+    PIB_CUDA(cudaGetLastError());
+    return PIB_OK;
+}
+
 }  // namespace pib

@@ -11,8 +11,8 @@ One kernel pass yields semivariance, covariance and pair counts together, so the
 both curves from a single launch where the reference runs its whole pipeline twice.
 The point cloud (``as_cloud=True`` / ``point_cloud_semivariance`` / ``VariogramCloud``) comes from a
 second kernel that writes (z_i - z_j)^2 per ordered pair in the reference's order.
-Not built yet (raise NotImplementedError, there is no CPU fallback): the triangle selection
-method ('t') and custom_weights.
+Directional variograms support both of the reference's selection methods: the ellipse ('e', tiled fast
+kernels) and the triangle ('t', the reference's default; exact reproduction of its floating-point masks).
 """
 from collections import OrderedDict
 
@@ -47,9 +47,36 @@ def _finalize(sums, directional):
 def _check_method(direction, method, custom_weights):
     if custom_weights is not None:
         return                              # the weighted directional path always selects with the ellipse
-    if direction is not None and method not in ("e", "ellipse"):
-        raise NotImplementedError("only dir_neighbors_selection_method='e' (ellipse) is implemented in "
-                                  "pyinterpolate_b200; the triangle method 't' is not built yet")
+    if direction is not None and method not in ("e", "ellipse", "t", "triangle"):
+        raise ValueError("dir_neighbors_selection_method must be 't' / 'triangle' or 'e' / 'ellipse'")
+
+
+def _triangle_lag_table(lags, direction, tolerance):
+    """Per-lag triangle offsets exactly as distance/angular.py:283-339 + :599-617 compute them
+    (``distance * np.cos(angle)`` with numpy scalars), handed to the kernel as nine doubles per lag."""
+    angle = np.radians(direction)
+    rot_90 = np.pi / 2
+    rows = []
+    for h in lags:
+        base_width = h * tolerance
+        rows.append([float(h),
+                     h * np.cos(float(angle)), h * np.sin(float(angle)),
+                     -h * np.cos(float(angle)), -h * np.sin(float(angle)),
+                     base_width * np.cos(angle + rot_90), base_width * np.sin(angle + rot_90),
+                     base_width * np.cos(angle - rot_90), base_width * np.sin(angle - rot_90)])
+    return np.array(rows, dtype=np.float64), float(np.cos(angle)), float(np.sin(angle))
+
+
+def _triangle_curves(xyz, lags, direction, tolerance):
+    """(semivariance, covariance, n_pairs) with the triangle selection: functions/directional.py:137-210.
+    The sums run over ORDERED pairs (centre, neighbour) because the reference's masks are evaluated per centre."""
+    table, c, s_ = _triangle_lag_table(lags, direction, tolerance)
+    sums, cnt = _lib.variogram_triangle_host(xyz, table, c, s_, tolerance)
+    n = cnt.astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sem = sums[0] / n / 2.0                                  # mean((v0 - vh)^2) / 2
+        cov = sums[1] / n - (sums[2] / n) ** 2                   # mean(v0 vh) - mean(vh)^2
+    return sem, cov, n
 
 
 def experimental_curves(ds, step_size=None, max_range=None, direction=None, tolerance=None,
@@ -76,15 +103,25 @@ def experimental_curves(ds, step_size=None, max_range=None, direction=None, tole
     if xyz.ndim != 2 or xyz.shape[1] < 3:
         raise ValueError("points must be rows of [x, y, value]")
     xyz = np.ascontiguousarray(xyz[:, [0, 1, xyz.shape[1] - 1]]) if xyz.shape[1] != 3 else xyz
-    if directional:
+    triangle = directional and dir_neighbors_selection_method in ("t", "triangle")
+    if triangle:
+        if shard != (0, 1):
+            raise NotImplementedError("the triangle method is not sharded across ranks")
         angles = [direction] if directions is None else list(directions)
-        W = np.stack([core.define_whitening_matrix(a, tolerance) for a in angles]).reshape(len(angles), 4)
-        sums = _lib.variogram_host(xyz, lags64, lower=core.ellipse_lower_limits(lags64), W=W, shard=shard)
+        curves = [_triangle_curves(xyz, lags, a, tolerance) for a in angles]
+        sem, cov, npairs = (np.stack([c[i] for c in curves]) for i in range(3))
+        empty = npairs == 0
+        sem, cov = np.where(empty, 0.0, sem), np.where(empty, 0.0, cov)
     else:
-        sums = _lib.variogram_host(xyz, lags64, shard=shard)
-    if reduce_fn is not None:
-        sums = reduce_fn(sums)
-    sem, cov, npairs = _finalize(sums, directional)
+        if directional:
+            angles = [direction] if directions is None else list(directions)
+            W = np.stack([core.define_whitening_matrix(a, tolerance) for a in angles]).reshape(len(angles), 4)
+            sums = _lib.variogram_host(xyz, lags64, lower=core.ellipse_lower_limits(lags64), W=W, shard=shard)
+        else:
+            sums = _lib.variogram_host(xyz, lags64, shard=shard)
+        if reduce_fn is not None:
+            sums = reduce_fn(sums)
+        sem, cov, npairs = _finalize(sums, directional)
     if directional:
         if directions is None:
             sem, cov, npairs = sem[0], cov[0], npairs[0]

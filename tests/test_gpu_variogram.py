@@ -238,8 +238,8 @@ def test_edge_cases(pib):
         pib.calculate_semivariance(pts)
     with pytest.raises(ValueError):
         pib.calculate_semivariance(pts, 1, 3, direction=10)
-    with pytest.raises(NotImplementedError):
-        pib.calculate_semivariance(pts, 1, 3, direction=10, tolerance=0.5)      # default method 't'
+    with pytest.raises(ValueError):
+        pib.calculate_semivariance(pts, 1, 3, direction=10, tolerance=0.5, dir_neighbors_selection_method="x")
     cloud = pib.ExperimentalVariogram(pts, 1, 3, as_cloud=True).point_cloud_semivariances
     assert [len(v) for v in cloud.values()] == [4, 2]          # np.arange(1, 3, 1) = two lags, ordered pairs
     with pytest.raises(_lib.PibError):
