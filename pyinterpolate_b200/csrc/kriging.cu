@@ -125,6 +125,8 @@ struct KnnParams {
     double range, direction;
     int last_tol;               // largest angular tolerance tried (degrees)
     int use_all;
+    int stride;                 // row stride of nbr_pos / nbr_d (>= kk)
+    int isotropic;              // range kernel without the angular filter (use_all_neighbors_in_range, isotropic model)
 };
 
 static __device__ __forceinline__ Cand make_cand(const GridIndex &g, int pos, double ux, double uy)
@@ -242,8 +244,8 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const KnnParams p)
                 for (int b = 0; b < E; ++b) {
                     const int t = lane * E + b;
                     if (t < kk) {
-                        p.nbr_pos[slot * kk + t] = c[b].pos;
-                        p.nbr_d[slot * kk + t] = c[b].d;
+                        p.nbr_pos[slot * p.stride + t] = c[b].pos;
+                        p.nbr_d[slot * p.stride + t] = c[b].d;
                     }
                     if (p.nbr_idx && t < p.k) p.nbr_idx[(int64_t)q * p.k + t] = t < kk ? c[b].orig : -1;
                 }
@@ -298,8 +300,8 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const KnnParams p)
     }
 
     for (int t = lane; t < kk; t += 32) {
-        p.nbr_pos[slot * kk + t] = top.best[t].pos;
-        p.nbr_d[slot * kk + t] = top.best[t].d;
+        p.nbr_pos[slot * p.stride + t] = top.best[t].pos;
+        p.nbr_d[slot * p.stride + t] = top.best[t].d;
     }
     if (p.nbr_idx)
         for (int t = lane; t < p.k; t += 32) p.nbr_idx[(int64_t)q * p.k + t] = t < kk ? top.best[t].orig : -1;
@@ -368,8 +370,8 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_dir_kernel(const KnnParams
                 double ad = 0.0;
                 if (pos < s1) {
                     c = make_cand(g, pos, ux, uy);
-                    if (c.d <= p.range) {                        // distances <= max_range (select_points.py:201)
-                        ad = angular_difference(ux, uy, g.x[pos], g.y[pos], p.direction);
+                    if (c.d <= p.range) {                        // distances <= max_range (select_points.py:201 / :93)
+                        ad = p.isotropic ? 0.0 : angular_difference(ux, uy, g.x[pos], g.y[pos], p.direction);
                         ok = true;
                     }
                 }
@@ -399,11 +401,24 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_dir_kernel(const KnnParams
     int found = 0;
     for (int t = lane; t < kk; t += 32) {
         const Cand c = top.best[t];
-        p.nbr_pos[slot * kk + t] = c.pos;
-        p.nbr_d[slot * kk + t] = c.d;
         found += (c.pos >= 0) ? 1 : 0;
     }
     for (int o = 16; o; o >>= 1) found += __shfl_xor_sync(0xffffffffu, found, o);
+    if (p.isotropic) {
+        // select_points.py:95-101: with at least k points in range ALL of them are used; otherwise the k nearest
+        // overall, which knn_kernel already wrote for this location — leave them
+        int in_range = 0;
+        for (int t = 1; t <= p.last_tol; ++t) in_range += hist[t];
+        if (in_range < p.k) {
+            if (lane == 0) p.nbr_count[slot] = min(p.k, (int)g.n);
+            return;
+        }
+    }
+    for (int t = lane; t < kk; t += 32) {
+        const Cand c = top.best[t];
+        p.nbr_pos[slot * p.stride + t] = c.pos;
+        p.nbr_d[slot * p.stride + t] = c.d;
+    }
     if (p.use_all) {                                             // all qualifying rows are wanted: did they fit?
         int qualifying = 0;
         for (int t = 1; t <= tol; ++t) qualifying += hist[t];
@@ -879,10 +894,9 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
                  double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, cudaStream_t stream)
 {
     const bool directional = !std::isnan(direction);
-    PIB_CHECK(directional || !use_all, PIB_ERR_UNSUPPORTED,
-              "krige: use_all_neighbors_in_range is only implemented for directional models");
-    PIB_CHECK(!directional || (neighbors_range > 0 && std::isfinite(neighbors_range)), PIB_ERR_INVALID,
-              "krige: directional selection needs a positive neighbors_range");
+    const bool ranged = directional || use_all;                 // the selection depends on neighbors_range
+    PIB_CHECK(!ranged || (neighbors_range > 0 && std::isfinite(neighbors_range)), PIB_ERR_INVALID,
+              "krige: directional / use_all selection needs a positive neighbors_range");
     PIB_CHECK(n >= 1 && m >= 0 && k >= 1, PIB_ERR_INVALID, "krige: need n >= 1, m >= 0, k >= 1");
     PIB_CHECK(n_sets >= 1 && params != nullptr, PIB_ERR_INVALID, "krige: need at least one parameter set");
     PIB_CHECK(model >= 0 && model <= 6, PIB_ERR_INVALID, "krige: unknown model id");
@@ -890,7 +904,7 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
     PIB_CHECK(m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31), PIB_ERR_UNSUPPORTED, "krige: more than 2^31-1 rows");
     PIB_CHECK(std::min<int64_t>(k, n) <= MAX_K, PIB_ERR_UNSUPPORTED, "krige: no_neighbors above 128 is not supported");
     const int kk = use_all ? (int)std::min<int64_t>(MAX_K, n) : (int)std::min<int64_t>(k, n);
-    int last_tol = 0;
+    int last_tol = 1;
     if (directional) {
         last_tol = std::max(2, (int)std::floor(max_tick) + 1);   // 1, 2, ... until the tolerance exceeds max_tick
         PIB_CHECK(last_tol <= MAX_TOL, PIB_ERR_UNSUPPORTED, "krige: max_tick above 63 degrees is not supported");
@@ -936,7 +950,8 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
     PIB_TRY(ws.alloc(&nbr_pos, (size_t)chunk * kk));
     PIB_TRY(ws.alloc(&nbr_d, (size_t)chunk * kk));
     int32_t *nbr_count = nullptr;
-    if (directional) PIB_TRY(ws.alloc(&nbr_count, (size_t)chunk));
+    if (ranged) PIB_TRY(ws.alloc(&nbr_count, (size_t)chunk));
+    const int ksel = (int)std::min<int64_t>(k, n);              // what the plain k-nearest search selects
 
     for (int64_t begin = 0; begin < m; begin += chunk) {
         const int64_t count = std::min(chunk, m - begin);
@@ -944,9 +959,15 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
         kp.g = g; kp.unknown = d_unknown; kp.order = order + begin; kp.count = count; kp.kk = kk; kp.k2 = k2; kp.r0 = r0;
         kp.nbr_pos = nbr_pos; kp.nbr_d = nbr_d; kp.nbr_idx = d_nbr_idx; kp.k = k;
         kp.nbr_count = nbr_count; kp.range = neighbors_range; kp.direction = direction; kp.last_tol = last_tol;
-        kp.use_all = use_all;
+        kp.use_all = use_all; kp.stride = kk; kp.isotropic = directional ? 0 : 1;
         timing_begin(PIB_T_KNN, stream);
-        if (directional)
+        if (!directional && use_all) {
+            // k nearest first (the fallback rows), then the range kernel replaces them where >= k points are in range
+            KnnParams kn = kp;
+            kn.kk = ksel;
+            knn_kernel<0><<<(int)((count + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, knn_smem, stream>>>(kn);
+            knn_dir_kernel<<<(int)((count + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, knn_smem, stream>>>(kp);
+        } else if (directional)
             knn_dir_kernel<<<(int)((count + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, knn_smem, stream>>>(kp);
         else if (knn_fast && kk <= 40)
             knn_kernel<4><<<(int)((count + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, knn_smem, stream>>>(kp);

@@ -9,8 +9,8 @@ Mirrors (file:line relative to /root/reference/src/pyinterpolate/):
 
 Models that carry a ``direction`` use the reference's angular neighbour selection
 (transform/select_points.py:104-257) inside ``neighbors_range`` (default: the model range).
-Not built yet (NotImplementedError, there is no CPU fallback): ``use_all_neighbors_in_range=True`` for
-isotropic models or with more than 128 rows in range, and ``allow_approximate_solutions=True`` (lstsq fallback).
+``use_all_neighbors_in_range=True`` is supported up to 128 rows per location (more raises NotImplementedError).
+Not built (NotImplementedError, there is no CPU fallback): ``allow_approximate_solutions=True`` (lstsq fallback).
 """
 import warnings
 
@@ -30,9 +30,6 @@ _SINGULAR_MSG = ("Singular matrix in Kriging system detected, "
 def _prepare(theoretical_model, known_locations, unknown_locations, use_all_neighbors_in_range,
              allow_approximate_solutions, neighbors_range=None, max_tick=5.):
     mid, nugget, sill, rang, direction = model_parameters(theoretical_model)
-    if use_all_neighbors_in_range and direction is None:
-        raise NotImplementedError("use_all_neighbors_in_range=True is only implemented for directional models "
-                                  "in pyinterpolate_b200")
     if allow_approximate_solutions:
         raise NotImplementedError("allow_approximate_solutions=True (least-squares fallback) is not implemented "
                                   "in pyinterpolate_b200 yet")

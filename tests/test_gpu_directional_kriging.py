@@ -46,3 +46,22 @@ def test_directional_kriging_golden(pib, case):
         np.testing.assert_allclose(got[:, :2], want[:, :2], rtol=1e-9, equal_nan=True)
         np.testing.assert_array_equal(got[:, 2:], want[:, 2:])
     assert (counts == 0).any() and (counts < k).any()            # the fixture really exercises short / empty sets
+
+
+def test_use_all_neighbors_in_range_isotropic_golden(pib):
+    """select_points.py:93-101: with >= k points inside the range ALL of them are used, otherwise the k nearest."""
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_use_all.npz"))
+    known = dem_like_field(20000, seed=61)
+    unk = uniform_locations(150, seed=63)
+    mdl = {"variogram_model_type": "exponential", "nugget": 0.5, "sill": float(gold["var"]), "rang": 2000.0}
+    ok = pib.ordinary_kriging(mdl, known, unk, no_neighbors=24, use_all_neighbors_in_range=True)
+    sk = pib.simple_kriging(mdl, known, unk, process_mean=float(known[:, 2].mean()), no_neighbors=24,
+                            use_all_neighbors_in_range=True)
+    np.testing.assert_allclose(ok[:, :2], gold["ok"][:, :2], rtol=1e-9)
+    np.testing.assert_allclose(sk[:, :2], gold["sk"][:, :2], rtol=1e-9)
+    ok3 = pib.ordinary_kriging(mdl, known, unk, neighbors_range=3000.0, no_neighbors=8, use_all_neighbors_in_range=True)
+    np.testing.assert_allclose(ok3[:, :2], gold["ok_range3000"][:, :2], rtol=1e-9)
+    assert (gold["counts"] > 24).any() and (gold["counts"] == 24).any() and gold["counts3000"].max() <= 128
+    # more than 128 rows in range is outside what the solvers hold
+    with pytest.raises(NotImplementedError):
+        pib.ordinary_kriging(mdl, known, unk[:4], neighbors_range=9000.0, no_neighbors=8, use_all_neighbors_in_range=True)

@@ -111,9 +111,6 @@ def test_edge_cases_golden(pib, golden):
         pib.ordinary_kriging({"variogram_model_type": "matern", "nugget": 0, "sill": 1, "rang": 1}, arm, unk)
     with pytest.raises(NotImplementedError):
         pib.ordinary_kriging({"variogram_model_type": "linear", "nugget": 0, "sill": 1, "rang": 1}, arm, unk,
-                             use_all_neighbors_in_range=True)          # isotropic use_all is not built
-    with pytest.raises(NotImplementedError):
-        pib.ordinary_kriging({"variogram_model_type": "linear", "nugget": 0, "sill": 1, "rang": 1}, arm, unk,
                              allow_approximate_solutions=True)
 
 
