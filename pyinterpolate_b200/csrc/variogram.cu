@@ -1194,42 +1194,66 @@ int variogram_cloud_device(const double *d_xyz, int64_t n, const double *edges, 
 //   s4 = sum (w_i + w_j)
 // One thread per point i over all j > i, global fp64 REDs (this path serves small areal data sets).
 // ---------------------------------------------------------------------------------------------
-__global__ void weighted_pair_kernel(const double *__restrict__ xyz, const double *__restrict__ wts, int64_t n,
+__global__ void gather_weights_kernel(const double *__restrict__ w, const int32_t *__restrict__ orig, int64_t n,
+                                      double *__restrict__ out)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = w[orig[i]];
+}
+
+// points are Hilbert sorted, so for a fixed i consecutive j fall into the same lag for long runs: a thread
+// accumulates a run in registers and issues its REDs only when the lag changes
+__global__ void weighted_pair_kernel(const double2 *__restrict__ xy, const double *__restrict__ z,
+                                     const double *__restrict__ wts, int64_t n,
                                      const double *__restrict__ up_d2, const double *__restrict__ low_d2, int n_lags,
                                      bool ellipse, double w00, double w01, double w10, double w11,
                                      double *__restrict__ sums /* [4][n_lags] */, unsigned long long *__restrict__ count)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double xi = xyz[3 * i], yi = xyz[3 * i + 1], zi = xyz[3 * i + 2], wi = wts[i];
+        const double2 pi = xy[i];
+        const double zi = z[i], wi = wts[i];
         const double ui = zi / wi;
+        int run = -1;
+        double r1 = 0, r2 = 0, r3 = 0, r4 = 0;
+        unsigned long long rc = 0;
+        auto flush = [&]() {
+            if (run >= 0 && rc) {
+                atomicAdd(&sums[run], r1); atomicAdd(&sums[n_lags + run], r2);
+                atomicAdd(&sums[2 * n_lags + run], r3); atomicAdd(&sums[3 * n_lags + run], r4);
+                atomicAdd(&count[run], rc);
+            }
+            r1 = r2 = r3 = r4 = 0; rc = 0;
+        };
         for (int64_t j = i + 1; j < n; ++j) {
+            const double2 pj = xy[j];
             double d2;
             if (ellipse) {
-                const double dx = __dsub_rn(xyz[3 * j], xi), dy = __dsub_rn(xyz[3 * j + 1], yi);
+                const double dx = __dsub_rn(pj.x, pi.x), dy = __dsub_rn(pj.y, pi.y);
                 const double n0 = __fma_rn(w01, dy, __dmul_rn(w00, dx));
                 const double n1 = __fma_rn(w11, dy, __dmul_rn(w10, dx));
                 d2 = __dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1));
             } else {
-                const double dx = __dsub_rn(xi, xyz[3 * j]), dy = __dsub_rn(yi, xyz[3 * j + 1]);
+                const double dx = __dsub_rn(pi.x, pj.x), dy = __dsub_rn(pi.y, pj.y);
                 d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
             }
-            if (!(d2 > 0.0)) continue;
-            for (int b = 0; b < n_lags; ++b) {
-                if (d2 <= up_d2[b] && d2 > low_d2[b]) {
-                    const double zj = xyz[3 * j + 2], wj = wts[j];
-                    const double wp = (wi * wj) / (wi + wj);
-                    double q, f;
-                    if (ellipse) { const double dz = zj - zi; q = dz * dz; f = wi * zi + wj * zj; }
-                    else { const double du = ui - zj / wj; q = du * du; f = ui + zj / wj; }
-                    atomicAdd(&sums[b], wp * q);
-                    atomicAdd(&sums[n_lags + b], wp);
-                    atomicAdd(&sums[2 * n_lags + b], f);
-                    atomicAdd(&sums[3 * n_lags + b], wi + wj);
-                    atomicAdd(&count[b], 1ull);
-                }
+            if (!(d2 > 0.0) || d2 > up_d2[n_lags - 1]) continue;
+            // fast check of the current run's lag, else search (lags are disjoint here: regular limits are required)
+            int b = run;
+            if (b < 0 || !(d2 <= up_d2[b] && d2 > low_d2[b])) {
+                int lo = 0, hi = n_lags - 1;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (d2 <= up_d2[mid]) hi = mid; else lo = mid + 1; }
+                b = (d2 > low_d2[lo]) ? lo : -1;
+                if (b < 0) continue;
+                if (b != run) { flush(); run = b; }
             }
+            const double zj = z[j], wj = wts[j];
+            const double wp = (wi * wj) / (wi + wj);
+            if (ellipse) { const double dz = zj - zi; r1 += wp * (dz * dz); r3 += wi * zi + wj * zj; }
+            else { const double uj = zj / wj, du = ui - uj; r1 += wp * (du * du); r3 += ui + uj; }
+            r2 += wp; r4 += wi + wj; ++rc;
         }
+        flush();
     }
 }
 
@@ -1252,8 +1276,17 @@ int variogram_weighted_device(const double *d_xyz, const double *d_weights, int6
     PIB_TRY(ws.alloc(&d_up, n_lags)); PIB_TRY(ws.alloc(&d_low, n_lags));
     PIB_CUDA(cudaMemcpyAsync(d_up, up.data(), n_lags * sizeof(double), cudaMemcpyHostToDevice, stream));
     PIB_CUDA(cudaMemcpyAsync(d_low, low.data(), n_lags * sizeof(double), cudaMemcpyHostToDevice, stream));
+    for (int b = 0; b < n_lags; ++b)       // the run-length kernel assumes disjoint lags
+        PIB_CHECK(low[b] == (b ? up[b - 1] : 0.0), PIB_ERR_UNSUPPORTED,
+                  "weighted variogram: irregular ellipse limits (lag - (lag - prev) != prev) are not supported");
+    SortedPoints sp;
+    PIB_TRY(build_sorted_points(d_xyz, n, TILE, TILE, ws, stream, &sp));
+    double *d_ws;
+    PIB_TRY(ws.alloc(&d_ws, (size_t)n));
+    gather_weights_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(d_weights, sp.orig, n, d_ws);
+    PIB_CUDA(cudaGetLastError());
     const int grid = (int)std::min<int64_t>((n + 127) / 128, 8 * sm_count());
-    weighted_pair_kernel<<<grid, 128, 0, stream>>>(d_xyz, d_weights, n, d_up, d_low, n_lags, n_dirs > 0,
+    weighted_pair_kernel<<<grid, 128, 0, stream>>>(sp.xy, sp.z, d_ws, n, d_up, d_low, n_lags, n_dirs > 0,
                                                    n_dirs ? W[0] : 0, n_dirs ? W[1] : 0, n_dirs ? W[2] : 0,
                                                    n_dirs ? W[3] : 0, d_sums,
                                                    reinterpret_cast<unsigned long long *>(d_count));
@@ -1309,7 +1342,8 @@ static __device__ __forceinline__ bool raw_mask_ref(const TriLag &L, double px, 
     return in_triangle_ref(ax, ay, bx, by, cx, cy, qx, qy) || in_triangle_ref(ax, ay, ix, iy, cx, cy, qx, qy);
 }
 
-__global__ void triangle_kernel(const double *__restrict__ xyz, int64_t n, const TriLag *__restrict__ lags, int n_lags,
+__global__ void triangle_kernel(const double2 *__restrict__ xy, const double *__restrict__ z, const int32_t *__restrict__ orig,
+                                int64_t n, const TriLag *__restrict__ lags, int n_lags,
                                 double cos_t, double sin_t, double inv_tol, double band_rel,
                                 double *__restrict__ sums /* [3][n_lags]: sq, prod, neighbour values */,
                                 unsigned long long *__restrict__ count)
@@ -1317,9 +1351,20 @@ __global__ void triangle_kernel(const double *__restrict__ xyz, int64_t n, const
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const double h_max = lags[n_lags - 1].h;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+        const double px = xy[i].x, py = xy[i].y, pz = z[i];
+        // certain pairs of the same lag come in runs (Hilbert order): accumulate a run in registers
+        int run = -1;
+        double r1 = 0, r2 = 0, r3 = 0;
+        unsigned long long rc = 0;
+        auto flush = [&]() {
+            if (run >= 0 && rc) {
+                atomicAdd(&sums[run], r1); atomicAdd(&sums[n_lags + run], r2); atomicAdd(&sums[2 * n_lags + run], r3);
+                atomicAdd(&count[run], rc);
+            }
+            r1 = r2 = r3 = 0; rc = 0;
+        };
         for (int64_t j = 0; j < n; ++j) {
-            const double qx = xyz[3 * j], qy = xyz[3 * j + 1];
+            const double qx = xy[j].x, qy = xy[j].y;
             const double dx = qx - px, dy = qy - py;
             const double u = dx * cos_t + dy * sin_t, v = dy * cos_t - dx * sin_t;
             const double rho = fabs(u) + fabs(v) * inv_tol;
@@ -1331,7 +1376,7 @@ __global__ void triangle_kernel(const double *__restrict__ xyz, int64_t n, const
             const int ks = lo;
             // lags whose edge is within the band of rho need the reference's own test; q == p needs it everywhere
             int k_first = ks, k_last = ks - 1;                      // empty range = everything certain
-            if (j == i) { k_first = 0; k_last = n_lags - 1; }
+            if (orig[j] == orig[i]) { k_first = 0; k_last = n_lags - 1; }
             else {
                 if (ks < n_lags && lags[ks].h - rho <= band) k_last = ks;
                 if (ks > 0 && rho - lags[ks - 1].h <= band) { k_first = ks - 1; if (k_last < k_first) k_last = ks - 1; }
@@ -1339,14 +1384,12 @@ __global__ void triangle_kernel(const double *__restrict__ xyz, int64_t n, const
                 while (k_first > 0 && rho - lags[k_first - 1].h <= band) --k_first;
                 while (k_last + 1 < n_lags && lags[k_last + 1].h - rho <= band) ++k_last;
             }
-            const double qz = xyz[3 * j + 2];
+            const double qz = z[j];
             const double dz = pz - qz;
             if (k_last < k_first) {
                 if (ks < n_lags) {                                  // certain: counted once, in lag k*
-                    atomicAdd(&sums[ks], dz * dz);
-                    atomicAdd(&sums[n_lags + ks], pz * qz);
-                    atomicAdd(&sums[2 * n_lags + ks], qz);
-                    atomicAdd(&count[ks], 1ull);
+                    if (ks != run) { flush(); run = ks; }
+                    r1 += dz * dz; r2 += pz * qz; r3 += qz; ++rc;
                 }
                 continue;
             }
@@ -1372,6 +1415,7 @@ __global__ void triangle_kernel(const double *__restrict__ xyz, int64_t n, const
                 atomicAdd(&count[ks], 1ull);
             }
         }
+        flush();
     }
 }
 
@@ -1389,8 +1433,10 @@ int variogram_triangle_device(const double *d_xyz, int64_t n, const double *tri_
     TriLag *d_lags;
     PIB_TRY(ws.alloc(&d_lags, n_lags));
     PIB_CUDA(cudaMemcpyAsync(d_lags, tri_lags, sizeof(TriLag) * n_lags, cudaMemcpyHostToDevice, stream));
+    SortedPoints sp;
+    PIB_TRY(build_sorted_points(d_xyz, n, TILE, TILE, ws, stream, &sp));
     const int grid = (int)std::min<int64_t>((n + 127) / 128, 8 * sm_count());
-    triangle_kernel<<<grid, 128, 0, stream>>>(d_xyz, n, d_lags, n_lags, cos_t, sin_t, 1.0 / tolerance, 1e-9, d_sums,
+    triangle_kernel<<<grid, 128, 0, stream>>>(sp.xy, sp.z, sp.orig, n, d_lags, n_lags, cos_t, sin_t, 1.0 / tolerance, 1e-9, d_sums,
                                               reinterpret_cast<unsigned long long *>(d_count));
     PIB_CUDA(cudaGetLastError());
     return PIB_OK;
