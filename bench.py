@@ -337,6 +337,19 @@ def run_b200(args):
                                         "solve_frac_of_fp64_peak": solve_flop / (solve_ms * 1e-3) / 1e12 / fp64_peak,
                                         "scaling": "weak"}
 
+    # CPU restatement of the kriging path on the host cores (bounded sample), for context next to the GPU numbers
+    if rank == 0 and not args.no_extra:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+        oracle.set_threads(os.cpu_count() or 1)
+        var = float(np.var(pts[:, 2]))
+        sample = uniform_locations(64 * max(1, oracle.num_threads()), extent=EXTENT, seed=99)
+        t0 = time.perf_counter()
+        oracle.krige(pts, sample, "linear", 0.0, var, 8000.0, 32, "ok")
+        dt = time.perf_counter() - t0
+        extra["cpu_port_kriged_points_per_s_ok_k32"] = {"value": len(sample) / dt, "cores": oracle.num_threads(),
+                                                         "sample": f"{len(sample)} locations against {n} known points in {dt:.1f} s"}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",

@@ -156,3 +156,33 @@ def test_two_rank_gloo_allreduce_and_gather(tmp_path, oracle):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+def test_triangle_lag_table_matches_reference_vertices():
+    """The nine doubles per lag handed to the triangle kernel are the reference's own vertex offsets
+    (distance/angular.py:283-339 generate_triangles): apex = p + (h cos a, h sin a), base = p +- (h tol)(cos, sin)(a +- 90)."""
+    from pyinterpolate_b200.variogram import _triangle_lag_table
+    lags = np.arange(500.0, 3000.0, 500.0)
+    table, c, s = _triangle_lag_table(lags, 30.0, 0.2)
+    assert table.shape == (5, 9)
+    a = np.radians(30.0)
+    np.testing.assert_array_equal(table[:, 0], lags)
+    np.testing.assert_array_equal(table[:, 1], lags * np.cos(float(a)))
+    np.testing.assert_array_equal(table[:, 3], -lags * np.cos(float(a)))
+    np.testing.assert_array_equal(table[:, 5], (lags * 0.2) * np.cos(a + np.pi / 2))
+    np.testing.assert_array_equal(table[:, 8], (lags * 0.2) * np.sin(a - np.pi / 2))
+    assert c == float(np.cos(a)) and s == float(np.sin(a))
+    # integer lags (np.arange of ints) give the same doubles
+    t_int, _, _ = _triangle_lag_table(np.arange(1, 4, 1), 15, 0.25)
+    t_flt, _, _ = _triangle_lag_table(np.arange(1.0, 4.0, 1.0), 15, 0.25)
+    np.testing.assert_array_equal(t_int, t_flt)
+
+
+def test_indicator_coding_and_thresholds():
+    from pyinterpolate_b200.indicator import IndicatorVariogramData, code_indicators, select_variogram_thresholds
+    ds = np.column_stack([np.arange(10.0), np.arange(10.0), np.arange(10.0)])
+    thr = select_variogram_thresholds(ds[:, 2], 4)
+    assert thr == [np.quantile(ds[:, 2], q) for q in (0.25, 0.5, 0.75, 1.0)]
+    ids = code_indicators(ds, thr)
+    assert ids.shape == (10, 6) and ids[:, 2:].sum(axis=0).tolist() == [3, 5, 7, 10]
+    assert IndicatorVariogramData(ds, 4).ids.shape == (10, 6)
