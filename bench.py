@@ -190,6 +190,11 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything native libraries print there (NCCL's version banner)
+    # goes to stderr while the run is in progress
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference for the CPU leg)")
     torch.cuda.set_device(local_rank)
@@ -360,9 +365,12 @@ def run_b200(args):
                 "gpu_launches_note": "per step: bbox_partial, curve_key, gather_soa, tile_box, pair_ring, reduce_partials "
                                      "(+ CUB radix-sort passes and memsets, not counted)",
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "extra": extra}
-        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
