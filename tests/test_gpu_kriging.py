@@ -191,3 +191,19 @@ def test_large_batch_properties(pib):
     np.testing.assert_array_equal(d_out[0].cpu().numpy(), out[0, :100_000])
     # predictions stay inside the data range up to the kriging overshoot one expects from a smooth field
     assert out[0, :, 0].min() > known[:, 2].min() - 10 and out[0, :, 0].max() < known[:, 2].max() + 10
+
+
+def test_more_locations_than_one_chunk(pib):
+    """The library processes locations in chunks of 2^21; 2.6M locations cross a chunk boundary
+    (BASELINE config 4 has 10M).  Results must not depend on where the boundaries fall."""
+    from pyinterpolate_b200 import _lib
+    known = dem_like_field(200_000, seed=4)
+    m = (1 << 21) + 500_001
+    unk = uniform_locations(m, seed=15)
+    params = np.array([[1.0, float(np.var(known[:, 2])), 20000.0]])
+    out, _, st = _lib.krige_host(known, unk, _lib.MODEL_IDS["spherical"], params, _lib.KRIGE_ORDINARY, 8)
+    assert (st == 0).all() and np.isfinite(out[0, :, :2]).all()
+    np.testing.assert_array_equal(out[0, :, 2:], unk)
+    lo = (1 << 21) - 1000
+    part, _, _ = _lib.krige_host(known, unk[lo:lo + 3000], _lib.MODEL_IDS["spherical"], params, _lib.KRIGE_ORDINARY, 8)
+    np.testing.assert_array_equal(part[0], out[0, lo:lo + 3000])
