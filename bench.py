@@ -342,6 +342,19 @@ def run_b200(args):
                                         "solve_frac_of_fp64_peak": solve_flop / (solve_ms * 1e-3) / 1e12 / fp64_peak,
                                         "scaling": "weak"}
 
+    # kriging end to end through the public Python call (host arrays in, host array out), rank 0 only
+    if rank == 0 and not args.no_extra:
+        import pyinterpolate_b200 as pib
+        var = float(np.var(pts[:, 2]))
+        unk_h = uniform_locations(1_000_000, extent=EXTENT, seed=5)
+        mdl = {"variogram_model_type": "linear", "nugget": 0.0, "sill": var, "rang": 8000.0}
+        pib.ordinary_kriging(mdl, pts, unk_h[:1000], no_neighbors=32)
+        t0 = time.perf_counter()
+        res = pib.ordinary_kriging(mdl, pts, unk_h, no_neighbors=32)
+        dt = time.perf_counter() - t0
+        extra["kriged_points_per_s_ok_k32_public_api_host_buffers"] = {
+            "value": len(unk_h) / dt, "h2d_bytes": int(pts.nbytes + unk_h.nbytes), "d2h_bytes": int(res.nbytes + len(unk_h))}
+
     # CPU restatement of the kriging path on the host cores (bounded sample), for context next to the GPU numbers
     if rank == 0 and not args.no_extra:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
