@@ -57,6 +57,10 @@ extern "C" {
 #define PIB_STATUS_SINGULAR 1        /* zero pivot: the reference raises RuntimeError (kriging/utils/errors.py:1-15) */
 #define PIB_STATUS_NEGATIVE_VARIANCE 2 /* sigma^2 < 0 -> NaN, like ordinary.py:125-126 */
 #define PIB_STATUS_TOO_MANY_NEIGHBORS 3 /* use_all_neighbors_in_range selected more than 128 rows (unsupported) */
+#define PIB_STATUS_LSA 4             /* singular system solved by least squares (allow_lsa): the reference warns
+                                        LeastSquaresApproximationWarning (kriging/utils/point_kriging_solve.py:142-145) */
+#define PIB_STATUS_ZERO_MATRIX 5     /* singular system whose matrix or right-hand side is all zero: weights = 0 and
+                                        ZerosMatrixWarning (point_kriging_solve.py:138-140) */
 
 PIB_API const char *pib_last_error(void);
 PIB_API int pib_version(void);
@@ -200,19 +204,24 @@ PIB_API int pib_krige_host(const double *known, int64_t n,
  *                  neighbors_range are filtered by their angular difference to it, the tolerance is widened 1, 2, ...
  *                  degrees until k qualify or it exceeds max_tick (transform/select_points.py:104-257); a location
  *                  may end up with fewer than k neighbours, or none (-> NaN row, like the reference)
- * use_all          use_all_neighbors_in_range (directional only; at most 128 rows, else status 3) */
+ * use_all          use_all_neighbors_in_range (at most 128 rows, else status 3)
+ * allow_lsa        allow_approximate_solutions: a singular system (zero pivot, what makes np.linalg.solve raise) is
+ *                  solved like np.linalg.lstsq(A, b, rcond=None) — minimum-norm least squares, singular values below
+ *                  eps * dim * s_max dropped — and marked PIB_STATUS_LSA (point_kriging_solve.py:134-147).
+ *                  Independently of the flag, a singular system with an all-zero matrix or right-hand side gets zero
+ *                  weights and PIB_STATUS_ZERO_MATRIX. */
 PIB_API int pib_krige_ex_device(const double *d_known, int64_t n,
                         const double *d_values, int n_sets, const double *params,
                         const double *d_unknown, int64_t m,
                         int model, int mode, double process_mean, int k,
-                        double neighbors_range, double direction, double max_tick, int use_all,
+                        double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
                         double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, void *stream);
 
 PIB_API int pib_krige_ex_host(const double *known, int64_t n,
                       const double *values, int n_sets, const double *params,
                       const double *unknown, int64_t m,
                       int model, int mode, double process_mean, int k,
-                      double neighbors_range, double direction, double max_tick, int use_all,
+                      double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
                       double *out, int32_t *nbr_idx, uint8_t *status);
 
 /* gamma(h) for h[0..n) with the device implementation of the seven models (for tests) */

@@ -183,3 +183,44 @@ def krige(known, unknown, model, nugget, sill, rang, no_neighbors, mode="ok", pr
                        float(rang), k, 0 if mode == "ok" else 1, float(process_mean),
                        _dp(out), _ip(idx), status.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
     return out, idx, status
+
+
+def krige_with_fallback(known, unknown, model, nugget, sill, rang, no_neighbors, mode="ok", process_mean=0.0,
+                        allow_lsa=True):
+    """``krige`` plus the reference's singular-system fallbacks (kriging/utils/point_kriging_solve.py:134-147):
+    a system whose LU meets a zero pivot gets zero weights when mean(A) == 0 or mean(b) == 0 (status 5), the
+    ``np.linalg.lstsq(A, b, rcond=None)`` solution when ``allow_lsa`` (status 4), else stays status 1.
+    Plain numpy per singular row — small cases only."""
+    known = np.ascontiguousarray(np.asarray(known, dtype=np.float64))
+    out, idx, status = krige(known, unknown, model, nugget, sill, rang, no_neighbors, mode, process_mean)
+    for u in np.nonzero(status == 1)[0]:
+        nb = known[idx[u][idx[u] >= 0]]
+        kk = len(nb)
+        dx = nb[:, None, 0] - nb[None, :, 0]
+        dy = nb[:, None, 1] - nb[None, :, 1]
+        big = gamma(model, np.sqrt(dx * dx + dy * dy), nugget, sill, rang)
+        ux, uy = out[u, 2], out[u, 3]
+        ddx, ddy = ux - nb[:, 0], uy - nb[:, 1]
+        kvec = gamma(model, np.sqrt(ddx * ddx + ddy * ddy), nugget, sill, rang)
+        if mode == "ok":                                         # ordinary.py:108-115
+            a = np.zeros((kk + 1, kk + 1))
+            a[:kk, :kk] = big
+            a[kk, :kk] = 1.0
+            a[:kk, kk] = 1.0
+            b = np.append(kvec, 1.0)
+        else:
+            a, b = big, kvec
+        if np.mean(a) == 0 or np.mean(b) == 0:
+            w = np.zeros(len(b))
+            status[u] = 5
+        elif allow_lsa:
+            w = np.linalg.lstsq(a, b, rcond=None)[0]
+            status[u] = 4
+        else:
+            continue
+        z = nb[:, 2]
+        zhat = z.dot(w[:kk]) if mode == "ok" else (z - process_mean).dot(w[:kk]) + process_mean
+        sigma = w.dot(b)
+        out[u, 0] = zhat
+        out[u, 1] = np.nan if sigma < 0 else sigma
+    return out, idx, status

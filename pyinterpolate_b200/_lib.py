@@ -17,6 +17,7 @@ KRIGE_ORDINARY, KRIGE_SIMPLE = 0, 1
 STATUS_OK, STATUS_SINGULAR, STATUS_NEGATIVE_VARIANCE = 0, 1, 2
 
 STATUS_TOO_MANY_NEIGHBORS = 3
+STATUS_LSA, STATUS_ZERO_MATRIX = 4, 5
 
 EXPORTS = ("pib_krige_ex_device", "pib_krige_ex_host", "pib_last_error", "pib_version", "pib_device_sm_count", "pib_variogram_device",
            "pib_variogram_host", "pib_krige_device", "pib_krige_host", "pib_gamma_host",
@@ -50,7 +51,7 @@ def load():
     kr_args = [dp, i64, dp, i32, dp, dp, i64, i32, i32, f64, i32, dp, dp, dp]
     L.pib_krige_device.argtypes = kr_args + [ctypes.c_void_p]
     L.pib_krige_host.argtypes = kr_args
-    kr_ex = kr_args[:11] + [f64, f64, f64, i32] + kr_args[11:]
+    kr_ex = kr_args[:11] + [f64, f64, f64, i32, i32] + kr_args[11:]
     L.pib_krige_ex_device.argtypes = kr_ex + [ctypes.c_void_p]
     L.pib_krige_ex_host.argtypes = kr_ex
     L.pib_gamma_host.argtypes = [i32, f64, f64, f64, dp, i64, dp]
@@ -173,9 +174,11 @@ def variogram_device(xyz_t, edges, lower=None, W=None, shard=(0, 1), want_pairs=
 
 
 def krige_host(known, unknown, model, params, mode, k, process_mean=0.0, values=None,
-               want_neighbors=False, neighbors_range=0.0, direction=None, max_tick=5.0, use_all=False):
+               want_neighbors=False, neighbors_range=0.0, direction=None, max_tick=5.0, use_all=False,
+               allow_lsa=False):
     """Host-buffer call. ``params`` is ``[n_sets, 3]`` (nugget, sill, rang).  ``direction`` (degrees) switches to
-    the directional neighbour selection within ``neighbors_range``.
+    the directional neighbour selection within ``neighbors_range``; ``allow_lsa`` solves singular systems by least
+    squares (status 4) instead of leaving them marked singular (status 1).
     Returns (out[n_sets, m, 4], nbr_idx[m, k] or None, status[n_sets, m])."""
     L = load()
     known, unknown = _f64(known), _f64(unknown).reshape(-1, 2)
@@ -188,7 +191,7 @@ def krige_host(known, unknown, model, params, mode, k, process_mean=0.0, values=
     rc = L.pib_krige_ex_host(_host_ptr(known), n, _host_ptr(values_c), n_sets, _host_ptr(params), _host_ptr(unknown), m,
                              int(model), int(mode), float(process_mean), int(k), float(neighbors_range),
                              float("nan") if direction is None else float(direction), float(max_tick),
-                             1 if use_all else 0, _host_ptr(out), _host_ptr(idx), _host_ptr(status))
+                             1 if use_all else 0, 1 if allow_lsa else 0, _host_ptr(out), _host_ptr(idx), _host_ptr(status))
     check(rc, "pib_krige_ex_host")
     return out, idx, status
 

@@ -78,7 +78,7 @@ int variogram_triangle_device(const double *d_xyz, int64_t n, const double *tri_
                               double sin_t, double tolerance, double *d_sums, int64_t *d_count, cudaStream_t stream);
 int krige_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
                  const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
-                 double neighbors_range, double direction, double max_tick, int use_all,
+                 double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
                  double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, cudaStream_t stream);
 int gamma_device(int model, double nugget, double sill, double rang, const double *d_h, int64_t n, double *d_out,
                  cudaStream_t stream);
@@ -250,12 +250,12 @@ int pib_variogram_cloud_host(const double *xyz, int64_t n, const double *edges, 
 
 int pib_krige_ex_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
                         const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
-                        double neighbors_range, double direction, double max_tick, int use_all,
+                        double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
                         double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, void *stream)
 {
     PIB_CHECK(d_known && (d_unknown || m == 0) && (d_out || m == 0), PIB_ERR_INVALID, "krige: NULL pointer");
     return krige_device(d_known, n, d_values, n_sets, params, d_unknown, m, model, mode, process_mean, k,
-                        neighbors_range, direction, max_tick, use_all, d_out, d_nbr_idx, d_status,
+                        neighbors_range, direction, max_tick, use_all, allow_lsa, d_out, d_nbr_idx, d_status,
                         static_cast<cudaStream_t>(stream));
 }
 
@@ -264,7 +264,7 @@ int pib_krige_device(const double *d_known, int64_t n, const double *d_values, i
                      double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, void *stream)
 {
     return pib_krige_ex_device(d_known, n, d_values, n_sets, params, d_unknown, m, model, mode, process_mean, k, 0.0,
-                               nan(""), 0.0, 0, d_out, d_nbr_idx, d_status, stream);
+                               nan(""), 0.0, 0, 0, d_out, d_nbr_idx, d_status, stream);
 }
 
 int pib_krige_host(const double *known, int64_t n, const double *values, int n_sets, const double *params,
@@ -272,13 +272,13 @@ int pib_krige_host(const double *known, int64_t n, const double *values, int n_s
                    int32_t *nbr_idx, uint8_t *status)
 {
     return pib_krige_ex_host(known, n, values, n_sets, params, unknown, m, model, mode, process_mean, k, 0.0, nan(""),
-                             0.0, 0, out, nbr_idx, status);
+                             0.0, 0, 0, out, nbr_idx, status);
 }
 
 int pib_krige_ex_host(const double *known, int64_t n, const double *values, int n_sets, const double *params,
                       const double *unknown, int64_t m, int model, int mode, double process_mean, int k,
-                      double neighbors_range, double direction, double max_tick, int use_all, double *out,
-                      int32_t *nbr_idx, uint8_t *status)
+                      double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
+                      double *out, int32_t *nbr_idx, uint8_t *status)
 {
     PIB_CHECK(known && (unknown || m == 0) && (out || m == 0), PIB_ERR_INVALID, "krige: NULL pointer");
     PIB_CHECK(n >= 1 && m >= 0 && k >= 1 && n_sets >= 1, PIB_ERR_INVALID, "krige: need n >= 1, m >= 0, k >= 1");
@@ -307,7 +307,7 @@ int pib_krige_ex_host(const double *known, int64_t n, const double *values, int 
         }
         if (rc == PIB_OK)
             rc = krige_device(d_known, n, d_values, n_sets, params, d_unknown, m, model, mode, process_mean, k,
-                              neighbors_range, direction, max_tick, use_all, d_out, d_idx, d_status, stream);
+                              neighbors_range, direction, max_tick, use_all, allow_lsa, d_out, d_idx, d_status, stream);
         if (rc == PIB_OK) {
             e = cudaMemcpyAsync(out, d_out, sizeof(double) * 4 * n_sets * m, cudaMemcpyDeviceToHost, stream);
             if (e == cudaSuccess && nbr_idx) e = cudaMemcpyAsync(nbr_idx, d_idx, sizeof(int32_t) * m * k, cudaMemcpyDeviceToHost, stream);

@@ -537,10 +537,12 @@ __global__ void solve_kernel(const SolveParams p)
     for (int set = 0; set < p.n_sets; ++set) {
         const double nugget = p.params[3 * set], sill = p.params[3 * set + 1], rang = p.params[3 * set + 2];
         // ---- assemble [Gamma 1; 1^T 0 | k 1] in the reference's row order (ordinary.py:108-115) ----
+        bool dup = false;
         for (int i = 0; i < kk; ++i) {
             for (int j = i + 1 + lane; j < kk; j += 32) {
                 const double dx = __dsub_rn(nx[i], nx[j]), dy = __dsub_rn(ny[i], ny[j]);
                 const double h = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                dup |= (h == 0.0);
                 const double gm = gamma_model(p.model, h, nugget, sill, rang);
                 A[i * st + j] = gm; A[j * st + i] = gm;
             }
@@ -555,8 +557,9 @@ __global__ void solve_kernel(const SolveParams p)
         __syncwarp();
 
         // ---- LU with partial pivoting on the augmented matrix (dgesv: dgetrf + dgetrs) ----------
-        bool singular = false;
-        for (int j = 0; j < dim; ++j) {
+        // duplicated coordinates among the neighbours = two identical rows: always singular (see solve_reg_kernel)
+        bool singular = __any_sync(0xffffffffu, dup);
+        for (int j = 0; j < dim && !singular; ++j) {
             double bv = -1.0; int bi = j;
             for (int r = j + lane; r < dim; r += 32) {
                 const double v = fabs(A[r * st + j]);
@@ -659,6 +662,7 @@ struct RegSysSmem {
     double redv[4];
     long long redk[2];
     int redi[4];
+    int dup;                   // a neighbour pair at distance 0 (duplicated coordinates): the system is singular
 };
 
 template <int K, bool ORD>
@@ -700,6 +704,7 @@ __global__ void __launch_bounds__(256) solve_reg_kernel(const SolveParams p)
     } else if (t < K) {
         S.nxy[t] = make_double2(0.0, 0.0);
     }
+    if (t == 0) S.dup = 0;
     sys_sync<TPS>(sid);
     const double2 me = (t < K) ? S.nxy[t] : make_double2(0.0, 0.0);
 
@@ -716,7 +721,9 @@ __global__ void __launch_bounds__(256) solve_reg_kernel(const SolveParams p)
                 if (t < kk && c < kk) {
                     const double2 o = S.nxy[c];
                     const double dx = __dsub_rn(me.x, o.x), dy = __dsub_rn(me.y, o.y);
-                    v = gamma_model(p.model, sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))), nugget, sill, rang);
+                    const double h = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                    if (h == 0.0) S.dup = 1;
+                    v = gamma_model(p.model, h, nugget, sill, rang);
                 } else v = 0.0;                                                 // identity padding (off diagonal)
                 S.G[t * (K + 1) + c] = v;
                 S.G[c * (K + 1) + t] = v;
@@ -738,7 +745,9 @@ __global__ void __launch_bounds__(256) solve_reg_kernel(const SolveParams p)
         bool border_active = ORD;
         int my_step = -1, border_step = -1;
         double my_inv = 0.0, border_inv = 0.0;
-        bool singular = false;
+        // two identical rows: singular in exact arithmetic.  LAPACK only notices when rounding happens to leave an
+        // exact zero pivot (about half of such systems with OpenBLAS, garbage for the rest); here it is always caught
+        bool singular = S.dup != 0;
         sys_sync<TPS>(sid);
 
         // ---- LU with partial pivoting, fully unrolled (column j) ------------------------------------
@@ -886,11 +895,203 @@ static int launch_solve_reg(const SolveParams &sp, int mode, cudaStream_t stream
 }
 
 // ---------------------------------------------------------------------------------------------
+// Singular systems: the reference's fallbacks in solve_weights (kriging/utils/point_kriging_solve.py:134-147)
+//
+//   try: np.linalg.solve(A, b)
+//   except LinAlgError:
+//       if mean(A) == 0 or mean(b) == 0: ZerosMatrixWarning, weights = 0
+//       elif allow_lsa:                  LeastSquaresApproximationWarning, weights = lstsq(A, b, rcond=None)[0]
+//       else:                            raise
+//
+// The solve kernels mark such systems PIB_STATUS_SINGULAR (exact zero pivot, the condition dgesv reports).
+// This kernel runs after them: warps scan the status bytes, and every singular system is rebuilt and
+// finished here.  lstsq(rcond=None) is the minimum-norm least-squares solution with singular values below
+// eps * n * s_max dropped; A is symmetric, so its SVD is its eigen-decomposition A = V L V^T (s = |l|) and
+// x = sum_{|l_i| > cut} v_i (v_i . b) / l_i.  The eigen-decomposition is a cyclic Jacobi iteration (warp per
+// system, A in shared memory, V in shared memory when both fit, else in a global scratch slab).
+// ---------------------------------------------------------------------------------------------
+struct SingularParams {
+    SolveParams s;
+    int allow_lsa;
+    double *vglobal;       // NULL (V lives in shared memory) or [gridDim.x][dmax * stride]
+};
+
+static __device__ int jacobi_eigen(double *A, double *V, int n, int st, int lane)
+{
+    for (int idx = lane; idx < n * n; idx += 32) {
+        const int i = idx / n, j = idx - i * n;
+        V[i * st + j] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    int sweep = 0;
+    for (; sweep < 60; ++sweep) {
+        double off = 0.0, tot = 0.0;
+        for (int idx = lane; idx < n * n; idx += 32) {
+            const int i = idx / n, j = idx - i * n;
+            const double a = A[i * st + j];
+            tot += a * a;
+            if (i != j) off += a * a;
+        }
+        for (int o = 16; o; o >>= 1) {
+            off += __shfl_xor_sync(0xffffffffu, off, o);
+            tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        }
+        if (!(off > tot * 1e-36)) break;                         // off-diagonal mass below 1e-18 ||A||_F (or NaN)
+        const double thr = sqrt(tot) * 1e-20;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = A[p * st + q];
+                if (!(fabs(apq) > thr)) continue;                // warp-uniform
+                const double app = A[p * st + p], aqq = A[q * st + q];
+                const double theta = (aqq - app) / (2.0 * apq);
+                double t;
+                if (fabs(theta) > 1e150) t = 0.5 / theta;
+                else t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                __syncwarp();
+                for (int i = lane; i < n; i += 32) {
+                    if (i != p && i != q) {
+                        const double aip = A[i * st + p], aiq = A[i * st + q];
+                        const double np_ = c * aip - s * aiq, nq_ = s * aip + c * aiq;
+                        A[i * st + p] = np_; A[p * st + i] = np_;
+                        A[i * st + q] = nq_; A[q * st + i] = nq_;
+                    }
+                    const double vip = V[i * st + p], viq = V[i * st + q];
+                    V[i * st + p] = c * vip - s * viq;
+                    V[i * st + q] = s * vip + c * viq;
+                }
+                if (lane == 0) {
+                    A[p * st + p] = app - t * apq; A[q * st + q] = aqq + t * apq;
+                    A[p * st + q] = 0.0; A[q * st + p] = 0.0;
+                }
+                __syncwarp();
+            }
+    }
+    return sweep;
+}
+
+__global__ void __launch_bounds__(32) singular_kernel(const SingularParams sp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SolveParams &p = sp.s;
+    const int lane = threadIdx.x;
+    const int kmax = p.kk, mode = p.mode;
+    const int dmax = (mode == PIB_KRIGE_ORDINARY) ? kmax + 1 : kmax;
+    const int st = p.stride;
+    double *A = reinterpret_cast<double *>(smem_raw);
+    double *V = sp.vglobal ? sp.vglobal + (size_t)blockIdx.x * dmax * st : A + (size_t)dmax * st;
+    double *rhs = (sp.vglobal ? A : V) + (size_t)dmax * st;
+    double *xv = rhs + dmax;
+    double *nx = xv + dmax, *ny = nx + kmax, *nd = ny + kmax;
+    int32_t *npos = reinterpret_cast<int32_t *>(nd + kmax);
+    const GridIndex &g = p.g;
+
+    for (int64_t base = (int64_t)blockIdx.x * 32; base < p.count; base += (int64_t)gridDim.x * 32) {
+        const int64_t mine = base + lane;
+        bool hit = false;
+        int32_t myq = 0;
+        if (mine < p.count) {
+            myq = p.order[mine];
+            for (int set = 0; set < p.n_sets; ++set) hit |= p.status[(size_t)set * p.m + myq] == PIB_STATUS_SINGULAR;
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, hit);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t slot = base + src;
+            const int32_t q = __shfl_sync(0xffffffffu, myq, src);
+            const int kk = p.nbr_count ? p.nbr_count[slot] : kmax;
+            if (kk <= 0) continue;
+            const int dim = (mode == PIB_KRIGE_ORDINARY) ? kk + 1 : kk;
+            __syncwarp();
+            for (int t = lane; t < kk; t += 32) {
+                const int pos = p.nbr_pos[slot * kmax + t];
+                npos[t] = pos; nx[t] = g.x[pos]; ny[t] = g.y[pos]; nd[t] = p.nbr_d[slot * kmax + t];
+            }
+            __syncwarp();
+            for (int set = 0; set < p.n_sets; ++set) {
+                if (p.status[(size_t)set * p.m + q] != PIB_STATUS_SINGULAR) continue;
+                const double nugget = p.params[3 * set], sill = p.params[3 * set + 1], rang = p.params[3 * set + 2];
+                for (int i = 0; i < kk; ++i)
+                    for (int j = i + 1 + lane; j < kk; j += 32) {
+                        const double dx = __dsub_rn(nx[i], nx[j]), dy = __dsub_rn(ny[i], ny[j]);
+                        const double h = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                        const double gm = gamma_model(p.model, h, nugget, sill, rang);
+                        A[i * st + j] = gm; A[j * st + i] = gm;
+                    }
+                for (int i = lane; i < kk; i += 32) {
+                    A[i * st + i] = nugget;
+                    rhs[i] = gamma_model(p.model, nd[i], nugget, sill, rang);
+                    if (mode == PIB_KRIGE_ORDINARY) { A[i * st + kk] = 1.0; A[kk * st + i] = 1.0; }
+                }
+                if (mode == PIB_KRIGE_ORDINARY && lane == 0) { A[kk * st + kk] = 0.0; rhs[kk] = 1.0; }
+                __syncwarp();
+                // np.mean(A) == 0 or np.mean(b) == 0  (entries are >= 0 for valid models, so sum == 0 <=> all zero)
+                double sa = 0.0, sb = 0.0;
+                for (int idx = lane; idx < dim * dim; idx += 32) { const int i = idx / dim, j = idx - i * dim; sa += A[i * st + j]; }
+                for (int i = lane; i < dim; i += 32) sb += rhs[i];
+                for (int o = 16; o; o >>= 1) {
+                    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                }
+                uint8_t stat;
+                if (sa == 0.0 || sb == 0.0) {
+                    for (int i = lane; i < dim; i += 32) xv[i] = 0.0;
+                    stat = PIB_STATUS_ZERO_MATRIX;
+                } else if (!sp.allow_lsa) {
+                    continue;                                     // stays PIB_STATUS_SINGULAR: the caller raises
+                } else {
+                    jacobi_eigen(A, V, dim, st, lane);
+                    double lmax = 0.0;
+                    for (int i = lane; i < dim; i += 32) lmax = fmax(lmax, fabs(A[i * st + i]));
+                    for (int o = 16; o; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+                    const double cut = 2.220446049250313e-16 * dim * lmax;   // lstsq(rcond=None): eps * max(M, N) * s_max
+                    for (int i = lane; i < dim; i += 32) xv[i] = 0.0;
+                    __syncwarp();
+                    for (int e = 0; e < dim; ++e) {
+                        const double lam = A[e * st + e];
+                        if (!(fabs(lam) > cut)) continue;
+                        double dot = 0.0;
+                        for (int r = lane; r < dim; r += 32) dot = __fma_rn(V[r * st + e], rhs[r], dot);
+                        for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                        const double coef = dot / lam;
+                        for (int r = lane; r < dim; r += 32) xv[r] = __fma_rn(coef, V[r * st + e], xv[r]);
+                    }
+                    stat = PIB_STATUS_LSA;
+                }
+                __syncwarp();
+                double zs = 0.0, ss = 0.0;
+                for (int i = lane; i < dim; i += 32) {
+                    const double w = xv[i];
+                    ss = __fma_rn(w, rhs[i], ss);
+                    if (i < kk) {
+                        double zv = p.values ? p.values[(size_t)set * p.n + g.orig[npos[i]]] : g.z[npos[i]];
+                        if (mode == PIB_KRIGE_SIMPLE) zv -= p.process_mean;
+                        zs = __fma_rn(zv, w, zs);
+                    }
+                }
+                for (int o = 16; o; o >>= 1) {
+                    zs += __shfl_xor_sync(0xffffffffu, zs, o);
+                    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                }
+                if (lane == 0) {
+                    double *o = p.out + ((size_t)set * p.m + q) * 4;
+                    o[0] = (mode == PIB_KRIGE_SIMPLE) ? zs + p.process_mean : zs;
+                    o[1] = ss < 0.0 ? nan("") : ss;               // ordinary.py:125-126
+                    p.status[(size_t)set * p.m + q] = stat;
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
 int krige_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
                  const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
-                 double neighbors_range, double direction, double max_tick, int use_all,
+                 double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
                  double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, cudaStream_t stream)
 {
     const bool directional = !std::isnan(direction);
@@ -952,6 +1153,18 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
     int32_t *nbr_count = nullptr;
     if (ranged) PIB_TRY(ws.alloc(&nbr_count, (size_t)chunk));
     const int ksel = (int)std::min<int64_t>(k, n);              // what the plain k-nearest search selects
+    if (!d_status) {                                            // the singular-system pass needs the status bytes
+        PIB_TRY(ws.alloc(&d_status, (size_t)n_sets * m));
+    }
+    // singular-system pass: one warp per CTA; V next to A in shared memory when both fit, else in global scratch
+    const size_t mat_bytes = (size_t)dim * stride * 8;
+    const size_t sing_tail = (size_t)dim * 16 + (size_t)kk * 24 + (size_t)((kk + 1) / 2 * 2) * 4 + 16;
+    const bool v_in_smem = 2 * mat_bytes + sing_tail <= 100 * 1024;
+    const size_t sing_smem = (v_in_smem ? 2 : 1) * mat_bytes + sing_tail;
+    const int sing_grid = sm_count() * (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(MAX_SMEM_K - 1024) / (sing_smem + 1024)));
+    double *vglobal = nullptr;
+    if (!v_in_smem) PIB_TRY(ws.alloc(&vglobal, (size_t)sing_grid * dim * stride));
+    PIB_CUDA(cudaFuncSetAttribute(singular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sing_smem));
 
     for (int64_t begin = 0; begin < m; begin += chunk) {
         const int64_t count = std::min(chunk, m - begin);
@@ -991,6 +1204,12 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
         else {
             solve_kernel<<<(int)((count + solve_warps - 1) / solve_warps), solve_warps * 32, per_warp * solve_warps, stream>>>(sp);
             if (cudaGetLastError() != cudaSuccess) { set_error("solve_kernel launch failed"); rc = PIB_ERR_CUDA; }
+        }
+        if (rc == PIB_OK) {
+            SingularParams sg;
+            sg.s = sp; sg.s.status = d_status; sg.allow_lsa = allow_lsa; sg.vglobal = vglobal;
+            singular_kernel<<<sing_grid, 32, sing_smem, stream>>>(sg);
+            if (cudaGetLastError() != cudaSuccess) { set_error("singular_kernel launch failed"); rc = PIB_ERR_CUDA; }
         }
         timing_end(PIB_T_SOLVE, stream);
         PIB_TRY(rc);

@@ -87,11 +87,11 @@ class IndicatorKriging:
         if kriging_type != 'ok':
             raise ValueError('Kriging type not supported. Please choose from: '
                              '"ok" - ordinary kriging, "sk" - simple kriging.')
-        if use_all_neighbors_in_range or allow_approximate_solutions:
-            raise NotImplementedError("use_all_neighbors_in_range / allow_approximate_solutions are not implemented")
         self.indicator_predictions = indicator_kriging(
             list(models.values()), self.thresholds, known_locations, unknown_locations, no_neighbors=no_neighbors,
-            reference_variance_column=reference_variance_column)
+            reference_variance_column=reference_variance_column, neighbors_range=neighbors_range,
+            use_all_neighbors_in_range=use_all_neighbors_in_range,
+            allow_approximate_solutions=allow_approximate_solutions)
         self.expected_values = None
         self.variances = None
         if get_expected_values:

@@ -10,7 +10,8 @@ Mirrors (file:line relative to /root/reference/src/pyinterpolate/):
 Models that carry a ``direction`` use the reference's angular neighbour selection
 (transform/select_points.py:104-257) inside ``neighbors_range`` (default: the model range).
 ``use_all_neighbors_in_range=True`` is supported up to 128 rows per location (more raises NotImplementedError).
-Not built (NotImplementedError, there is no CPU fallback): ``allow_approximate_solutions=True`` (lstsq fallback).
+``allow_approximate_solutions=True`` solves singular systems like ``np.linalg.lstsq`` on the device
+(kriging/utils/point_kriging_solve.py:134-147) and warns like the reference.
 """
 import warnings
 
@@ -30,9 +31,6 @@ _SINGULAR_MSG = ("Singular matrix in Kriging system detected, "
 def _prepare(theoretical_model, known_locations, unknown_locations, use_all_neighbors_in_range,
              allow_approximate_solutions, neighbors_range=None, max_tick=5.):
     mid, nugget, sill, rang, direction = model_parameters(theoretical_model)
-    if allow_approximate_solutions:
-        raise NotImplementedError("allow_approximate_solutions=True (least-squares fallback) is not implemented "
-                                  "in pyinterpolate_b200 yet")
     known = np.ascontiguousarray(core.variogram_points(known_locations), dtype=np.float64)
     unknown = np.ascontiguousarray(core.interpolation_points(unknown_locations), dtype=np.float64)
     if known.ndim != 2 or known.shape[1] != 3:
@@ -41,11 +39,23 @@ def _prepare(theoretical_model, known_locations, unknown_locations, use_all_neig
         raise ValueError("unknown_locations must be rows of [x, y]")
     # neighbors_range defaults to the model range (kriging/utils/point_kriging_solve.py:68-69)
     selection = dict(neighbors_range=rang if neighbors_range is None else float(neighbors_range),
-                     direction=direction, max_tick=max_tick, use_all=bool(use_all_neighbors_in_range))
+                     direction=direction, max_tick=max_tick, use_all=bool(use_all_neighbors_in_range),
+                     allow_lsa=bool(allow_approximate_solutions))
     return mid, np.array([[nugget, sill, rang]]), known, unknown, selection
 
 
+# core/ptp_warnings/ptp_warnings.py:8-34 — the reference warns with the message STRING (a UserWarning)
+_ZEROS_MSG = repr('Matrix in your Kriging system is populated only be zeros. It is probably data error. '
+                  'Prediction will return 0 as a predicted value and np.nan as an error.')
+_LSA_MSG = repr('Kriging system solution is based on the approximate solution, output may be incorrect!')
+
+
 def _raise_on_singular(status):
+    # kriging/utils/point_kriging_solve.py:134-147
+    if (status == _lib.STATUS_ZERO_MATRIX).any():
+        warnings.warn(_ZEROS_MSG)
+    if (status == _lib.STATUS_LSA).any():
+        warnings.warn(_LSA_MSG)
     if (status == _lib.STATUS_SINGULAR).any():
         # kriging/utils/errors.py:1-15 via ordinary.py:130-131
         raise RuntimeError(_SINGULAR_MSG)
@@ -103,11 +113,14 @@ def interpolate_points(theoretical_model, known_locations, unknown_locations, ne
 
 
 def indicator_kriging(theoretical_models, thresholds, known_locations, unknown_locations, no_neighbors=4,
-                      reference_variance_column=True):
+                      reference_variance_column=True, neighbors_range=None, use_all_neighbors_in_range=False,
+                      allow_approximate_solutions=False):
     """Batched core of kriging/point/indicator.py:200-325 for ``kriging_type='ok'``.
 
     ``theoretical_models`` are the per-threshold models (same model family), ``thresholds`` the cut values;
-    indicators are ``(z <= threshold)`` (indicator.py:272-275).  All thresholds share one neighbour search.
+    indicators are ``(z <= threshold)`` (indicator.py:272-275).  All thresholds share one neighbour search
+    (with ``use_all_neighbors_in_range`` and per-threshold ranges that differ, the selection differs per
+    threshold, so each threshold gets its own call).
     Returns ``[M, T]`` clipped to [0, 1].  With ``reference_variance_column=True`` the column the reference
     stores is reproduced — it keeps ``_pred_arr[0][1]``, the kriging VARIANCE, not zhat (indicator.py:312-313);
     pass False to get the indicator predictions themselves."""
@@ -120,8 +133,19 @@ def indicator_kriging(theoretical_models, thresholds, known_locations, unknown_l
         raise NotImplementedError("directional indicator models are not implemented")
     params = np.array([[p[1], p[2], p[3]] for p in parsed])
     values = np.stack([(known[:, 2] <= float(t)).astype(np.float64) for t in thresholds])
-    out, _, status = _lib.krige_host(known, unknown, parsed[0][0], params, _lib.KRIGE_ORDINARY, int(no_neighbors),
-                                     values=values)
+    sel = dict(use_all=bool(use_all_neighbors_in_range), allow_lsa=bool(allow_approximate_solutions))
+    ranges = params[:, 2] if neighbors_range is None else np.full(len(parsed), float(neighbors_range))
+    if use_all_neighbors_in_range and len(set(ranges.tolist())) > 1:
+        outs, stats = [], []
+        for t in range(len(parsed)):
+            o, _, st = _lib.krige_host(known, unknown, parsed[0][0], params[t:t + 1], _lib.KRIGE_ORDINARY,
+                                       int(no_neighbors), values=values[t:t + 1], neighbors_range=float(ranges[t]), **sel)
+            outs.append(o[0])
+            stats.append(st[0])
+        out, status = np.stack(outs), np.stack(stats)
+    else:
+        out, _, status = _lib.krige_host(known, unknown, parsed[0][0], params, _lib.KRIGE_ORDINARY, int(no_neighbors),
+                                         values=values, neighbors_range=float(ranges[0]), **sel)
     _raise_on_singular(status)
     col = 1 if reference_variance_column else 0
     res = out[:, :, col].T.copy()

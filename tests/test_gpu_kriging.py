@@ -109,9 +109,6 @@ def test_edge_cases_golden(pib, golden):
                              np.array([[0.4, 0.3]]), no_neighbors=8)
     with pytest.raises(KeyError):
         pib.ordinary_kriging({"variogram_model_type": "matern", "nugget": 0, "sill": 1, "rang": 1}, arm, unk)
-    with pytest.raises(NotImplementedError):
-        pib.ordinary_kriging({"variogram_model_type": "linear", "nugget": 0, "sill": 1, "rang": 1}, arm, unk,
-                             allow_approximate_solutions=True)
 
 
 def test_exact_interpolation_at_known_points(pib):

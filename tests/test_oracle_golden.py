@@ -200,3 +200,25 @@ def test_kriging_edge_cases(oracle, golden):
     assert bool(golden["dup_raises"])
     _, _, st = oracle.krige(dup, np.array([[0.4, 0.3]]), "spherical", 0.0, float(golden["armstrong_krige_sill"]), 4.0, 8, "ok")
     assert st[0] == 1
+
+
+def test_lstsq_fallback_golden(oracle):
+    """allow_approximate_solutions (point_kriging_solve.py:134-147): the oracle reproduces the reference on every
+    row where the reference itself went through np.linalg.lstsq and on every non-singular row.  (On the other
+    duplicate-coordinate rows the reference's LAPACK misses the singularity and returns garbage; the oracle
+    treats them as singular — tests/golden/make_golden_lsa.py records which is which.)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden_lsa.npz"))
+    known, unk, var = g["known"], g["unknown"], float(g["var"])
+    for name, nug in (("spherical", 0.0), ("exponential", 0.7), ("linear", 0.0)):
+        for mode, k, pm in (("ok", 16, 0.0), ("sk", 12, float(known[:, 2].mean()))):
+            out, _, st = oracle.krige_with_fallback(known, unk, name, nug, var, 9000.0, k, mode, pm)
+            ref, ls, sing = g[f"{mode}_{name}"], g[f"{mode}_{name}_lstsq"], g[f"singular{k}"]
+            np.testing.assert_array_equal(st == 4, sing)
+            keep = ls | ~sing
+            assert ls.sum() >= 10
+            np.testing.assert_array_equal(np.isnan(out[keep, 1]), np.isnan(ref[keep, 1]))
+            np.testing.assert_allclose(np.nan_to_num(out[keep, :2]), np.nan_to_num(ref[keep, :2]), rtol=1e-10)
+    out, _, st = oracle.krige_with_fallback(known, unk[:10], "spherical", 0.0, 0.0, 9000.0, 6, "sk", 3.5)
+    assert (st == 5).all()
+    np.testing.assert_array_equal(out, g["sk_zero"])
