@@ -665,11 +665,26 @@ struct RegSysSmem {
     int dup;                   // a neighbour pair at distance 0 (duplicated coordinates): the system is singular
 };
 
+// Threads per CTA / CTAs per SM.  The kernel is latency bound (a chain of dependent elimination steps per system),
+// so what matters is how many systems are in flight per SM.  ptxas takes every register the launch bounds allow
+// (240 at 256 threads for K = 64) although the row itself needs 128: capping it at 168 (384 threads) costs a
+// 48-byte spill and puts 6 systems on an SM instead of 4; K = 32 is fastest as 2 x 256 threads at 128 registers (2 x 320 at 96 spills and is 12 % slower).
+#ifndef PIB_SOLVE64_THREADS
+#define PIB_SOLVE64_THREADS 384
+#endif
+#ifndef PIB_SOLVE32_THREADS
+#define PIB_SOLVE32_THREADS 256
+#endif
+template <int K>
+__host__ __device__ constexpr int solve_reg_threads() { return K == 64 ? PIB_SOLVE64_THREADS : K == 32 ? PIB_SOLVE32_THREADS : 256; }
+template <int K>
+__host__ __device__ constexpr int solve_reg_min_ctas() { return K == 32 ? 2 : 1; }
+
 template <int K, bool ORD>
-__global__ void __launch_bounds__(256) solve_reg_kernel(const SolveParams p)
+__global__ void __launch_bounds__(solve_reg_threads<K>(), solve_reg_min_ctas<K>()) solve_reg_kernel(const SolveParams p)
 {
     constexpr int TPS = K < 32 ? 32 : K;          // threads per system
-    constexpr int SPC = 256 / TPS;                // systems per CTA
+    constexpr int SPC = solve_reg_threads<K>() / TPS;   // systems per CTA
     constexpr int NSTEP = ORD ? K + 1 : K;
     constexpr int WARPS = TPS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -879,16 +894,17 @@ __global__ void __launch_bounds__(256) solve_reg_kernel(const SolveParams p)
 template <int K>
 static int launch_solve_reg(const SolveParams &sp, int mode, cudaStream_t stream)
 {
-    constexpr int SPC = 256 / (K < 32 ? 32 : K);
+    constexpr int NT = solve_reg_threads<K>();
+    constexpr int SPC = NT / (K < 32 ? 32 : K);
     const int grid = (int)((sp.count + SPC - 1) / SPC);
     if (mode == PIB_KRIGE_ORDINARY) {
         const size_t bytes = sizeof(RegSysSmem<K, true>) * SPC;
         PIB_CUDA(cudaFuncSetAttribute(solve_reg_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        solve_reg_kernel<K, true><<<grid, 256, bytes, stream>>>(sp);
+        solve_reg_kernel<K, true><<<grid, NT, bytes, stream>>>(sp);
     } else {
         const size_t bytes = sizeof(RegSysSmem<K, false>) * SPC;
         PIB_CUDA(cudaFuncSetAttribute(solve_reg_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        solve_reg_kernel<K, false><<<grid, 256, bytes, stream>>>(sp);
+        solve_reg_kernel<K, false><<<grid, NT, bytes, stream>>>(sp);
     }
     PIB_CUDA(cudaGetLastError());
     return PIB_OK;
