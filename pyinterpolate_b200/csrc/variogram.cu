@@ -56,6 +56,7 @@ struct PairParams {
     int shard_index, shard_count;
     double *partial;             // [grid][warps][n_slots][4]  (sum_sq, sum_prod, sum_val, count as double-exact int64 bits)
     unsigned long long *pairs_evaluated;
+    int group_path;              // ring kernel: one slot lookup per group of 8 pairs (off-diagonal tile pairs)
 };
 
 // ---- PTX helpers: mbarrier + 1D TMA bulk copy -------------------------------------------------
@@ -662,20 +663,124 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
                 cnt[r_lo] = c_lo + (uint32_t)(U - ch - n_out);
                 cnt[r_hi] = c_hi + (uint32_t)ch;
             };
+            // ---- group path (tile pairs off the diagonal): ONE table lookup per group of U pairs ----------
+            // The smallest high word of the U squared distances, with a zero low word, is a lower bound of all
+            // of them; its slot `lo` (same table + threshold steps as above) is therefore <= every pair's slot and
+            // equals the smallest one unless a threshold falls into the 2^-20 relative gap.  Each pair then needs a
+            // single fp64 compare against the threshold between lo and lo + 1.  A group whose largest high word
+            // could exceed the NEXT threshold takes the per-pair slow path under a warp vote (exact slot search).
+            struct Grp { double a1, h1, a2, h2; int lo, ch, nout; };
+            auto compute2 = [&](int j0, Grp &g) {
+                double d2[U], dzv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const double2 pj = bxy[j0 + u];
+                    dzv[u] = __dsub_rn(zi, bz[j0 + u]);
+                    if (ELLIPSE) {
+                        const double dx = __dsub_rn(pj.x, xi), dy = __dsub_rn(pj.y, yi);
+                        const double n0 = __fma_rn(w01, dy, __dmul_rn(w00, dx));
+                        const double n1 = __fma_rn(w11, dy, __dmul_rn(w10, dx));
+                        d2[u] = __dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1));
+                    } else {
+                        const double dx = __dsub_rn(xi, pj.x), dy = __dsub_rn(yi, pj.y);
+                        d2[u] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                    }
+                }
+                int mn = __double2hiint(d2[0]), mx = mn;
+#pragma unroll
+                for (int u = 1; u < U; ++u) {
+                    const int h = __double2hiint(d2[u]);
+                    mn = min(mn, h); mx = max(mx, h);
+                }
+                int idx = (mn - base_hi) >> LUT2_SHIFT;
+                idx = min(max(idx, 0), lut_last);
+                int lo = s_lut[idx];
+                const int *upper_hi = reinterpret_cast<const int *>(s_upper) + 1;      // high words of the thresholds
+                if (FIX > 0) {
+#pragma unroll
+                    for (int t = 0; t < FIX; ++t) lo += (mn > upper_hi[2 * lo]) ? 1 : 0;   // bound = (mn << 32)
+                } else {
+                    while (mn > upper_hi[2 * lo]) ++lo;
+                }
+                const int lo1 = min(lo + 1, n_slots - 1);
+                const double t_lo = __longlong_as_double(s_upper[lo]);
+                const long long t_hi_bits = s_upper[lo1];
+                int nout = 0;
+                if (__any_sync(0xffffffffu, mx + 1 > (int)(t_hi_bits >> 32))) {            // rare: maybe beyond lo + 1
+                    const double t_hi = __longlong_as_double(t_hi_bits);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (d2[u] > t_hi) {
+                            int sx = lo1 + 1;
+                            while (__double_as_longlong(d2[u]) > s_upper[sx]) ++sx;
+                            const int r = ring_of(sx, TRASH_HI);
+                            double2 a = acc[r];
+                            a.x += dzv[u];
+                            a.y = __fma_rn(dzv[u], dzv[u], a.y);
+                            acc[r] = a;
+                            cnt[r] += 1u;
+                            dzv[u] = 0.0; d2[u] = -1.0; ++nout;
+                        }
+                    }
+                }
+                double dh[U];
+                int ch = 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool is_hi = d2[u] > t_lo;
+                    dh[u] = is_hi ? dzv[u] : 0.0;
+                    ch += is_hi ? 1 : 0;
+                }
+                g.a1 = ((dzv[0] + dzv[1]) + (dzv[2] + dzv[3])) + ((dzv[4] + dzv[5]) + (dzv[6] + dzv[7]));
+                g.h1 = ((dh[0] + dh[1]) + (dh[2] + dh[3])) + ((dh[4] + dh[5]) + (dh[6] + dh[7]));
+                double a2e = dzv[0] * dzv[0], a2o = dzv[1] * dzv[1], h2e = dh[0] * dh[0], h2o = dh[1] * dh[1];
+#pragma unroll
+                for (int u = 2; u < U; u += 2) {
+                    a2e = __fma_rn(dzv[u], dzv[u], a2e); a2o = __fma_rn(dzv[u + 1], dzv[u + 1], a2o);
+                    h2e = __fma_rn(dh[u], dh[u], h2e);   h2o = __fma_rn(dh[u + 1], dh[u + 1], h2o);
+                }
+                g.a2 = a2e + a2o; g.h2 = h2e + h2o;
+                g.lo = lo; g.ch = ch; g.nout = nout;
+            };
+            auto consume2 = [&](const Grp &g) {
+                const int r_lo = ring_of(g.lo, TRASH_LO), r_hi = ring_of(g.lo + 1, TRASH_HI);   // never equal
+                double2 v_lo = acc[r_lo], v_hi = acc[r_hi];
+                const uint32_t c_lo = cnt[r_lo], c_hi = cnt[r_hi];
+                v_lo.x += g.a1 - g.h1; v_lo.y += g.a2 - g.h2;
+                v_hi.x += g.h1;        v_hi.y += g.h2;
+                acc[r_lo] = v_lo; acc[r_hi] = v_hi;
+                cnt[r_lo] = c_lo + (uint32_t)(U - g.ch - g.nout);
+                cnt[r_hi] = c_hi + (uint32_t)g.ch;
+            };
             int sA[U], sB[U];
             double dA[U], dB[U];
+            Grp gA, gB;
             auto sweep = [&]() {                              // all 128 points of the B tile, software pipelined
-                compute(0, sA, dA);
+                if (diagonal || !p.group_path) {
+                    compute(0, sA, dA);
 #pragma unroll 1
-                for (int j0 = 0; j0 < TILE - 2 * U; j0 += 2 * U) {
-                    compute(j0 + U, sB, dB);
+                    for (int j0 = 0; j0 < TILE - 2 * U; j0 += 2 * U) {
+                        compute(j0 + U, sB, dB);
+                        consume(sA, dA);
+                        compute(j0 + 2 * U, sA, dA);
+                        consume(sB, dB);
+                    }
+                    compute(TILE - U, sB, dB);
                     consume(sA, dA);
-                    compute(j0 + 2 * U, sA, dA);
                     consume(sB, dB);
+                } else {
+                    compute2(0, gA);
+#pragma unroll 1
+                    for (int j0 = 0; j0 < TILE - 2 * U; j0 += 2 * U) {
+                        compute2(j0 + U, gB);
+                        consume2(gA);
+                        compute2(j0 + 2 * U, gA);
+                        consume2(gB);
+                    }
+                    compute2(TILE - U, gB);
+                    consume2(gA);
+                    consume2(gB);
                 }
-                compute(TILE - U, sB, dB);
-                consume(sA, dA);
-                consume(sB, dB);
             };
             if (!wide) {
                 sweep();
@@ -1001,6 +1106,10 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         p.pairs_evaluated = d_evaluated;
         p.lut2 = d_lut2; p.lut2_base = lut2_base; p.lut2_n = (int)lut2.size();
         p.box_slack = 0.0;
+        {
+            const char *gp = std::getenv("PIB_GROUP_PATH");
+            p.group_path = (gp && gp[0] == '0') ? 0 : 1;
+        }
         double4 *d_boxw = nullptr;                 // ellipse: bounding boxes of the whitened coordinates, per direction
         if (n_dirs > 0) PIB_TRY(ws.alloc(&d_boxw, n_tiles));
         for (int t = 0; t < out_dirs; ++t) {
