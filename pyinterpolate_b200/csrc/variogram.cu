@@ -57,6 +57,7 @@ struct PairParams {
     double *partial;             // [grid][warps][n_slots][4]  (sum_sq, sum_prod, sum_val, count as double-exact int64 bits)
     unsigned long long *pairs_evaluated;
     int group_path;              // ring kernel: one slot lookup per group of 8 pairs (off-diagonal tile pairs)
+    const double *gsum;          // [n_pad / 8] sum of z over each group of 8 consecutive (sorted) points
 };
 
 // ---- PTX helpers: mbarrier + 1D TMA bulk copy -------------------------------------------------
@@ -381,6 +382,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
     static_assert(NT % TILE == 0 && RING <= 32, "A sub-tile is whole tiles; one lane folds one ring slot");
     __shared__ __align__(16) double2 s_txy[2][TILE];
     __shared__ __align__(16) double s_tz[2][TILE];
+    __shared__ __align__(16) double s_gs[2][TILE / 8];
     __shared__ long long s_upper[MAX_SLOTS];
     __shared__ uint16_t s_lut[LUT2_MAX];
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -485,6 +487,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
         const double2 pa = p.xy[ig];
         const double xi = pa.x, yi = pa.y, zi = p.z[ig];
         s_zi[tid] = zi;
+        const double z8 = zi * 8.0;
         int win_lo = 0x7fff, win_hi = 0;                      // lag slots touched since the last fold (empty)
 
         // fold the rings of my warp into its global partials (lane l owns ring slot l)
@@ -524,9 +527,10 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
         live &= live - 1;
         if (tid == 0) {
             const uint32_t b = seq & 1;
-            mbar_expect_tx(&s_bar[b], TILE * (sizeof(double2) + sizeof(double)));
+            mbar_expect_tx(&s_bar[b], TILE * (sizeof(double2) + sizeof(double)) + (TILE / 8) * sizeof(double));
             tma_load_1d(s_txy[b], p.xy + (size_t)tb * TILE, TILE * sizeof(double2), &s_bar[b]);
             tma_load_1d(s_tz[b], p.z + (size_t)tb * TILE, TILE * sizeof(double), &s_bar[b]);
+            tma_load_1d(s_gs[b], p.gsum + (size_t)tb * (TILE / 8), (TILE / 8) * sizeof(double), &s_bar[b]);
         }
         while (true) {
             const uint32_t b = seq & 1, phase = (seq >> 1) & 1;
@@ -534,9 +538,10 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
             live &= live - 1;
             if (tid == 0 && tb_next >= 0) {
                 const uint32_t nb = b ^ 1;
-                mbar_expect_tx(&s_bar[nb], TILE * (sizeof(double2) + sizeof(double)));
+                mbar_expect_tx(&s_bar[nb], TILE * (sizeof(double2) + sizeof(double)) + (TILE / 8) * sizeof(double));
                 tma_load_1d(s_txy[nb], p.xy + (size_t)tb_next * TILE, TILE * sizeof(double2), &s_bar[nb]);
                 tma_load_1d(s_tz[nb], p.z + (size_t)tb_next * TILE, TILE * sizeof(double), &s_bar[nb]);
+                tma_load_1d(s_gs[nb], p.gsum + (size_t)tb_next * (TILE / 8), (TILE / 8) * sizeof(double), &s_bar[nb]);
             }
             // ---- ring window bookkeeping (uniform over the CTA) ---------------------------------
             const short2 rng = s_range[tb - tb0];
@@ -551,6 +556,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
 
             const double2 *bxy = s_txy[b];
             const double *bz = s_tz[b];
+            const double *bgs = s_gs[b];
             const bool diagonal = (tb <= ta_last);
             const int jbase = tb * TILE;
             if (tid == 0) {
@@ -706,6 +712,9 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
                 const double t_lo = __longlong_as_double(s_upper[lo]);
                 const long long t_hi_bits = s_upper[lo1];
                 int nout = 0;
+                // sum of dz over the whole group from the pre-summed z of the group: 8 z_i - sum z_j (one fp64 op
+                // instead of seven; this sum only feeds the covariance terms, where it meets c z_i^2 - z_i * sum)
+                double a1 = __dsub_rn(z8, bgs[j0 >> 3]);
                 if (__any_sync(0xffffffffu, mx + 1 > (int)(t_hi_bits >> 32))) {            // rare: maybe beyond lo + 1
                     const double t_hi = __longlong_as_double(t_hi_bits);
 #pragma unroll
@@ -719,6 +728,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
                             a.y = __fma_rn(dzv[u], dzv[u], a.y);
                             acc[r] = a;
                             cnt[r] += 1u;
+                            a1 -= dzv[u];
                             dzv[u] = 0.0; d2[u] = -1.0; ++nout;
                         }
                     }
@@ -728,10 +738,12 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const bool is_hi = d2[u] > t_lo;
-                    dh[u] = is_hi ? dzv[u] : 0.0;
+                    // one select instead of two: a "lo" pair keeps the low word of dz under a zero high word, a
+                    // subnormal below 1e-308 whose contribution to the fp64 sums is far below one ulp
+                    dh[u] = __hiloint2double(is_hi ? __double2hiint(dzv[u]) : 0, __double2loint(dzv[u]));
                     ch += is_hi ? 1 : 0;
                 }
-                g.a1 = ((dzv[0] + dzv[1]) + (dzv[2] + dzv[3])) + ((dzv[4] + dzv[5]) + (dzv[6] + dzv[7]));
+                g.a1 = a1;
                 g.h1 = ((dh[0] + dh[1]) + (dh[2] + dh[3])) + ((dh[4] + dh[5]) + (dh[6] + dh[7]));
                 double a2e = dzv[0] * dzv[0], a2o = dzv[1] * dzv[1], h2e = dh[0] * dh[0], h2o = dh[1] * dh[1];
 #pragma unroll
@@ -804,6 +816,15 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
         acc[TRASH_LO * NT] = make_double2(0.0, 0.0); acc[TRASH_HI * NT] = make_double2(0.0, 0.0);
     }
     if (tid == 0 && evaluated) atomicAdd(p.pairs_evaluated, evaluated);
+}
+
+// sum of z over each group of 8 consecutive sorted points (pads included, as the pair kernel sees them)
+__global__ void group_sum_kernel(const double *__restrict__ z, int64_t n_groups, double *__restrict__ gsum)
+{
+    const int64_t gidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (gidx >= n_groups) return;
+    const double *q = z + gidx * 8;
+    gsum[gidx] = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
 }
 
 // bounding boxes of the whitened coordinates (u, v) = W p of every tile (one warp per tile)
@@ -1106,6 +1127,15 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         p.pairs_evaluated = d_evaluated;
         p.lut2 = d_lut2; p.lut2_base = lut2_base; p.lut2_n = (int)lut2.size();
         p.box_slack = 0.0;
+        p.gsum = nullptr;
+        if (use_ring) {
+            const int64_t n_groups = (int64_t)n_tiles * (TILE / 8);
+            double *d_gsum;
+            PIB_TRY(ws.alloc(&d_gsum, (size_t)n_groups));
+            group_sum_kernel<<<(int)((n_groups + 255) / 256), 256, 0, stream>>>(sp.z, n_groups, d_gsum);
+            PIB_CUDA(cudaGetLastError());
+            p.gsum = d_gsum;
+        }
         {
             const char *gp = std::getenv("PIB_GROUP_PATH");
             p.group_path = (gp && gp[0] == '0') ? 0 : 1;
