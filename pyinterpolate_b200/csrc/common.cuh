@@ -87,6 +87,9 @@ struct SortedPoints {
 int build_sorted_points(const double *d_xyz, int64_t n, int tile, int pad_to, Scratch &ws,
                         cudaStream_t stream, SortedPoints *out);
 
+int sort_pairs_u32(const uint32_t *keys_in, uint32_t *keys_out, const int32_t *vals_in, int32_t *vals_out,
+                   int64_t n, int end_bit, Scratch &ws, cudaStream_t stream);
+
 // Uniform grid over the known points for neighbour search.
 struct GridIndex {
     int64_t n = 0;

@@ -153,6 +153,13 @@ static int radix_sort_pairs(const K *keys_in, K *keys_out, const int32_t *vals_i
     return PIB_OK;
 }
 
+// stable radix sort of (key, value) pairs on the low `end_bit` bits (used for the pair kernel's work-item order)
+int sort_pairs_u32(const uint32_t *keys_in, uint32_t *keys_out, const int32_t *vals_in, int32_t *vals_out,
+                   int64_t n, int end_bit, Scratch &ws, cudaStream_t stream)
+{
+    return radix_sort_pairs<uint32_t>(keys_in, keys_out, vals_in, vals_out, n, end_bit, ws, stream);
+}
+
 int build_sorted_points(const double *d_xyz, int64_t n, int tile, int pad_to, Scratch &ws,
                         cudaStream_t stream, SortedPoints *out)
 {

@@ -58,6 +58,8 @@ struct PairParams {
     unsigned long long *pairs_evaluated;
     int group_path;              // ring kernel: one slot lookup per group of 8 pairs (off-diagonal tile pairs)
     const double *gsum;          // [n_pad / 8] sum of z over each group of 8 consecutive (sorted) points
+    const int32_t *item_list;    // ring kernel: work items ordered by descending cost (NULL: natural order)
+    const unsigned *n_live_items;  // number of items with at least one live tile pair (device scalar)
 };
 
 // ---- PTX helpers: mbarrier + 1D TMA bulk copy -------------------------------------------------
@@ -424,8 +426,12 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
     // difference between W (p_j - p_i) as the pairs compute it and W p_j - W p_i
     const double slack = p.box_slack;
 
-    for (int64_t item = ((int64_t)blockIdx.x) * p.shard_count + p.shard_index; item < n_items;
-         item += (int64_t)gridDim.x * p.shard_count) {
+    // Static, deterministic load balance: a pre-pass orders the items by descending cost (live B tiles) and drops
+    // the empty ones; dealing that list round-robin over CTAs and ranks gives every CTA one item of each cost stratum.
+    const int64_t n_work = p.item_list ? (int64_t)*p.n_live_items : n_items;
+    for (int64_t k = ((int64_t)blockIdx.x) * p.shard_count + p.shard_index; k < n_work;
+         k += (int64_t)gridDim.x * p.shard_count) {
+        const int64_t item = p.item_list ? (int64_t)p.item_list[k] : k;
         const int64_t a0 = (item / n_chunks) * NT;            // first point of my A sub-tile
         const int ta = (int)(a0 / TILE);                      // first of its tiles
         const int ta_last = min(ta + A_TILES, n_tiles) - 1;
@@ -818,6 +824,54 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
     if (tid == 0 && evaluated) atomicAdd(p.pairs_evaluated, evaluated);
 }
 
+// Cost of every ring-kernel work item = number of B tiles of its chunk that can hold a pair within range
+// (the same box test as the kernel's).  One warp per item; key = CHUNK - cost so that an ascending radix sort
+// puts the most expensive items first.
+template <bool ELLIPSE>
+__global__ void item_cost_kernel(const PairParams p, int a_tiles, int64_t n_items, uint32_t *__restrict__ keys,
+                                 int32_t *__restrict__ vals, unsigned *__restrict__ n_live)
+{
+    const int64_t item = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (item >= n_items) return;
+    const int n_tiles = p.n_tiles;
+    const int n_chunks = (n_tiles + CHUNK - 1) / CHUNK;
+    const int ta = (int)(item / n_chunks) * a_tiles;
+    const int ta_last = min(ta + a_tiles, n_tiles) - 1;
+    const int tb0 = (int)(item % n_chunks) * CHUNK;
+    const int tb1 = min(tb0 + CHUNK, n_tiles);
+    int cost = 0;
+    if (tb1 > ta && (int64_t)ta * TILE < p.n) {
+        double4 abox = p.tile_box[ta];
+        for (int t = ta + 1; t <= ta_last; ++t) {
+            const double4 o = p.tile_box[t];
+            abox.x = fmin(abox.x, o.x); abox.y = fmin(abox.y, o.y);
+            abox.z = fmax(abox.z, o.z); abox.w = fmax(abox.w, o.w);
+        }
+        const int tb_first = max(tb0, ta);
+        for (int h = 0; h < CHUNK / 32; ++h) {
+            const int tb = tb0 + h * 32 + lane;
+            bool live = false;
+            if (tb >= tb_first && tb < tb1) {
+                const double4 bbox = p.tile_box[tb];
+                double dmin;
+                if (ELLIPSE) {
+                    const double gx = fmax(0.0, fmax(abox.x - bbox.z, bbox.x - abox.z) - p.box_slack);
+                    const double gy = fmax(0.0, fmax(abox.y - bbox.w, bbox.y - abox.w) - p.box_slack);
+                    dmin = (gx * gx + gy * gy) * (1.0 - 1e-12);
+                } else dmin = box_min_d2(abox, bbox);
+                live = dmin <= p.max_d2;
+            }
+            cost += __popc(__ballot_sync(0xffffffffu, live));
+        }
+    }
+    if (lane == 0) {
+        keys[item] = (uint32_t)(CHUNK - cost);
+        vals[item] = (int32_t)item;
+        if (cost) atomicAdd(n_live, 1u);
+    }
+}
+
 // sum of z over each group of 8 consecutive sorted points (pads included, as the pair kernel sees them)
 __global__ void group_sum_kernel(const double *__restrict__ z, int64_t n_groups, double *__restrict__ gsum)
 {
@@ -853,21 +907,33 @@ __global__ void tile_box_whitened_kernel(const double2 *__restrict__ xy, int64_t
     if (lane == 0) box[t] = make_double4(umin, vmin, umax, vmax);
 }
 
-// Fixed-order sum of the per-warp partials -> outputs (one thread per lag)
-__global__ void reduce_partials_kernel(const double *__restrict__ partial, int n_parts, int n_slots, int n_lags,
-                                       double *__restrict__ sum_sq, double *__restrict__ sum_prod,
-                                       double *__restrict__ sum_val, int64_t *__restrict__ count)
+// Fixed-order sum of the per-warp partials -> outputs.  One 128-thread block per lag: thread t sums parts
+// t, t + 128, ... in order, then a fixed shared-memory tree combines the 128 sub-sums (deterministic).
+__global__ void __launch_bounds__(128) reduce_partials_kernel(const double *__restrict__ partial, int n_parts, int n_slots,
+                                                              int n_lags, double *__restrict__ sum_sq,
+                                                              double *__restrict__ sum_prod, double *__restrict__ sum_val,
+                                                              int64_t *__restrict__ count)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double sh[3][128];
+    __shared__ unsigned long long shc[128];
+    const int b = blockIdx.x, t = threadIdx.x;
     if (b >= n_lags) return;
     double s0 = 0, s1 = 0, s2 = 0;
     unsigned long long c = 0;
-    for (int q = 0; q < n_parts; ++q) {
+    for (int q = t; q < n_parts; q += 128) {
         const double *src = partial + ((size_t)q * n_slots + (b + 1)) * 4;
         s0 += src[0]; s1 += src[1]; s2 += src[2];
         c += reinterpret_cast<const unsigned long long *>(src)[3];
     }
-    sum_sq[b] = s0; sum_prod[b] = s1; sum_val[b] = s2; count[b] = (int64_t)c;
+    sh[0][t] = s0; sh[1][t] = s1; sh[2][t] = s2; shc[t] = c;
+    __syncthreads();
+    for (int o = 64; o; o >>= 1) {
+        if (t < o) {
+            sh[0][t] += sh[0][t + o]; sh[1][t] += sh[1][t + o]; sh[2][t] += sh[2][t + o]; shc[t] += shc[t + o];
+        }
+        __syncthreads();
+    }
+    if (t == 0) { sum_sq[b] = sh[0][0]; sum_prod[b] = sh[1][0]; sum_val[b] = sh[2][0]; count[b] = (int64_t)shc[0]; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1128,6 +1194,18 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         p.lut2 = d_lut2; p.lut2_base = lut2_base; p.lut2_n = (int)lut2.size();
         p.box_slack = 0.0;
         p.gsum = nullptr;
+        p.item_list = nullptr; p.n_live_items = nullptr;
+        const int64_t n_items_all = a_tiles * n_chunks;            // over all ranks
+        const char *bal_env = std::getenv("PIB_BALANCE");
+        const bool balance = use_ring && n_items_all < ((int64_t)1 << 31) && !(bal_env && bal_env[0] == '0');
+        uint32_t *d_keys = nullptr, *d_keys2 = nullptr;
+        int32_t *d_items = nullptr, *d_items2 = nullptr;
+        unsigned *d_nlive = nullptr;
+        if (balance) {
+            PIB_TRY(ws.alloc(&d_keys, (size_t)n_items_all)); PIB_TRY(ws.alloc(&d_keys2, (size_t)n_items_all));
+            PIB_TRY(ws.alloc(&d_items, (size_t)n_items_all)); PIB_TRY(ws.alloc(&d_items2, (size_t)n_items_all));
+            PIB_TRY(ws.alloc(&d_nlive, 1));
+        }
         if (use_ring) {
             const int64_t n_groups = (int64_t)n_tiles * (TILE / 8);
             double *d_gsum;
@@ -1155,6 +1233,17 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
                 const double pmax = std::fabs(sp.box[0]) + std::fabs(sp.box[1]) + std::fabs(sp.box[2]) + std::fabs(sp.box[3]);
                 p.box_slack = 1e-12 * pmax * (std::fabs(p.w00) + std::fabs(p.w01) + std::fabs(p.w10) + std::fabs(p.w11));
             } else p.w00 = p.w01 = p.w10 = p.w11 = 0;
+            if (balance) {
+                PIB_CUDA(cudaMemsetAsync(d_nlive, 0, sizeof(unsigned), stream));
+                const int cgrid = (int)((n_items_all * 32 + 255) / 256);
+                if (n_dirs > 0)
+                    item_cost_kernel<true><<<cgrid, 256, 0, stream>>>(p, ring_nt / TILE, n_items_all, d_keys, d_items, d_nlive);
+                else
+                    item_cost_kernel<false><<<cgrid, 256, 0, stream>>>(p, ring_nt / TILE, n_items_all, d_keys, d_items, d_nlive);
+                PIB_CUDA(cudaGetLastError());
+                PIB_TRY(sort_pairs_u32(d_keys, d_keys2, d_items, d_items2, n_items_all, 7, ws, stream));
+                p.item_list = d_items2; p.n_live_items = d_nlive;
+            }
             timing_begin(PIB_T_PAIR, stream);
             if (use_ring) {
                 const size_t smem = (size_t)(ring + 2) * ring_nt * (sizeof(double2) + sizeof(uint32_t));
@@ -1193,7 +1282,7 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             }
             timing_end(PIB_T_PAIR, stream);
             PIB_TRY(rc);
-            reduce_partials_kernel<<<(n_lags + 127) / 128, 128, 0, stream>>>(
+            reduce_partials_kernel<<<n_lags, 128, 0, stream>>>(
                 d_partial, grid * warps + 1, n_slots, n_lags, d_sum_sq + (size_t)t * n_lags, d_sum_prod + (size_t)t * n_lags,
                 d_sum_val + (size_t)t * n_lags, d_count + (size_t)t * n_lags);
             PIB_CUDA(cudaGetLastError());
