@@ -374,9 +374,9 @@ def run_b200(args):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n, world),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 24), "d2h_bytes_per_step": out_bytes},
-                "gpu_launches": 6 * args.steps,
-                "gpu_launches_note": "per step: bbox_partial, curve_key, gather_soa, tile_box, pair_ring, reduce_partials "
-                                     "(+ CUB radix-sort passes and memsets, not counted)",
+                "gpu_launches": 8 * args.steps,
+                "gpu_launches_note": "per step: bbox_partial, curve_key, gather_soa, tile_box, group_sum, item_cost, pair_ring, "
+                                     "reduce_partials (+ CUB radix-sort passes and memsets, not counted)",
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "extra": extra}
     if world > 1:
         dist.destroy_process_group()
