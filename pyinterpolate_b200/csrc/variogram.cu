@@ -1570,16 +1570,45 @@ static __device__ __forceinline__ bool raw_mask_ref(const TriLag &L, double px, 
     return in_triangle_ref(ax, ay, bx, by, cx, cy, qx, qy) || in_triangle_ref(ax, ay, ix, iy, cx, cy, qx, qy);
 }
 
-__global__ void triangle_kernel(const double2 *__restrict__ xy, const double *__restrict__ z, const int32_t *__restrict__ orig,
-                                int64_t n, const TriLag *__restrict__ lags, int n_lags,
-                                double cos_t, double sin_t, double inv_tol, double band_rel,
-                                double *__restrict__ sums /* [3][n_lags]: sq, prod, neighbour values */,
-                                unsigned long long *__restrict__ count)
+__global__ void __launch_bounds__(128) triangle_kernel(const double2 *__restrict__ xy, const double *__restrict__ z,
+                                                       const int32_t *__restrict__ orig, int64_t n,
+                                                       const double4 *__restrict__ rbox /* per tile, rotated (u, v) */,
+                                                       int n_tiles, double cull_rho,
+                                                       const TriLag *__restrict__ lags, int n_lags,
+                                                       double cos_t, double sin_t, double inv_tol, double band_rel,
+                                                       double *sums /* [3][n_lags]: sq, prod, neighbour values */,
+                                                       unsigned long long *count, int use_smem)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const double h_max = lags[n_lags - 1].h;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double px = xy[i].x, py = xy[i].y, pz = z[i];
+    const int lane = threadIdx.x & 31;
+    // CTA-private accumulators and the lag distances in shared memory (the per-lag global addresses are shared
+    // by every SM; with global REDs they were the hottest lines of the L2); g_sums/g_count get one RED per lag per CTA
+    extern __shared__ __align__(16) unsigned char tri_smem[];
+    double *const g_sums = sums;
+    unsigned long long *const g_count = count;
+    const double *lag_h = nullptr;
+    if (use_smem) {
+        double *sh = reinterpret_cast<double *>(tri_smem);
+        for (int k = threadIdx.x; k < n_lags; k += blockDim.x) sh[k] = lags[k].h;
+        for (int k = threadIdx.x; k < 4 * n_lags; k += blockDim.x) sh[n_lags + k] = 0.0;     // 3 sums + count (bits of 0)
+        lag_h = sh;
+        sums = sh + n_lags;
+        count = reinterpret_cast<unsigned long long *>(sh + 4 * n_lags);
+        __syncthreads();
+    }
+    auto H = [&](int k) -> double { return lag_h ? lag_h[k] : lags[k].h; };
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+        const int64_t i = base + threadIdx.x;
+        const bool valid = i < n;
+        const int64_t ic = valid ? i : n - 1;
+        const double px = xy[ic].x, py = xy[ic].y, pz = z[ic];
+        // box of my warp's 32 centre points in the rotated frame (u along the direction, v across)
+        double u0 = px * cos_t + py * sin_t, v0 = py * cos_t - px * sin_t, u1 = u0, v1 = v0;
+        for (int o = 16; o; o >>= 1) {
+            u0 = fmin(u0, __shfl_xor_sync(0xffffffffu, u0, o)); u1 = fmax(u1, __shfl_xor_sync(0xffffffffu, u1, o));
+            v0 = fmin(v0, __shfl_xor_sync(0xffffffffu, v0, o)); v1 = fmax(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+        }
         // certain pairs of the same lag come in runs (Hilbert order): accumulate a run in registers
         int run = -1;
         double r1 = 0, r2 = 0, r3 = 0;
@@ -1591,7 +1620,22 @@ __global__ void triangle_kernel(const double2 *__restrict__ xy, const double *__
             }
             r1 = r2 = r3 = 0; rc = 0;
         };
-        for (int64_t j = 0; j < n; ++j) {
+        // tiles whose rotated box lies outside every rhombus of every point of the warp are skipped: the union of the
+        // lags' double triangles is the rhombus |u| + |v| / tol <= h_max (cull_rho = h_max + the certainty band + slack)
+        for (int t0 = 0; t0 < n_tiles; t0 += 32) {
+            bool live = false;
+            if (t0 + lane < n_tiles) {
+                const double4 b = rbox[t0 + lane];
+                const double gu = fmax(0.0, fmax(u0 - b.z, b.x - u1)), gv = fmax(0.0, fmax(v0 - b.w, b.y - v1));
+                live = gu + gv * inv_tol <= cull_rho;
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, live);
+            while (todo) {
+                const int tl = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int64_t j0 = (int64_t)(t0 + tl) * TILE, j1 = min(j0 + (int64_t)TILE, n);
+                if (!valid) continue;
+        for (int64_t j = j0; j < j1; ++j) {
             const double qx = xy[j].x, qy = xy[j].y;
             const double dx = qx - px, dy = qy - py;
             const double u = dx * cos_t + dy * sin_t, v = dy * cos_t - dx * sin_t;
@@ -1600,17 +1644,17 @@ __global__ void triangle_kernel(const double2 *__restrict__ xy, const double *__
             if (rho > h_max + band) continue;                       // outside every rhombus for certain
             // k* = first lag with rho <= h_k
             int lo = 0, hi = n_lags;                                // hi == n_lags: beyond the last lag
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (rho <= lags[mid].h) hi = mid; else lo = mid + 1; }
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (rho <= H(mid)) hi = mid; else lo = mid + 1; }
             const int ks = lo;
             // lags whose edge is within the band of rho need the reference's own test; q == p needs it everywhere
             int k_first = ks, k_last = ks - 1;                      // empty range = everything certain
             if (orig[j] == orig[i]) { k_first = 0; k_last = n_lags - 1; }
             else {
-                if (ks < n_lags && lags[ks].h - rho <= band) k_last = ks;
-                if (ks > 0 && rho - lags[ks - 1].h <= band) { k_first = ks - 1; if (k_last < k_first) k_last = ks - 1; }
+                if (ks < n_lags && H(ks) - rho <= band) k_last = ks;
+                if (ks > 0 && rho - H(ks - 1) <= band) { k_first = ks - 1; if (k_last < k_first) k_last = ks - 1; }
                 // (edges farther away than the neighbours of k* are farther than the band too: lags ascend)
-                while (k_first > 0 && rho - lags[k_first - 1].h <= band) --k_first;
-                while (k_last + 1 < n_lags && lags[k_last + 1].h - rho <= band) ++k_last;
+                while (k_first > 0 && rho - H(k_first - 1) <= band) --k_first;
+                while (k_last + 1 < n_lags && H(k_last + 1) - rho <= band) ++k_last;
             }
             const double qz = z[j];
             const double dz = pz - qz;
@@ -1643,7 +1687,19 @@ __global__ void triangle_kernel(const double2 *__restrict__ xy, const double *__
                 atomicAdd(&count[ks], 1ull);
             }
         }
+            }
+        }
         flush();
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < n_lags; k += blockDim.x) {
+            if (count[k]) {
+                atomicAdd(&g_sums[k], sums[k]); atomicAdd(&g_sums[n_lags + k], sums[n_lags + k]);
+                atomicAdd(&g_sums[2 * n_lags + k], sums[2 * n_lags + k]);
+                atomicAdd(&g_count[k], count[k]);
+            }
+        }
     }
 }
 
@@ -1663,9 +1719,26 @@ int variogram_triangle_device(const double *d_xyz, int64_t n, const double *tri_
     PIB_CUDA(cudaMemcpyAsync(d_lags, tri_lags, sizeof(TriLag) * n_lags, cudaMemcpyHostToDevice, stream));
     SortedPoints sp;
     PIB_TRY(build_sorted_points(d_xyz, n, TILE, TILE, ws, stream, &sp));
+    const int n_tiles = (int)((n + TILE - 1) / TILE);
+    double4 *d_rbox;
+    PIB_TRY(ws.alloc(&d_rbox, n_tiles));
+    tile_box_whitened_kernel<<<(int)(((int64_t)n_tiles * 32 + 255) / 256), 256, 0, stream>>>(sp.xy, n, n_tiles, cos_t, sin_t,
+                                                                                             -sin_t, cos_t, d_rbox);
+    PIB_CUDA(cudaGetLastError());
+    // every pair the kernel keeps has rho <= h_max + band; the boxes are of u = x cos + y sin, the pairs use
+    // (x_j - x_i) cos + ...: a few ulps of |coordinates| apart, covered by the same 1e-9-relative band once more
+    const double h_max = tri_lags[9 * (n_lags - 1)];
+    const double cmax = std::max(std::fabs(sp.box[0]), std::fabs(sp.box[2])) + std::max(std::fabs(sp.box[1]), std::fabs(sp.box[3]));
+    const double band_max = 1e-9 * (2.0 * cmax + h_max) * (1.0 + 1.0 / tolerance);
+    const double cull_rho = h_max + 2.0 * band_max;
     const int grid = (int)std::min<int64_t>((n + 127) / 128, 8 * sm_count());
-    triangle_kernel<<<grid, 128, 0, stream>>>(sp.xy, sp.z, sp.orig, n, d_lags, n_lags, cos_t, sin_t, 1.0 / tolerance, 1e-9, d_sums,
-                                              reinterpret_cast<unsigned long long *>(d_count));
+    const int use_smem = n_lags <= 2048;
+    const size_t tri_smem = use_smem ? (size_t)n_lags * 5 * sizeof(double) : 0;
+    if (tri_smem > 48 * 1024)
+        PIB_CUDA(cudaFuncSetAttribute(triangle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_smem));
+    triangle_kernel<<<grid, 128, tri_smem, stream>>>(sp.xy, sp.z, sp.orig, n, d_rbox, n_tiles, cull_rho, d_lags, n_lags, cos_t,
+                                                     sin_t, 1.0 / tolerance, 1e-9, d_sums,
+                                                     reinterpret_cast<unsigned long long *>(d_count), use_smem);
     PIB_CUDA(cudaGetLastError());
     return PIB_OK;
 }
