@@ -1431,17 +1431,47 @@ __global__ void gather_weights_kernel(const double *__restrict__ w, const int32_
 
 // points are Hilbert sorted, so for a fixed i consecutive j fall into the same lag for long runs: a thread
 // accumulates a run in registers and issues its REDs only when the lag changes
-__global__ void weighted_pair_kernel(const double2 *__restrict__ xy, const double *__restrict__ z,
-                                     const double *__restrict__ wts, int64_t n,
-                                     const double *__restrict__ up_d2, const double *__restrict__ low_d2, int n_lags,
-                                     bool ellipse, double w00, double w01, double w10, double w11,
-                                     double *__restrict__ sums /* [4][n_lags] */, unsigned long long *__restrict__ count)
+__global__ void __launch_bounds__(128) weighted_pair_kernel(const double2 *__restrict__ xy, const double *__restrict__ z,
+                                                            const double *__restrict__ wts, int64_t n,
+                                                            const double4 *__restrict__ tbox /* per tile; whitened for ellipse */,
+                                                            int n_tiles, double box_slack,
+                                                            const double *__restrict__ up_g, const double *__restrict__ low_g,
+                                                            int n_lags, bool ellipse, double w00, double w01, double w10,
+                                                            double w11, double *sums /* [4][n_lags] */,
+                                                            unsigned long long *count, int use_smem)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double2 pi = xy[i];
-        const double zi = z[i], wi = wts[i];
+    const int lane = threadIdx.x & 31;
+    // CTA-private accumulators and thresholds in shared memory; one global RED per lag per CTA at the end
+    extern __shared__ __align__(16) unsigned char wt_smem[];
+    double *const g_sums = sums;
+    unsigned long long *const g_count = count;
+    const double *up_d2 = up_g, *low_d2 = low_g;
+    if (use_smem) {
+        double *sh = reinterpret_cast<double *>(wt_smem);
+        for (int k = threadIdx.x; k < n_lags; k += blockDim.x) { sh[k] = up_g[k]; sh[n_lags + k] = low_g[k]; }
+        for (int k = threadIdx.x; k < 5 * n_lags; k += blockDim.x) sh[2 * n_lags + k] = 0.0;
+        up_d2 = sh; low_d2 = sh + n_lags;
+        sums = sh + 2 * n_lags;
+        count = reinterpret_cast<unsigned long long *>(sh + 6 * n_lags);
+        __syncthreads();
+    }
+    const double max_d2 = up_d2[n_lags - 1];
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+        const int64_t i = base + threadIdx.x;
+        const bool valid = i < n;
+        const int64_t ic = valid ? i : n - 1;
+        const double2 pi = xy[ic];
+        const double zi = z[ic], wi = wts[ic];
         const double ui = zi / wi;
+        // bounding box of my warp's 32 points (whitened coordinates for ellipse runs, like the tile boxes)
+        double bx0 = ellipse ? w00 * pi.x + w01 * pi.y : pi.x, by0 = ellipse ? w10 * pi.x + w11 * pi.y : pi.y;
+        double bx1 = bx0, by1 = by0;
+        for (int o = 16; o; o >>= 1) {
+            bx0 = fmin(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); bx1 = fmax(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+            by0 = fmin(by0, __shfl_xor_sync(0xffffffffu, by0, o)); by1 = fmax(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+        }
+        const int64_t warp_first = base + (threadIdx.x & ~31);          // smallest i of my warp
         int run = -1;
         double r1 = 0, r2 = 0, r3 = 0, r4 = 0;
         unsigned long long rc = 0;
@@ -1453,35 +1483,63 @@ __global__ void weighted_pair_kernel(const double2 *__restrict__ xy, const doubl
             }
             r1 = r2 = r3 = r4 = 0; rc = 0;
         };
-        for (int64_t j = i + 1; j < n; ++j) {
-            const double2 pj = xy[j];
-            double d2;
-            if (ellipse) {
-                const double dx = __dsub_rn(pj.x, pi.x), dy = __dsub_rn(pj.y, pi.y);
-                const double n0 = __fma_rn(w01, dy, __dmul_rn(w00, dx));
-                const double n1 = __fma_rn(w11, dy, __dmul_rn(w10, dx));
-                d2 = __dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1));
-            } else {
-                const double dx = __dsub_rn(pi.x, pj.x), dy = __dsub_rn(pi.y, pj.y);
-                d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        // only j > i: tiles before my warp's first point hold nothing; tiles whose box is farther than the last lag
+        // from the warp's box are skipped
+        for (int t0 = (int)(warp_first / TILE) & ~31; t0 < n_tiles; t0 += 32) {
+            bool live = false;
+            const int t = t0 + lane;
+            if (t < n_tiles && (int64_t)(t + 1) * TILE > warp_first + 1) {
+                const double4 b = tbox[t];
+                const double gx = fmax(0.0, fmax(bx0 - b.z, b.x - bx1) - box_slack);
+                const double gy = fmax(0.0, fmax(by0 - b.w, b.y - by1) - box_slack);
+                live = (gx * gx + gy * gy) * (1.0 - 1e-12) <= max_d2;
             }
-            if (!(d2 > 0.0) || d2 > up_d2[n_lags - 1]) continue;
-            // fast check of the current run's lag, else search (lags are disjoint here: regular limits are required)
-            int b = run;
-            if (b < 0 || !(d2 <= up_d2[b] && d2 > low_d2[b])) {
-                int lo = 0, hi = n_lags - 1;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (d2 <= up_d2[mid]) hi = mid; else lo = mid + 1; }
-                b = (d2 > low_d2[lo]) ? lo : -1;
-                if (b < 0) continue;
-                if (b != run) { flush(); run = b; }
+            unsigned todo = __ballot_sync(0xffffffffu, live);
+            while (todo) {
+                const int tl = __ffs(todo) - 1;
+                todo &= todo - 1;
+                if (!valid) continue;
+                const int64_t j0 = max((int64_t)(t0 + tl) * TILE, i + 1), j1 = min((int64_t)(t0 + tl + 1) * TILE, n);
+                for (int64_t j = j0; j < j1; ++j) {
+                    const double2 pj = xy[j];
+                    double d2;
+                    if (ellipse) {
+                        const double dx = __dsub_rn(pj.x, pi.x), dy = __dsub_rn(pj.y, pi.y);
+                        const double n0 = __fma_rn(w01, dy, __dmul_rn(w00, dx));
+                        const double n1 = __fma_rn(w11, dy, __dmul_rn(w10, dx));
+                        d2 = __dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1));
+                    } else {
+                        const double dx = __dsub_rn(pi.x, pj.x), dy = __dsub_rn(pi.y, pj.y);
+                        d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                    }
+                    if (!(d2 > 0.0) || d2 > max_d2) continue;
+                    // fast check of the current run's lag, else search (lags are disjoint here: regular limits are required)
+                    int b = run;
+                    if (b < 0 || !(d2 <= up_d2[b] && d2 > low_d2[b])) {
+                        int lo = 0, hi = n_lags - 1;
+                        while (lo < hi) { const int mid = (lo + hi) >> 1; if (d2 <= up_d2[mid]) hi = mid; else lo = mid + 1; }
+                        b = (d2 > low_d2[lo]) ? lo : -1;
+                        if (b < 0) continue;
+                        if (b != run) { flush(); run = b; }
+                    }
+                    const double zj = z[j], wj = wts[j];
+                    const double wp = (wi * wj) / (wi + wj);
+                    if (ellipse) { const double dz = zj - zi; r1 += wp * (dz * dz); r3 += wi * zi + wj * zj; }
+                    else { const double uj = zj / wj, du = ui - uj; r1 += wp * (du * du); r3 += ui + uj; }
+                    r2 += wp; r4 += wi + wj; ++rc;
+                }
             }
-            const double zj = z[j], wj = wts[j];
-            const double wp = (wi * wj) / (wi + wj);
-            if (ellipse) { const double dz = zj - zi; r1 += wp * (dz * dz); r3 += wi * zi + wj * zj; }
-            else { const double uj = zj / wj, du = ui - uj; r1 += wp * (du * du); r3 += ui + uj; }
-            r2 += wp; r4 += wi + wj; ++rc;
         }
         flush();
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < n_lags; k += blockDim.x) {
+            if (count[k]) {
+                for (int q = 0; q < 4; ++q) atomicAdd(&g_sums[q * n_lags + k], sums[q * n_lags + k]);
+                atomicAdd(&g_count[k], count[k]);
+            }
+        }
     }
 }
 
@@ -1513,11 +1571,28 @@ int variogram_weighted_device(const double *d_xyz, const double *d_weights, int6
     PIB_TRY(ws.alloc(&d_ws, (size_t)n));
     gather_weights_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(d_weights, sp.orig, n, d_ws);
     PIB_CUDA(cudaGetLastError());
+    const int n_tiles = (int)((n + TILE - 1) / TILE);
+    const double4 *d_tbox = sp.tile_box;
+    double box_slack = 0.0;
+    if (n_dirs > 0) {                                          // whitened boxes, as in the ring kernel
+        double4 *d_boxw;
+        PIB_TRY(ws.alloc(&d_boxw, n_tiles));
+        tile_box_whitened_kernel<<<(int)(((int64_t)n_tiles * 32 + 255) / 256), 256, 0, stream>>>(sp.xy, n, n_tiles, W[0], W[1],
+                                                                                                 W[2], W[3], d_boxw);
+        PIB_CUDA(cudaGetLastError());
+        d_tbox = d_boxw;
+        const double pmax = std::fabs(sp.box[0]) + std::fabs(sp.box[1]) + std::fabs(sp.box[2]) + std::fabs(sp.box[3]);
+        box_slack = 1e-12 * pmax * (std::fabs(W[0]) + std::fabs(W[1]) + std::fabs(W[2]) + std::fabs(W[3]));
+    }
+    const int use_smem = n_lags <= 2048;
+    const size_t wt_smem = use_smem ? (size_t)n_lags * 7 * sizeof(double) : 0;
+    if (wt_smem > 48 * 1024)
+        PIB_CUDA(cudaFuncSetAttribute(weighted_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wt_smem));
     const int grid = (int)std::min<int64_t>((n + 127) / 128, 8 * sm_count());
-    weighted_pair_kernel<<<grid, 128, 0, stream>>>(sp.xy, sp.z, d_ws, n, d_up, d_low, n_lags, n_dirs > 0,
-                                                   n_dirs ? W[0] : 0, n_dirs ? W[1] : 0, n_dirs ? W[2] : 0,
-                                                   n_dirs ? W[3] : 0, d_sums,
-                                                   reinterpret_cast<unsigned long long *>(d_count));
+    weighted_pair_kernel<<<grid, 128, wt_smem, stream>>>(sp.xy, sp.z, d_ws, n, d_tbox, n_tiles, box_slack, d_up, d_low, n_lags,
+                                                         n_dirs > 0, n_dirs ? W[0] : 0, n_dirs ? W[1] : 0, n_dirs ? W[2] : 0,
+                                                         n_dirs ? W[3] : 0, d_sums,
+                                                         reinterpret_cast<unsigned long long *>(d_count), use_smem);
     PIB_CUDA(cudaGetLastError());
     return PIB_OK;
 }
