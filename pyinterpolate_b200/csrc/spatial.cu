@@ -181,10 +181,13 @@ int build_sorted_points(const double *d_xyz, int64_t n, int tile, int pad_to, Sc
     sp.n = n; sp.tile = tile;
     for (int i = 0; i < 4; ++i) sp.box[i] = box[i];
     sp.n_pad = (n + pad_to - 1) / pad_to * pad_to;
-    PIB_TRY(ws.alloc(&sp.xy, sp.n_pad)); PIB_TRY(ws.alloc(&sp.z, sp.n_pad));
-    PIB_TRY(ws.alloc(&sp.orig, sp.n_pad));
-    gather_soa_kernel<<<(int)((sp.n_pad + 255) / 256), 256, 0, stream>>>(d_xyz, vals_s, n, sp.n_pad, sp.xy, sp.z,
-                                                                         sp.orig);
+    // the pair kernels read whole A sub-tiles (up to 1024 points) that may start in the last tile: keep that many
+    // sentinel rows behind n_pad so the reads stay inside the arrays
+    const int64_t n_alloc = sp.n_pad + 1024;
+    PIB_TRY(ws.alloc(&sp.xy, n_alloc)); PIB_TRY(ws.alloc(&sp.z, n_alloc));
+    PIB_TRY(ws.alloc(&sp.orig, n_alloc));
+    gather_soa_kernel<<<(int)((n_alloc + 255) / 256), 256, 0, stream>>>(d_xyz, vals_s, n, n_alloc, sp.xy, sp.z,
+                                                                        sp.orig);
     PIB_CUDA(cudaGetLastError());
     const int64_t n_tiles = sp.n_pad / tile;
     PIB_TRY(ws.alloc(&sp.tile_box, n_tiles));

@@ -577,13 +577,15 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
                 evaluated += np;
             }
 
+            // (the lambdas below are forced inline: left to its own budget the compiler kept some of them out of line in
+            // some instantiations, which puts every captured variable into a 1 KB stack frame and costs a factor of 4)
             int wlo = 1;                                      // lag slots accepted by the ring: [wlo, wlo + wlen)
             unsigned wlen = (unsigned)n_lags;
-            auto ring_of = [&](int s, int trash) -> int {
+            auto ring_of = [&](int s, int trash) __attribute__((always_inline)) -> int {
                 return (((unsigned)(s - wlo) < wlen) ? (s & (RING - 1)) : trash) * NT;
             };
             // ---- stage 1: exact lag slot and dz of U consecutive pairs (independent chains) -------
-            auto compute = [&](int j0, int (&sl)[U], double (&dzv)[U]) {
+            auto compute = [&](int j0, int (&sl)[U], double (&dzv)[U]) __attribute__((always_inline)) {
                 double d2[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -629,7 +631,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
                 }
             };
             // ---- stage 2: accumulate the group in registers, touch the ring twice ----------------
-            auto consume = [&](int (&sl)[U], double (&dzv)[U]) {
+            auto consume = [&](int (&sl)[U], double (&dzv)[U]) __attribute__((always_inline)) {
                 int lo = sl[0], mx = sl[0];
 #pragma unroll
                 for (int u = 1; u < U; ++u) { lo = min(lo, sl[u]); mx = max(mx, sl[u]); }
@@ -682,7 +684,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
             // single fp64 compare against the threshold between lo and lo + 1.  A group whose largest high word
             // could exceed the NEXT threshold takes the per-pair slow path under a warp vote (exact slot search).
             struct Grp { double a1, h1, a2, h2; int lo, ch, nout; };
-            auto compute2 = [&](int j0, Grp &g) {
+            auto compute2 = [&](int j0, Grp &g) __attribute__((always_inline)) {
                 double d2[U], dzv[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -760,7 +762,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
                 g.a2 = a2e + a2o; g.h2 = h2e + h2o;
                 g.lo = lo; g.ch = ch; g.nout = nout;
             };
-            auto consume2 = [&](const Grp &g) {
+            auto consume2 = [&](const Grp &g) __attribute__((always_inline)) {
                 const int r_lo = ring_of(g.lo, TRASH_LO), r_hi = ring_of(g.lo + 1, TRASH_HI);   // never equal
                 double2 v_lo = acc[r_lo], v_hi = acc[r_hi];
                 const uint32_t c_lo = cnt[r_lo], c_hi = cnt[r_hi];
@@ -773,7 +775,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
             int sA[U], sB[U];
             double dA[U], dB[U];
             Grp gA, gB;
-            auto sweep = [&]() {                              // all 128 points of the B tile, software pipelined
+            auto sweep = [&]() __attribute__((always_inline)) {                              // all 128 points of the B tile, software pipelined
                 if (diagonal || !p.group_path) {
                     compute(0, sA, dA);
 #pragma unroll 1
