@@ -742,15 +742,16 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
                     }
                 }
                 double dh[U];
-                int ch = 0;
+                unsigned hi_mask = 0;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const bool is_hi = d2[u] > t_lo;
                     // one select instead of two: a "lo" pair keeps the low word of dz under a zero high word, a
                     // subnormal below 1e-308 whose contribution to the fp64 sums is far below one ulp
                     dh[u] = __hiloint2double(is_hi ? __double2hiint(dzv[u]) : 0, __double2loint(dzv[u]));
-                    ch += is_hi ? 1 : 0;
+                    if (is_hi) hi_mask |= 1u << u;                                        // one predicated OR per pair
                 }
+                const int ch = __popc(hi_mask);
                 g.a1 = a1;
                 g.h1 = ((dh[0] + dh[1]) + (dh[2] + dh[3])) + ((dh[4] + dh[5]) + (dh[6] + dh[7]));
                 double a2e = dzv[0] * dzv[0], a2o = dzv[1] * dzv[1], h2e = dh[0] * dh[0], h2o = dh[1] * dh[1];
