@@ -8,6 +8,8 @@ There is no CPU fallback: without the CUDA library or a GPU every compute call r
 from .indicator import ExperimentalIndicatorVariogram, IndicatorKriging, IndicatorVariogramData
 from .kriging import indicator_kriging, interpolate_points, ordinary_kriging, simple_kriging
 from .models import TheoreticalVariogram
+from .pipelines import (MultivariateRegression, UniversalKriging, interpolate_points_dask, interpolate_raster,
+                        set_dimensions)
 from .variogram import (DirectionalVariogram, ExperimentalVariogram, VariogramCloud, build_experimental_variogram,
                         calculate_covariance, calculate_semivariance, point_cloud_semivariance)
 
@@ -16,4 +18,5 @@ __all__ = ["ExperimentalVariogram", "DirectionalVariogram", "build_experimental_
            "calculate_semivariance", "calculate_covariance", "point_cloud_semivariance", "VariogramCloud",
            "TheoreticalVariogram",
            "ordinary_kriging", "simple_kriging", "interpolate_points", "indicator_kriging",
-           "ExperimentalIndicatorVariogram", "IndicatorVariogramData", "IndicatorKriging"]
+           "ExperimentalIndicatorVariogram", "IndicatorVariogramData", "IndicatorKriging",
+           "interpolate_points_dask", "interpolate_raster", "set_dimensions", "MultivariateRegression", "UniversalKriging"]
