@@ -386,3 +386,39 @@ class VariogramCloud:
             import pandas as pd
             return pd.DataFrame(stats)
         return stats
+
+    def remove_outliers(self, method='zscore', z_lower_limit=-3, z_upper_limit=3, iqr_lower_limit=1.5,
+                        iqr_upper_limit=1.5, inplace=False):
+        """variogram_cloud.py:334-397 with the detectors of transform/statistical.py:14-95: per lag, drop the cloud
+        values whose z-score leaves ``[z_lower_limit, z_upper_limit]`` or that lie more than ``iqr_*_limit`` standard
+        deviations outside the quartiles."""
+        if method == 'zscore':
+            if z_lower_limit >= 0:
+                raise ValueError('The parameter z_lower must be a float lesser than zero.')
+            if z_upper_limit <= 0:
+                raise ValueError('The parameter z_upper must be a float greater than zero.')
+        elif method == 'iqr':
+            if iqr_upper_limit < 0 or iqr_lower_limit < 0:
+                raise ValueError('Parameters iqr_lower and iqr_upper must be floats greater or equal to 0.')
+        else:
+            raise KeyError(f'Given detection method: {method} is not available. '
+                           f'Available methods are "zscore" and "iqr".')
+        cleaned = {}
+        for lag, values in self.semivariances.items():
+            values = np.asarray(values)
+            if method == 'zscore':
+                with np.errstate(invalid='ignore', divide='ignore'):
+                    score = (values - values.mean()) / values.std()          # scipy.stats.zscore, ddof = 0
+                bad = (score > z_upper_limit) | (score < z_lower_limit)
+            else:
+                spread = np.std(values)
+                bad = ((values > np.quantile(values, q=0.75) + spread * iqr_upper_limit)
+                       | (values < np.quantile(values, q=0.25) - spread * iqr_lower_limit))
+            cleaned[lag] = values[~bad]
+        if inplace:
+            self.semivariances = cleaned
+            return None
+        import copy
+        other = copy.copy(self)
+        other.semivariances = cleaned
+        return other

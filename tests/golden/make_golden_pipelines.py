@@ -44,6 +44,18 @@ def main():
     g["uk_bias_sill"] = np.array(float(np.var(uk.bias_values)))
     g["uk_coefficients"] = np.append(uk.trend_model.coefficients, uk.trend_model.intercept)
     g["uk_pred"] = uk.predict(unk, no_neighbors=10, show_progress_bar=False)
+    # VariogramCloud.remove_outliers (classes/variogram_cloud.py:334-397 -> transform/statistical.py:165-247)
+    from pyinterpolate.transform.statistical import remove_outliers
+    rng = np.random.default_rng(93)
+    cloud = {500.0: rng.gamma(2.0, 3.0, 400), 1000.0: np.append(rng.normal(10, 1, 300), [40.0, -25.0]),
+             1500.0: rng.exponential(5.0, 50)}
+    for lag, v in cloud.items():
+        g[f"cloud_in_{int(lag)}"] = v
+    for name, kw in (("z", dict(method="zscore")), ("z2", dict(method="zscore", z_lower_limit=-1.5, z_upper_limit=2.0)),
+                     ("iqr", dict(method="iqr")), ("iqr2", dict(method="iqr", iqr_lower_limit=0.5, iqr_upper_limit=1.0))):
+        out = remove_outliers(cloud, **kw)
+        for lag, v in out.items():
+            g[f"cloud_{name}_{int(lag)}"] = v
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_golden_pipelines.npz"), **g)
     print(g["raster_result"].shape, g["uk_pred"][:2], g["uk_coefficients"])
 

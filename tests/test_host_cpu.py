@@ -186,3 +186,26 @@ def test_indicator_coding_and_thresholds():
     ids = code_indicators(ds, thr)
     assert ids.shape == (10, 6) and ids[:, 2:].sum(axis=0).tolist() == [3, 5, 7, 10]
     assert IndicatorVariogramData(ds, 4).ids.shape == (10, 6)
+
+
+def test_variogram_cloud_remove_outliers_matches_reference():
+    """Host-side outlier filters of VariogramCloud (classes/variogram_cloud.py:334-397) against fixtures from the
+    reference's remove_outliers (tests/golden/make_golden_pipelines.py); no GPU involved."""
+    from pyinterpolate_b200.variogram import VariogramCloud
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_pipelines.npz"))
+    vc = VariogramCloud.__new__(VariogramCloud)
+    vc.semivariances = {lag: g[f"cloud_in_{int(lag)}"] for lag in (500.0, 1000.0, 1500.0)}
+    vc.lags = np.array([500.0, 1000.0, 1500.0])
+    cases = (("z", dict(method="zscore")), ("z2", dict(method="zscore", z_lower_limit=-1.5, z_upper_limit=2.0)),
+             ("iqr", dict(method="iqr")), ("iqr2", dict(method="iqr", iqr_lower_limit=0.5, iqr_upper_limit=1.0)))
+    for name, kw in cases:
+        out = vc.remove_outliers(**kw)
+        for lag in vc.lags:
+            np.testing.assert_array_equal(out.semivariances[lag], g[f"cloud_{name}_{int(lag)}"])
+        assert out is not vc and len(vc.semivariances[1000.0]) == 302
+    with pytest.raises(KeyError):
+        vc.remove_outliers(method="mad")
+    with pytest.raises(ValueError):
+        vc.remove_outliers(z_lower_limit=1)
+    assert vc.remove_outliers(method="iqr", inplace=True) is None
+    np.testing.assert_array_equal(vc.semivariances[1000.0], g["cloud_iqr_1000"])
