@@ -224,6 +224,14 @@ PIB_API int pib_krige_ex_host(const double *known, int64_t n,
                       double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
                       double *out, int32_t *nbr_idx, uint8_t *status);
 
+/* Leave-one-out cross-validation in one batched call — replaces the loop of evaluate/cross_validation.py:78-131
+ * (np.delete(points, i) + ordinary_kriging / simple_kriging at point i, for every i): location i is known row i,
+ * and the neighbour search skips that row.  out [n][4] = [zhat_i, sigma^2_i, x_i, y_i]; status as above.
+ * One parameter set: params = {nugget, sill, rang}.  Selection arguments as in pib_krige_ex_host. */
+PIB_API int pib_krige_loo_host(const double *known, int64_t n, const double *params, int model, int mode,
+                       double process_mean, int k, double neighbors_range, double direction, double max_tick,
+                       int use_all, int allow_lsa, double *out, uint8_t *status);
+
 /* gamma(h) for h[0..n) with the device implementation of the seven models (for tests) */
 PIB_API int pib_gamma_host(int model, double nugget, double sill, double rang,
                    const double *h, int64_t n, double *out);

@@ -19,7 +19,7 @@ STATUS_OK, STATUS_SINGULAR, STATUS_NEGATIVE_VARIANCE = 0, 1, 2
 STATUS_TOO_MANY_NEIGHBORS = 3
 STATUS_LSA, STATUS_ZERO_MATRIX = 4, 5
 
-EXPORTS = ("pib_krige_ex_device", "pib_krige_ex_host", "pib_last_error", "pib_version", "pib_device_sm_count", "pib_variogram_device",
+EXPORTS = ("pib_krige_loo_host", "pib_krige_ex_device", "pib_krige_ex_host", "pib_last_error", "pib_version", "pib_device_sm_count", "pib_variogram_device",
            "pib_variogram_host", "pib_krige_device", "pib_krige_host", "pib_gamma_host",
            "pib_fp64_peak_tflops", "pib_last_kernel_ms", "pib_variogram_cloud_host",
            "pib_variogram_weighted_host", "pib_variogram_triangle_host")
@@ -54,6 +54,7 @@ def load():
     kr_ex = kr_args[:11] + [f64, f64, f64, i32, i32] + kr_args[11:]
     L.pib_krige_ex_device.argtypes = kr_ex + [ctypes.c_void_p]
     L.pib_krige_ex_host.argtypes = kr_ex
+    L.pib_krige_loo_host.argtypes = [dp, i64, dp, i32, i32, f64, i32, f64, f64, f64, i32, i32, dp, dp]
     L.pib_gamma_host.argtypes = [i32, f64, f64, f64, dp, i64, dp]
     L.pib_fp64_peak_tflops.argtypes = [dp]
     L.pib_last_kernel_ms.argtypes = [i32, dp, dp]
@@ -194,6 +195,23 @@ def krige_host(known, unknown, model, params, mode, k, process_mean=0.0, values=
                              1 if use_all else 0, 1 if allow_lsa else 0, _host_ptr(out), _host_ptr(idx), _host_ptr(status))
     check(rc, "pib_krige_ex_host")
     return out, idx, status
+
+
+def krige_loo_host(known, model, params, mode, k, process_mean=0.0, neighbors_range=0.0, direction=None, max_tick=5.0,
+                   use_all=False, allow_lsa=False):
+    """Leave-one-out kriging of every known row from the others.  Returns (out[n, 4], status[n])."""
+    L = load()
+    known = _f64(known)
+    params = _f64(params).reshape(1, 3)
+    n = known.shape[0]
+    out = np.zeros((n, 4))
+    status = np.zeros(n, dtype=np.uint8)
+    rc = L.pib_krige_loo_host(_host_ptr(known), n, _host_ptr(params), int(model), int(mode), float(process_mean), int(k),
+                              float(neighbors_range), float("nan") if direction is None else float(direction),
+                              float(max_tick), 1 if use_all else 0, 1 if allow_lsa else 0, _host_ptr(out),
+                              _host_ptr(status))
+    check(rc, "pib_krige_loo_host")
+    return out, status
 
 
 def krige_device(known_t, unknown_t, model, params, mode, k, process_mean=0.0, values_t=None,

@@ -79,7 +79,7 @@ int variogram_triangle_device(const double *d_xyz, int64_t n, const double *tri_
 int krige_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
                  const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
                  double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
-                 double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, cudaStream_t stream);
+                 const int32_t *d_exclude, double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, cudaStream_t stream);
 int gamma_device(int model, double nugget, double sill, double rang, const double *d_h, int64_t n, double *d_out,
                  cudaStream_t stream);
 
@@ -255,7 +255,7 @@ int pib_krige_ex_device(const double *d_known, int64_t n, const double *d_values
 {
     PIB_CHECK(d_known && (d_unknown || m == 0) && (d_out || m == 0), PIB_ERR_INVALID, "krige: NULL pointer");
     return krige_device(d_known, n, d_values, n_sets, params, d_unknown, m, model, mode, process_mean, k,
-                        neighbors_range, direction, max_tick, use_all, allow_lsa, d_out, d_nbr_idx, d_status,
+                        neighbors_range, direction, max_tick, use_all, allow_lsa, nullptr, d_out, d_nbr_idx, d_status,
                         static_cast<cudaStream_t>(stream));
 }
 
@@ -307,13 +307,66 @@ int pib_krige_ex_host(const double *known, int64_t n, const double *values, int 
         }
         if (rc == PIB_OK)
             rc = krige_device(d_known, n, d_values, n_sets, params, d_unknown, m, model, mode, process_mean, k,
-                              neighbors_range, direction, max_tick, use_all, allow_lsa, d_out, d_idx, d_status, stream);
+                              neighbors_range, direction, max_tick, use_all, allow_lsa, nullptr, d_out, d_idx, d_status, stream);
         if (rc == PIB_OK) {
             e = cudaMemcpyAsync(out, d_out, sizeof(double) * 4 * n_sets * m, cudaMemcpyDeviceToHost, stream);
             if (e == cudaSuccess && nbr_idx) e = cudaMemcpyAsync(nbr_idx, d_idx, sizeof(int32_t) * m * k, cudaMemcpyDeviceToHost, stream);
             if (e == cudaSuccess && status) e = cudaMemcpyAsync(status, d_status, (size_t)n_sets * m, cudaMemcpyDeviceToHost, stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
             if (e != cudaSuccess) { set_error(std::string("krige: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; }
+        }
+    }
+    cudaStreamSynchronize(stream);
+    cudaStreamDestroy(stream);
+    return rc;
+}
+
+// leave-one-out: location i = known row i, kriged from the other rows
+__global__ void loo_setup_kernel(const double *__restrict__ known, int64_t n, double *__restrict__ unknown,
+                                 int32_t *__restrict__ exclude)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unknown[2 * i] = known[3 * i]; unknown[2 * i + 1] = known[3 * i + 1];
+    exclude[i] = (int32_t)i;
+}
+
+int pib_krige_loo_host(const double *known, int64_t n, const double *params, int model, int mode, double process_mean,
+                       int k, double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
+                       double *out, uint8_t *status)
+{
+    PIB_CHECK(known && out && params, PIB_ERR_INVALID, "krige_loo: NULL pointer");
+    PIB_CHECK(n >= 2 && k >= 1, PIB_ERR_INVALID, "krige_loo: need n >= 2, k >= 1");
+    cudaStream_t stream;
+    PIB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    int rc;
+    {
+        Scratch ws(stream);
+        double *d_known, *d_unknown, *d_out;
+        int32_t *d_exclude;
+        uint8_t *d_status = nullptr;
+        rc = ws.alloc(&d_known, (size_t)n * 3);
+        if (rc == PIB_OK) rc = ws.alloc(&d_unknown, (size_t)n * 2);
+        if (rc == PIB_OK) rc = ws.alloc(&d_exclude, (size_t)n);
+        if (rc == PIB_OK) rc = ws.alloc(&d_out, (size_t)n * 4);
+        if (rc == PIB_OK && status) rc = ws.alloc(&d_status, (size_t)n);
+        cudaError_t e = cudaSuccess;
+        if (rc == PIB_OK) {
+            e = cudaMemcpyAsync(d_known, known, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, stream);
+            if (e == cudaSuccess) {
+                loo_setup_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(d_known, n, d_unknown, d_exclude);
+                e = cudaGetLastError();
+            }
+            if (e != cudaSuccess) { set_error(std::string("krige_loo: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; }
+        }
+        if (rc == PIB_OK)
+            rc = krige_device(d_known, n, nullptr, 1, params, d_unknown, n, model, mode, process_mean, k, neighbors_range,
+                              direction, max_tick, use_all, allow_lsa, d_exclude, d_out, nullptr, d_status, stream);
+        if (rc == PIB_OK) {
+            e = cudaMemcpyAsync(out, d_out, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess && status) e = cudaMemcpyAsync(status, d_status, (size_t)n, cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) { set_error(std::string("krige_loo: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; }
         }
     }
     cudaStreamSynchronize(stream);

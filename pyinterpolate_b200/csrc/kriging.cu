@@ -127,6 +127,7 @@ struct KnnParams {
     int use_all;
     int stride;                 // row stride of nbr_pos / nbr_d (>= kk)
     int isotropic;              // range kernel without the angular filter (use_all_neighbors_in_range, isotropic model)
+    const int32_t *exclude;     // NULL, or [m]: row of `known` that location q must not use (leave-one-out), -1 = none
 };
 
 static __device__ __forceinline__ Cand make_cand(const GridIndex &g, int pos, double ux, double uy)
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const KnnParams p)
     const int cx = clampi((int)floor((ux - g.x0) * g.inv_h), 0, g.gx - 1);
     const int cy = clampi((int)floor((uy - g.y0) * g.inv_h), 0, g.gy - 1);
     const double slack = 1e-9 * (fabs(ux) + fabs(uy) + fabs(g.x0) + fabs(g.y0) + g.h * (g.gx + g.gy));
+    const int ex = p.exclude ? p.exclude[q] : -1;               // leave-one-out: this row is not a neighbour
 
     if constexpr (E > 0) {
         const int r = p.r0;
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const KnnParams p)
         }
         const int total = __shfl_sync(0xffffffffu, pre, 31);
         pre -= len;
-        if (n_rows <= 32 && total <= 32 * E && total >= kk) {
+        if (n_rows <= 32 && total <= 32 * E && total - (ex >= 0 ? 1 : 0) >= kk) {
             Cand c[E];
 #pragma unroll
             for (int b = 0; b < E; ++b) {
@@ -192,7 +194,10 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const KnnParams p)
                     const int rs = __shfl_sync(0xffffffffu, seg0, row);
                     if (f >= rp && f < rp + rl) pos = rs + (f - rp);
                 }
-                if (pos >= 0) c[b] = make_cand(g, pos, ux, uy);
+                if (pos >= 0) {
+                    c[b] = make_cand(g, pos, ux, uy);
+                    if (c[b].orig == ex) c[b] = cand_inf();
+                }
             }
             // bitonic sort of the 32 * E candidates; element index = lane * E + b
 #pragma unroll
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const KnnParams p)
                     const int pos = base + lane;
                     Cand c = cand_inf();
                     if (pos < s1) c = make_cand(g, pos, ux, uy);
-                    topk_offer(top, c, pos < s1, lane);
+                    topk_offer(top, c, pos < s1 && c.orig != ex, lane);
                 }
             }
         }
@@ -353,6 +358,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_dir_kernel(const KnnParams
     const int x_hi = clampi((int)floor((ux + p.range - g.x0) * g.inv_h) + 1, 0, g.gx - 1);
     const int y_lo = clampi((int)floor((uy - p.range - g.y0) * g.inv_h) - 1, 0, g.gy - 1);
     const int y_hi = clampi((int)floor((uy + p.range - g.y0) * g.inv_h) + 1, 0, g.gy - 1);
+    const int ex = p.exclude ? p.exclude[q] : -1;
     int *hist = s_hist[warp];
     for (int t = lane; t < MAX_TOL + 2; t += 32) hist[t] = 0;
     __syncwarp();
@@ -370,7 +376,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_dir_kernel(const KnnParams
                 double ad = 0.0;
                 if (pos < s1) {
                     c = make_cand(g, pos, ux, uy);
-                    if (c.d <= p.range) {                        // distances <= max_range (select_points.py:201 / :93)
+                    if (c.d <= p.range && c.orig != ex) {        // distances <= max_range (select_points.py:201 / :93)
                         ad = p.isotropic ? 0.0 : angular_difference(ux, uy, g.x[pos], g.y[pos], p.direction);
                         ok = true;
                     }
@@ -410,7 +416,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_dir_kernel(const KnnParams
         int in_range = 0;
         for (int t = 1; t <= p.last_tol; ++t) in_range += hist[t];
         if (in_range < p.k) {
-            if (lane == 0) p.nbr_count[slot] = min(p.k, (int)g.n);
+            if (lane == 0) p.nbr_count[slot] = min(p.k, (int)g.n - (ex >= 0 ? 1 : 0));
             return;
         }
     }
@@ -1108,7 +1114,7 @@ __global__ void __launch_bounds__(32) singular_kernel(const SingularParams sp)
 int krige_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
                  const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
                  double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
-                 double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, cudaStream_t stream)
+                 const int32_t *d_exclude, double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, cudaStream_t stream)
 {
     const bool directional = !std::isnan(direction);
     const bool ranged = directional || use_all;                 // the selection depends on neighbors_range
@@ -1120,7 +1126,9 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
     PIB_CHECK(mode == PIB_KRIGE_ORDINARY || mode == PIB_KRIGE_SIMPLE, PIB_ERR_INVALID, "krige: unknown mode");
     PIB_CHECK(m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31), PIB_ERR_UNSUPPORTED, "krige: more than 2^31-1 rows");
     PIB_CHECK(std::min<int64_t>(k, n) <= MAX_K, PIB_ERR_UNSUPPORTED, "krige: no_neighbors above 128 is not supported");
-    const int kk = use_all ? (int)std::min<int64_t>(MAX_K, n) : (int)std::min<int64_t>(k, n);
+    const int64_t n_avail = d_exclude ? n - 1 : n;              // leave-one-out: every location loses one row
+    PIB_CHECK(n_avail >= 1, PIB_ERR_INVALID, "krige: leave-one-out needs at least two known points");
+    const int kk = use_all ? (int)std::min<int64_t>(MAX_K, n_avail) : (int)std::min<int64_t>(k, n_avail);
     int last_tol = 1;
     if (directional) {
         last_tol = std::max(2, (int)std::floor(max_tick) + 1);   // 1, 2, ... until the tolerance exceeds max_tick
@@ -1168,7 +1176,7 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
     PIB_TRY(ws.alloc(&nbr_d, (size_t)chunk * kk));
     int32_t *nbr_count = nullptr;
     if (ranged) PIB_TRY(ws.alloc(&nbr_count, (size_t)chunk));
-    const int ksel = (int)std::min<int64_t>(k, n);              // what the plain k-nearest search selects
+    const int ksel = (int)std::min<int64_t>(k, n_avail);        // what the plain k-nearest search selects
     if (!d_status) {                                            // the singular-system pass needs the status bytes
         PIB_TRY(ws.alloc(&d_status, (size_t)n_sets * m));
     }
@@ -1188,7 +1196,7 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
         kp.g = g; kp.unknown = d_unknown; kp.order = order + begin; kp.count = count; kp.kk = kk; kp.k2 = k2; kp.r0 = r0;
         kp.nbr_pos = nbr_pos; kp.nbr_d = nbr_d; kp.nbr_idx = d_nbr_idx; kp.k = k;
         kp.nbr_count = nbr_count; kp.range = neighbors_range; kp.direction = direction; kp.last_tol = last_tol;
-        kp.use_all = use_all; kp.stride = kk; kp.isotropic = directional ? 0 : 1;
+        kp.use_all = use_all; kp.stride = kk; kp.isotropic = directional ? 0 : 1; kp.exclude = d_exclude;
         timing_begin(PIB_T_KNN, stream);
         if (!directional && use_all) {
             // k nearest first (the fallback rows), then the range kernel replaces them where >= k points are in range

@@ -104,6 +104,28 @@ def simple_kriging(theoretical_model, known_locations, unknown_locations=None, p
     return (out[0], idx) if return_neighbors else out[0]
 
 
+def validate_kriging(points, theoretical_model, how='ok', neighbors_range=None, no_neighbors=4,
+                     use_all_neighbors_in_range=False, sk_mean=None, allow_approximate_solutions=False):
+    """Leave-one-out cross-validation — evaluate/cross_validation.py:11-138 — as ONE batched launch: every known
+    point is kriged from the others (the neighbour search skips the point's own row, which is what
+    ``np.delete(points, idx, 0)`` does in the reference's loop).
+
+    Returns ``(mean prediction error, mean variance error, [x, y, prediction error, kriging variance] rows)``."""
+    if how not in ('ok', 'sk'):
+        raise KeyError('Allowed kriging types (parameter "how") are: "ok" - ordinary kriging, and "sk" - simple kriging.')
+    mid, params, known, _, sel = _prepare(theoretical_model, points, np.zeros((1, 2)), use_all_neighbors_in_range,
+                                          allow_approximate_solutions, neighbors_range)
+    if how == 'sk' and sk_mean is None:
+        raise TypeError("validate_kriging(how='sk') needs sk_mean")
+    out, status = _lib.krige_loo_host(known, mid, params, _lib.KRIGE_ORDINARY if how == 'ok' else _lib.KRIGE_SIMPLE,
+                                      int(no_neighbors), process_mean=0.0 if sk_mean is None else float(sk_mean), **sel)
+    _raise_on_singular(status)
+    output_arr = np.column_stack([out[:, 2], out[:, 3], known[:, 2] - out[:, 0], out[:, 1]])
+    mean_prediction_error = np.mean(output_arr[:, 2])
+    mean_variance_error = np.var(output_arr[:, 2]) / np.mean(output_arr[:, 3])
+    return mean_prediction_error, mean_variance_error, output_arr
+
+
 def interpolate_points(theoretical_model, known_locations, unknown_locations, neighbors_range=None,
                        no_neighbors=4, max_tick=5., use_all_neighbors_in_range=False,
                        allow_approximate_solutions=False, progress_bar=True):

@@ -44,6 +44,18 @@ def main():
     g["uk_bias_sill"] = np.array(float(np.var(uk.bias_values)))
     g["uk_coefficients"] = np.append(uk.trend_model.coefficients, uk.trend_model.intercept)
     g["uk_pred"] = uk.predict(unk, no_neighbors=10, show_progress_bar=False)
+    # leave-one-out cross-validation (evaluate/cross_validation.py:11-138)
+    from pyinterpolate.evaluate.cross_validation import validate_kriging
+    cv_pts = dem_like_field(600, extent=8_000.0, seed=94)
+    g["cv_points"] = cv_pts
+    mcv = TheoreticalVariogram()
+    mcv.from_dict({"variogram_model_type": "spherical", "nugget": 0.4, "sill": float(np.var(cv_pts[:, 2])), "rang": 2500.0})
+    for how, kw in (("ok", {}), ("sk", {"sk_mean": float(cv_pts[:, 2].mean())})):
+        mpe, mve, arr = validate_kriging(cv_pts, mcv, how=how, no_neighbors=8, **kw)
+        g[f"cv_{how}_stats"] = np.array([mpe, mve])
+        g[f"cv_{how}_arr"] = arr
+    mpe, mve, arr = validate_kriging(cv_pts[:40], mcv, how="ok", no_neighbors=64)       # fewer points than neighbours
+    g["cv_small_arr"] = arr
     # VariogramCloud.remove_outliers (classes/variogram_cloud.py:334-397 -> transform/statistical.py:165-247)
     from pyinterpolate.transform.statistical import remove_outliers
     rng = np.random.default_rng(93)

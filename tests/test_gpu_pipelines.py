@@ -65,3 +65,37 @@ def test_universal_kriging(pib, gold):
     assert pred.shape == gold["uk_pred"].shape
     np.testing.assert_allclose(pred[:, 0], gold["uk_pred"][:, 0], rtol=RTOL)
     np.testing.assert_array_equal(pred[:, 1:], gold["uk_pred"][:, 1:])
+
+
+def test_validate_kriging_leave_one_out(pib, gold):
+    """evaluate/cross_validation.py:11-138 as one batched launch with the point's own row excluded."""
+    pts = gold["cv_points"]
+    mdl = {"variogram_model_type": "spherical", "nugget": 0.4, "sill": float(np.var(pts[:, 2])), "rang": 2500.0}
+    for how, kw in (("ok", {}), ("sk", {"sk_mean": float(pts[:, 2].mean())})):
+        mpe, mve, arr = pib.validate_kriging(pts, mdl, how=how, no_neighbors=8, **kw)
+        want = gold[f"cv_{how}_arr"]
+        np.testing.assert_array_equal(arr[:, :2], want[:, :2])
+        np.testing.assert_allclose(arr[:, 2], want[:, 2], rtol=1e-8, atol=1e-9 * np.abs(pts[:, 2]).max())
+        np.testing.assert_allclose(arr[:, 3], want[:, 3], rtol=RTOL)
+        np.testing.assert_allclose([mpe, mve], gold[f"cv_{how}_stats"], rtol=1e-7, atol=1e-12)
+    _, _, arr = pib.validate_kriging(pts[:40], mdl, how="ok", no_neighbors=64)          # k > n - 1: all other rows
+    np.testing.assert_allclose(arr[:, 2:], gold["cv_small_arr"][:, 2:], rtol=1e-7, atol=1e-9 * np.abs(pts[:, 2]).max())
+    with pytest.raises(KeyError):
+        pib.validate_kriging(pts, mdl, how="uk")
+
+
+def test_leave_one_out_equals_explicit_deletion(pib):
+    """The exclusion in the neighbour search is the same as kriging each point from the array without it —
+    checked on clustered data (incremental search path) and with a directional model."""
+    rng = np.random.default_rng(95)
+    centres = rng.uniform(0, 30_000, size=(6, 2))
+    xy = np.vstack([c + rng.normal(0, 150.0, size=(60, 2)) for c in centres])
+    pts = np.column_stack([xy, 20 + np.sin(xy[:, 0] / 3000.0) + rng.normal(0, 0.2, len(xy))])
+    for mdl in ({"variogram_model_type": "exponential", "nugget": 0.01, "sill": float(np.var(pts[:, 2])), "rang": 4000.0},
+                {"variogram_model_type": "exponential", "nugget": 0.01, "sill": float(np.var(pts[:, 2])), "rang": 4000.0,
+                 "direction": 40.0}):
+        _, _, arr = pib.validate_kriging(pts, mdl, how="ok", no_neighbors=6)
+        for i in (0, 59, 60, 200, 359):
+            one = pib.ordinary_kriging(mdl, np.delete(pts, i, 0), pts[i:i + 1, :2], no_neighbors=6)[0]
+            np.testing.assert_allclose(pts[i, 2] - arr[i, 2], one[0], rtol=1e-12, equal_nan=True)
+            np.testing.assert_allclose(arr[i, 3], one[1], rtol=1e-12, equal_nan=True)
