@@ -31,3 +31,7 @@ pts = dem_like_field(30_000, seed=7)
 timed("variogram cloud, 30k points, 20 lags to 10 km", lambda: pib.ExperimentalVariogram(pts, 500, 10_000, as_cloud=True))
 timed("directional variogram 't' (default), 4 directions + ISO, 100k points", lambda: pib.DirectionalVariogram(known[:100_000], step_size=500, max_range=40_500, tolerance=0.2))
 timed("directional variogram 'e', 4 directions + ISO, 100k points", lambda: pib.DirectionalVariogram(known[:100_000], step_size=500, max_range=40_500, tolerance=0.2, dir_neighbors_selection_method="e"))
+big = dem_like_field(1_000_000, seed=8)
+mb = {"variogram_model_type": "spherical", "nugget": 0.5, "sill": float(np.var(big[:, 2])), "rang": 2000.0}
+timed("validate_kriging (leave-one-out), 1M points, k=16", lambda: pib.validate_kriging(big, mb, no_neighbors=16))
+timed("interpolate_raster, 1M known points, 1000 x 1000 pixels, k=16", lambda: pib.interpolate_raster(big, dim=1000, number_of_neighbors=16, semivariogram_model=mb))
