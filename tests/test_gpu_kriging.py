@@ -204,3 +204,32 @@ def test_more_locations_than_one_chunk(pib):
     lo = (1 << 21) - 1000
     part, _, _ = _lib.krige_host(known, unk[lo:lo + 3000], _lib.MODEL_IDS["spherical"], params, _lib.KRIGE_ORDINARY, 8)
     np.testing.assert_array_equal(part[0], out[0, lo:lo + 3000])
+
+
+def test_baseline_config3_full_size(pib):
+    """BASELINE config 3 at full size: simple kriging of 10M locations from 1M known points, k=64 (five chunks).
+    Size-independent property: a random subset kriged on its own reproduces its rows bit for bit."""
+    known = dem_like_field(1_000_000, seed=0)
+    unk = uniform_locations(10_000_000, seed=1)
+    mdl = {"variogram_model_type": "spherical", "nugget": 1.0, "sill": float(np.var(known[:, 2])), "rang": 5000.0}
+    pm = float(known[:, 2].mean())
+    sk = pib.simple_kriging(mdl, known, unk, process_mean=pm, no_neighbors=64)
+    assert sk.shape == (10_000_000, 4) and np.isfinite(sk[:, 0]).all()
+    np.testing.assert_array_equal(sk[:, 2:], unk)
+    sub = np.random.default_rng(2).choice(len(unk), 3000, replace=False)
+    np.testing.assert_array_equal(pib.simple_kriging(mdl, known, unk[sub], process_mean=pm, no_neighbors=64), sk[sub])
+
+
+def test_baseline_config4_full_size(pib):
+    """BASELINE config 4 at full size: indicator kriging with 8 thresholds on 500k points (one neighbour search,
+    eight solves per location)."""
+    known = dem_like_field(500_000, seed=3)
+    unk = uniform_locations(500_000, seed=4)
+    thr = np.quantile(known[:, 2], np.linspace(0.1, 0.9, 8))
+    models = [{"variogram_model_type": "spherical", "nugget": 0.02, "sill": 0.2, "rang": 4000.0 + 250.0 * t} for t in range(8)]
+    ik = pib.kriging.indicator_kriging(models, thr, known, unk, no_neighbors=16, reference_variance_column=False)
+    assert ik.shape == (500_000, 8) and ik.min() >= 0.0 and ik.max() <= 1.0
+    assert np.all(np.diff(ik.mean(axis=0)) > 0)                   # P(z <= threshold) grows with the threshold
+    sub = np.random.default_rng(5).choice(len(unk), 3000, replace=False)
+    np.testing.assert_array_equal(
+        pib.kriging.indicator_kriging(models, thr, known, unk[sub], no_neighbors=16, reference_variance_column=False), ik[sub])
