@@ -296,3 +296,30 @@ def test_1m_points_properties(pib):
     torch.cuda.synchronize()
     np.testing.assert_array_equal(dev["count"].cpu().numpy(), base["count"])
     np.testing.assert_array_equal(dev["sum_sq"].cpu().numpy(), base["sum_sq"])   # deterministic reduction order
+
+
+def test_baseline_config_directional_full_size(pib):
+    """BASELINE directional config at full size (200k points, 4 ellipse directions, tolerance 0.2, 80 lags):
+    permutation invariance with exact counts, shard additivity, and the fused 4-direction call equals four
+    single-direction calls bit for bit."""
+    from pyinterpolate_b200 import _lib, core
+    pts = dem_like_field(200_000, seed=6)
+    lags = np.arange(500.0, 40500.0, 500.0)
+    angles = [90, 0, 45, 135]
+    W = np.stack([core.define_whitening_matrix(a, 0.2) for a in angles]).reshape(-1, 4)
+    lower = core.ellipse_lower_limits(lags)
+    base = _lib.variogram_host(pts, lags, lower=lower, W=W)
+    assert base["count"].shape == (4, 80) and (base["count"] > 0).all()
+    n = len(pts)
+    assert base["count"].sum(axis=1).max() < n * (n - 1) // 2
+    perm = np.random.default_rng(1).permutation(n)
+    shuffled = _lib.variogram_host(pts[perm], lags, lower=lower, W=W)
+    np.testing.assert_array_equal(shuffled["count"], base["count"])
+    np.testing.assert_allclose(shuffled["sum_sq"], base["sum_sq"], rtol=1e-11)
+    for t in (0, 3):
+        one = _lib.variogram_host(pts, lags, lower=lower, W=W[t:t + 1])
+        np.testing.assert_array_equal(one["count"][0], base["count"][t])
+        np.testing.assert_array_equal(one["sum_sq"][0], base["sum_sq"][t])
+    parts = [_lib.variogram_host(pts, lags, lower=lower, W=W, shard=(r, 4)) for r in range(4)]
+    np.testing.assert_array_equal(sum(p["count"] for p in parts), base["count"])
+    np.testing.assert_allclose(sum(p["sum_sq"] for p in parts), base["sum_sq"], rtol=1e-12)
