@@ -57,7 +57,7 @@ struct PairParams {
     double *partial;             // [grid][warps][n_slots][4]  (sum_sq, sum_prod, sum_val, count as double-exact int64 bits)
     unsigned long long *pairs_evaluated;
     int group_path;              // ring kernel: one slot lookup per group of 8 pairs (off-diagonal tile pairs)
-    const double *gsum;          // [n_pad / 8] sum of z over each group of 8 consecutive (sorted) points
+    const double2 *gsum;         // [n_pad / 8] (sum z, sum z^2) over each group of 8 consecutive (sorted) points; z centred
     const int32_t *item_list;    // ring kernel: work items ordered by descending cost (NULL: natural order)
     const unsigned *n_live_items;  // number of items with at least one live tile pair (device scalar)
 };
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
     static_assert(NT % TILE == 0 && RING <= 32, "A sub-tile is whole tiles; one lane folds one ring slot");
     __shared__ __align__(16) double2 s_txy[2][TILE];
     __shared__ __align__(16) double s_tz[2][TILE];
-    __shared__ __align__(16) double s_gs[2][TILE / 8];
+    __shared__ __align__(16) double2 s_gs[2][TILE / 8];
     __shared__ long long s_upper[MAX_SLOTS];
     __shared__ uint16_t s_lut[LUT2_MAX];
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
         const double2 pa = p.xy[ig];
         const double xi = pa.x, yi = pa.y, zi = p.z[ig];
         s_zi[tid] = zi;
-        const double z8 = zi * 8.0;
+        const double z8 = zi * 8.0, zm2 = zi * -2.0, zq8 = (zi * zi) * 8.0;
         int win_lo = 0x7fff, win_hi = 0;                      // lag slots touched since the last fold (empty)
 
         // fold the rings of my warp into its global partials (lane l owns ring slot l)
@@ -533,10 +533,10 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
         live &= live - 1;
         if (tid == 0) {
             const uint32_t b = seq & 1;
-            mbar_expect_tx(&s_bar[b], TILE * (sizeof(double2) + sizeof(double)) + (TILE / 8) * sizeof(double));
+            mbar_expect_tx(&s_bar[b], TILE * (sizeof(double2) + sizeof(double)) + (TILE / 8) * sizeof(double2));
             tma_load_1d(s_txy[b], p.xy + (size_t)tb * TILE, TILE * sizeof(double2), &s_bar[b]);
             tma_load_1d(s_tz[b], p.z + (size_t)tb * TILE, TILE * sizeof(double), &s_bar[b]);
-            tma_load_1d(s_gs[b], p.gsum + (size_t)tb * (TILE / 8), (TILE / 8) * sizeof(double), &s_bar[b]);
+            tma_load_1d(s_gs[b], p.gsum + (size_t)tb * (TILE / 8), (TILE / 8) * sizeof(double2), &s_bar[b]);
         }
         while (true) {
             const uint32_t b = seq & 1, phase = (seq >> 1) & 1;
@@ -544,10 +544,10 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
             live &= live - 1;
             if (tid == 0 && tb_next >= 0) {
                 const uint32_t nb = b ^ 1;
-                mbar_expect_tx(&s_bar[nb], TILE * (sizeof(double2) + sizeof(double)) + (TILE / 8) * sizeof(double));
+                mbar_expect_tx(&s_bar[nb], TILE * (sizeof(double2) + sizeof(double)) + (TILE / 8) * sizeof(double2));
                 tma_load_1d(s_txy[nb], p.xy + (size_t)tb_next * TILE, TILE * sizeof(double2), &s_bar[nb]);
                 tma_load_1d(s_tz[nb], p.z + (size_t)tb_next * TILE, TILE * sizeof(double), &s_bar[nb]);
-                tma_load_1d(s_gs[nb], p.gsum + (size_t)tb_next * (TILE / 8), (TILE / 8) * sizeof(double), &s_bar[nb]);
+                tma_load_1d(s_gs[nb], p.gsum + (size_t)tb_next * (TILE / 8), (TILE / 8) * sizeof(double2), &s_bar[nb]);
             }
             // ---- ring window bookkeeping (uniform over the CTA) ---------------------------------
             const short2 rng = s_range[tb - tb0];
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
 
             const double2 *bxy = s_txy[b];
             const double *bz = s_tz[b];
-            const double *bgs = s_gs[b];
+            const double2 *bgs = s_gs[b];
             const bool diagonal = (tb <= ta_last);
             const int jbase = tb * TILE;
             if (tid == 0) {
@@ -722,7 +722,12 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
                 int nout = 0;
                 // sum of dz over the whole group from the pre-summed z of the group: 8 z_i - sum z_j (one fp64 op
                 // instead of seven; this sum only feeds the covariance terms, where it meets c z_i^2 - z_i * sum)
-                double a1 = __dsub_rn(z8, bgs[j0 >> 3]);
+                // ... and the sum of dz^2 from the pre-summed z and z^2: 8 z_i^2 - 2 z_i sum z_j + sum z_j^2.  The z values
+                // are centred by the host side, so the cancellation costs eps * var(z) / (2 gamma(h)) relative — far
+                // below the 1e-9 bar for any field with gamma(h) > 1e-7 var(z)
+                const double2 gs = bgs[j0 >> 3];
+                double a1 = __dsub_rn(z8, gs.x);
+                double a2 = __fma_rn(zm2, gs.x, zq8) + gs.y;
                 if (__any_sync(0xffffffffu, mx + 1 > (int)(t_hi_bits >> 32))) {            // rare: maybe beyond lo + 1
                     const double t_hi = __longlong_as_double(t_hi_bits);
 #pragma unroll
@@ -737,6 +742,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
                             acc[r] = a;
                             cnt[r] += 1u;
                             a1 -= dzv[u];
+                            a2 = __fma_rn(-dzv[u], dzv[u], a2);
                             dzv[u] = 0.0; d2[u] = -1.0; ++nout;
                         }
                     }
@@ -754,13 +760,12 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
                 const int ch = __popc(hi_mask);
                 g.a1 = a1;
                 g.h1 = ((dh[0] + dh[1]) + (dh[2] + dh[3])) + ((dh[4] + dh[5]) + (dh[6] + dh[7]));
-                double a2e = dzv[0] * dzv[0], a2o = dzv[1] * dzv[1], h2e = dh[0] * dh[0], h2o = dh[1] * dh[1];
+                double h2e = dh[0] * dh[0], h2o = dh[1] * dh[1];
 #pragma unroll
                 for (int u = 2; u < U; u += 2) {
-                    a2e = __fma_rn(dzv[u], dzv[u], a2e); a2o = __fma_rn(dzv[u + 1], dzv[u + 1], a2o);
                     h2e = __fma_rn(dh[u], dh[u], h2e);   h2o = __fma_rn(dh[u + 1], dh[u + 1], h2o);
                 }
-                g.a2 = a2e + a2o; g.h2 = h2e + h2o;
+                g.a2 = a2; g.h2 = h2e + h2o;
                 g.lo = lo; g.ch = ch; g.nout = nout;
             };
             auto consume2 = [&](const Grp &g) __attribute__((always_inline)) {
@@ -875,13 +880,37 @@ __global__ void item_cost_kernel(const PairParams p, int a_tiles, int64_t n_item
     }
 }
 
-// sum of z over each group of 8 consecutive sorted points (pads included, as the pair kernel sees them)
-__global__ void group_sum_kernel(const double *__restrict__ z, int64_t n_groups, double *__restrict__ gsum)
+// mean of z over the real points, fixed summation order (one block): the ring kernel works on centred values
+__global__ void __launch_bounds__(1024) mean_kernel(const double *__restrict__ z, int64_t n, double *__restrict__ mean)
+{
+    __shared__ double sh[1024];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) s += z[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *mean = sh[0] / (double)n;
+}
+
+// centred copy of z and, per group of 8 consecutive sorted points (pads included, as the pair kernel sees them),
+// the sums of the centred values and of their squares
+__global__ void group_sum_kernel(const double *__restrict__ z, const double *__restrict__ mean, int64_t n_groups,
+                                 double *__restrict__ zc, double2 *__restrict__ gsum)
 {
     const int64_t gidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (gidx >= n_groups) return;
-    const double *q = z + gidx * 8;
-    gsum[gidx] = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+    const double m = *mean;
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { v[u] = z[gidx * 8 + u] - m; zc[gidx * 8 + u] = v[u]; }
+    const double s1 = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    double qe = v[0] * v[0], qo = v[1] * v[1];
+#pragma unroll
+    for (int u = 2; u < 8; u += 2) { qe = __fma_rn(v[u], v[u], qe); qo = __fma_rn(v[u + 1], v[u + 1], qo); }
+    gsum[gidx] = make_double2(s1, qe + qo);
 }
 
 // bounding boxes of the whitened coordinates (u, v) = W p of every tile (one warp per tile)
@@ -913,7 +942,8 @@ __global__ void tile_box_whitened_kernel(const double2 *__restrict__ xy, int64_t
 // Fixed-order sum of the per-warp partials -> outputs.  One 128-thread block per lag: thread t sums parts
 // t, t + 128, ... in order, then a fixed shared-memory tree combines the 128 sub-sums (deterministic).
 __global__ void __launch_bounds__(128) reduce_partials_kernel(const double *__restrict__ partial, int n_parts, int n_slots,
-                                                              int n_lags, double *__restrict__ sum_sq,
+                                                              int n_lags, const double *__restrict__ mean,
+                                                              double *__restrict__ sum_sq,
                                                               double *__restrict__ sum_prod, double *__restrict__ sum_val,
                                                               int64_t *__restrict__ count)
 {
@@ -936,7 +966,17 @@ __global__ void __launch_bounds__(128) reduce_partials_kernel(const double *__re
         }
         __syncthreads();
     }
-    if (t == 0) { sum_sq[b] = sh[0][0]; sum_prod[b] = sh[1][0]; sum_val[b] = sh[2][0]; count[b] = (int64_t)shc[0]; }
+    if (t == 0) {
+        double prod = sh[1][0], val = sh[2][0];
+        if (mean) {
+            // the ring kernel summed centred values z' = z - m:  sum (z_i + z_j) = sum' + 2 c m,
+            // sum z_i z_j = sum' z'_i z'_j + m sum' (z'_i + z'_j) + c m^2
+            const double m = *mean, c = (double)shc[0];
+            prod = prod + m * val + c * m * m;
+            val = val + 2.0 * c * m;
+        }
+        sum_sq[b] = sh[0][0]; sum_prod[b] = prod; sum_val[b] = val; count[b] = (int64_t)shc[0];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1197,6 +1237,7 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         p.lut2 = d_lut2; p.lut2_base = lut2_base; p.lut2_n = (int)lut2.size();
         p.box_slack = 0.0;
         p.gsum = nullptr;
+        double *d_mean = nullptr;                  // ring kernel: mean of z (its sums come out centred)
         p.item_list = nullptr; p.n_live_items = nullptr;
         const int64_t n_items_all = a_tiles * n_chunks;            // over all ranks
         const char *bal_env = std::getenv("PIB_BALANCE");
@@ -1211,9 +1252,15 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         }
         if (use_ring) {
             const int64_t n_groups = (int64_t)n_tiles * (TILE / 8);
-            double *d_gsum;
+            double2 *d_gsum;
+            double *d_zc;
             PIB_TRY(ws.alloc(&d_gsum, (size_t)n_groups));
-            group_sum_kernel<<<(int)((n_groups + 255) / 256), 256, 0, stream>>>(sp.z, n_groups, d_gsum);
+            PIB_TRY(ws.alloc(&d_zc, (size_t)n_groups * 8 + 1024));
+            PIB_TRY(ws.alloc(&d_mean, 1));
+            PIB_CUDA(cudaMemsetAsync(d_zc, 0, ((size_t)n_groups * 8 + 1024) * sizeof(double), stream));
+            mean_kernel<<<1, 1024, 0, stream>>>(sp.z, n, d_mean);
+            group_sum_kernel<<<(int)((n_groups + 255) / 256), 256, 0, stream>>>(sp.z, d_mean, n_groups, d_zc, d_gsum);
+            p.z = d_zc;
             PIB_CUDA(cudaGetLastError());
             p.gsum = d_gsum;
         }
@@ -1286,7 +1333,7 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             timing_end(PIB_T_PAIR, stream);
             PIB_TRY(rc);
             reduce_partials_kernel<<<n_lags, 128, 0, stream>>>(
-                d_partial, grid * warps + 1, n_slots, n_lags, d_sum_sq + (size_t)t * n_lags, d_sum_prod + (size_t)t * n_lags,
+                d_partial, grid * warps + 1, n_slots, n_lags, d_mean, d_sum_sq + (size_t)t * n_lags, d_sum_prod + (size_t)t * n_lags,
                 d_sum_val + (size_t)t * n_lags, d_count + (size_t)t * n_lags);
             PIB_CUDA(cudaGetLastError());
         }
