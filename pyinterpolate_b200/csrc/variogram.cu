@@ -897,15 +897,20 @@ __global__ void __launch_bounds__(1024) mean_kernel(const double *__restrict__ z
 
 // centred copy of z and, per group of 8 consecutive sorted points (pads included, as the pair kernel sees them),
 // the sums of the centred values and of their squares
-__global__ void group_sum_kernel(const double *__restrict__ z, const double *__restrict__ mean, int64_t n_groups,
-                                 double *__restrict__ zc, double2 *__restrict__ gsum)
+__global__ void group_sum_kernel(const double *__restrict__ z, const double *__restrict__ mean, int64_t n,
+                                 int64_t n_groups, double *__restrict__ zc, double2 *__restrict__ gsum)
 {
     const int64_t gidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (gidx >= n_groups) return;
     const double m = *mean;
     double v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { v[u] = z[gidx * 8 + u] - m; zc[gidx * 8 + u] = v[u]; }
+    for (int u = 0; u < 8; ++u) {
+        // padding rows sit at the mean (centred 0): their pairs only ever reach the trash slots, but the two-lag
+        // sums form "all 8 minus second lag", and a huge padding dz would cancel there (data with a large offset)
+        v[u] = (gidx * 8 + u < n) ? z[gidx * 8 + u] - m : 0.0;
+        zc[gidx * 8 + u] = v[u];
+    }
     const double s1 = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
     double qe = v[0] * v[0], qo = v[1] * v[1];
 #pragma unroll
@@ -1259,7 +1264,7 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             PIB_TRY(ws.alloc(&d_mean, 1));
             PIB_CUDA(cudaMemsetAsync(d_zc, 0, ((size_t)n_groups * 8 + 1024) * sizeof(double), stream));
             mean_kernel<<<1, 1024, 0, stream>>>(sp.z, n, d_mean);
-            group_sum_kernel<<<(int)((n_groups + 255) / 256), 256, 0, stream>>>(sp.z, d_mean, n_groups, d_zc, d_gsum);
+            group_sum_kernel<<<(int)((n_groups + 255) / 256), 256, 0, stream>>>(sp.z, d_mean, n, n_groups, d_zc, d_gsum);
             p.z = d_zc;
             PIB_CUDA(cudaGetLastError());
             p.gsum = d_gsum;

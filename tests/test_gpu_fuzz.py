@@ -52,13 +52,20 @@ def _case(name):
     elif name == "custom_bins":              # irregular lag widths (custom_bins), wide and narrow mixed
         xy = rng.uniform(0, 40_000, size=(6001, 2))
         lags = np.array([50.0, 75.0, 400.0, 410.0, 2_000.0, 2_001.0, 9_000.0, 15_000.0, 15_500.0, 30_000.0])
+    elif name in ("z_offset", "z_heavy_tail"):  # values that stress the centred / expanded sums of the ring kernel
+        xy = rng.uniform(0, 40_000, size=(7001, 2))
+        lags = np.arange(400.0, 16_000.0, 400.0)
     else:
         raise KeyError(name)
     z = 100.0 + 10.0 * np.sin(xy[:, 0] / (np.ptp(xy[:, 0]) + 1e-300) * 6.0) + rng.normal(0, 1.0, len(xy))
+    if name == "z_offset":
+        z = 1.0e9 + (z - 100.0)                 # huge mean, small spread: z - mean is exact, z^2 would not be
+    elif name == "z_heavy_tail":
+        z = np.exp(rng.normal(0.0, 2.5, len(xy)))   # log-normal over five orders of magnitude
     return np.column_stack([xy, z]), lags
 
 
-CASES = ["grid", "grid_offset", "clustered", "utm", "strip", "duplicates", "tiny", "custom_bins"]
+CASES = ["grid", "grid_offset", "clustered", "utm", "strip", "duplicates", "tiny", "custom_bins", "z_offset", "z_heavy_tail"]
 
 
 @pytest.fixture(scope="module")
