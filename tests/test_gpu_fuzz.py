@@ -172,3 +172,25 @@ def test_kriging_fuzz(lib, oracle, name, k):
         np.testing.assert_array_equal(gst[0], wst)
         ok = wst == 0
         np.testing.assert_allclose(got[0][ok, :2], want[ok, :2], rtol=1e-8 if k >= 64 else RTOL, atol=1e-9 * var)
+
+
+@pytest.mark.parametrize("values", ["offset", "heavy_tail"])
+def test_kriging_value_stress(lib, oracle, values):
+    """Values with a huge offset / five orders of magnitude of spread through the neighbour search and the solver."""
+    known, unk, rang = _krige_case("utm")
+    rng = np.random.default_rng(11)
+    if values == "offset":
+        known[:, 2] = 1.0e9 + (known[:, 2] - 50.0)
+    else:
+        known[:, 2] = np.exp(rng.normal(0.0, 2.5, len(known)))
+    var = float(np.var(known[:, 2]))
+    scale = np.abs(known[:, 2]).max()
+    for mode, mid in (("ok", lib.KRIGE_ORDINARY), ("sk", lib.KRIGE_SIMPLE)):
+        pm = float(known[:, 2].mean())
+        want, widx, wst = oracle.krige(known, unk, "spherical", 0.1 * var, var, rang, 24, mode, pm)
+        got, gidx, gst = lib.krige_host(known, unk, 6, [[0.1 * var, var, rang]], mid, 24, process_mean=pm, want_neighbors=True)
+        np.testing.assert_array_equal(gidx, widx)
+        np.testing.assert_array_equal(gst[0], wst)
+        ok = wst == 0
+        np.testing.assert_allclose(got[0][ok, 0], want[ok, 0], rtol=0, atol=1e-9 * scale)
+        np.testing.assert_allclose(got[0][ok, 1], want[ok, 1], rtol=1e-8, atol=1e-9 * var)
