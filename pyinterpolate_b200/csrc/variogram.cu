@@ -880,15 +880,29 @@ __global__ void item_cost_kernel(const PairParams p, int a_tiles, int64_t n_item
     }
 }
 
-// mean of z over the real points, fixed summation order (one block): the ring kernel works on centred values
-__global__ void __launch_bounds__(1024) mean_kernel(const double *__restrict__ z, int64_t n, double *__restrict__ mean)
+// mean of z over the real points in a fixed summation order (256 blocks of partial sums, then one block):
+// the ring kernel works on centred values
+__global__ void __launch_bounds__(256) mean_partial_kernel(const double *__restrict__ z, int64_t n, double *__restrict__ partial)
 {
-    __shared__ double sh[1024];
+    __shared__ double sh[256];
     double s = 0.0;
-    for (int64_t i = threadIdx.x; i < n; i += 1024) s += z[i];
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) s += z[i];
     sh[threadIdx.x] = s;
     __syncthreads();
-    for (int o = 512; o; o >>= 1) {
+    for (int o = 128; o; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+__global__ void __launch_bounds__(256) mean_final_kernel(const double *__restrict__ partial, int n_partial, int64_t n,
+                                                         double *__restrict__ mean)
+{
+    __shared__ double sh[256];
+    sh[threadIdx.x] = ((int)threadIdx.x < n_partial) ? partial[threadIdx.x] : 0.0;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
         if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
         __syncthreads();
     }
@@ -1263,7 +1277,10 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             PIB_TRY(ws.alloc(&d_zc, (size_t)n_groups * 8 + 1024));
             PIB_TRY(ws.alloc(&d_mean, 1));
             PIB_CUDA(cudaMemsetAsync(d_zc, 0, ((size_t)n_groups * 8 + 1024) * sizeof(double), stream));
-            mean_kernel<<<1, 1024, 0, stream>>>(sp.z, n, d_mean);
+            double *d_mpart;
+            PIB_TRY(ws.alloc(&d_mpart, 256));
+            mean_partial_kernel<<<256, 256, 0, stream>>>(sp.z, n, d_mpart);
+            mean_final_kernel<<<1, 256, 0, stream>>>(d_mpart, 256, n, d_mean);
             group_sum_kernel<<<(int)((n_groups + 255) / 256), 256, 0, stream>>>(sp.z, d_mean, n, n_groups, d_zc, d_gsum);
             p.z = d_zc;
             PIB_CUDA(cudaGetLastError());
