@@ -35,7 +35,8 @@ namespace pib {
 
 constexpr int TILE = 128;        // points per tile
 constexpr int CHUNK = 64;        // B tiles per work item
-constexpr int LUT_N = 1024;      // distance -> first candidate slot table
+constexpr int LUT2_MAX = 2048;   // slot table: (high word of the fp64 squared distance - base) >> LUT2_SHIFT -> first candidate slot
+constexpr int LUT2_SHIFT = 13;   // keep 7 of the 20 mantissa bits of the high word: 128 cells per octave
 constexpr int MAX_SMEM = 232448; // opt-in dynamic shared memory per CTA on sm_100
 
 struct PairParams {
@@ -46,9 +47,7 @@ struct PairParams {
     int n_tiles;
     int n_slots;                 // n_lags + 2: slot 0 = "d2 <= 0 / masked", slot s = lag s-1, last = beyond range
     const double *upper;         // [n_slots] slot upper thresholds on d2: U[0] = 0, U[s] = T(edge[s-1]), U[last] = +inf
-    const uint16_t *lut;         // [LUT_N] full-histogram kernel: float distance estimate -> first candidate slot
-    float lut_scale;
-    const uint16_t *lut2;        // [lut2_n] ring kernel: (hi word of d2 - lut2_base) >> 13 -> first candidate slot
+    const uint16_t *lut2;        // [lut2_n] (hi word of d2 - lut2_base) >> 13 -> first candidate slot
     int lut2_base, lut2_n;
     double box_slack;            // ellipse ring kernel: slack on the whitened bounding boxes
     double max_d2;               // T(edges[n_lags-1])
@@ -109,7 +108,7 @@ static __device__ __forceinline__ double box_min_d2(const double4 a, const doubl
 // alias the private histogram stores and may hoist them freely (that is what lets it overlap the
 // distance / slot computation of one batch of pairs with the read-modify-writes of the previous batch).
 constexpr int MAX_SLOTS = 352;
-constexpr int STATIC_SMEM = 2 * TILE * 24 + MAX_SLOTS * 8 + LUT_N * 2 + 64;
+constexpr int STATIC_SMEM = 2 * TILE * 24 + MAX_SLOTS * 8 + LUT2_MAX * 2 + 64;
 
 template <int NT>
 static size_t pair_smem_bytes(int n_slots)
@@ -128,7 +127,7 @@ __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
     __shared__ __align__(16) double2 s_txy[2][TILE];
     __shared__ __align__(16) double s_tz[2][TILE];
     __shared__ long long s_upper[MAX_SLOTS];       // thresholds as bit patterns: d2 >= 0, so integer order == fp order
-    __shared__ uint16_t s_lut[LUT_N];
+    __shared__ uint16_t s_lut[LUT2_MAX];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint64_t s_live;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -143,7 +142,7 @@ __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
         cnt[s * NT] = 0u;
     }
     for (int s = tid; s < n_slots; s += NT) s_upper[s] = __double_as_longlong(p.upper[s]);
-    for (int s = tid; s < LUT_N; s += NT) s_lut[s] = p.lut[s];
+    for (int s = tid; s < p.lut2_n; s += NT) s_lut[s] = p.lut2[s];
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -157,7 +156,7 @@ __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
     uint32_t seq = 0;                       // tiles staged so far by this CTA (buffer = seq & 1, phase = (seq >> 1) & 1)
     unsigned long long evaluated = 0;
     double *my_partial = p.partial + ((size_t)blockIdx.x * (NT / 32) + warp) * n_slots * 4;
-    const float lut_scale = p.lut_scale;
+    const int base_hi = p.lut2_base, lut_last = p.lut2_n - 1;
     const double w00 = p.w00, w01 = p.w01, w10 = p.w10, w11 = p.w11;
 
     for (int64_t item = ((int64_t)blockIdx.x) * p.shard_count + p.shard_index; item < n_items;
@@ -253,17 +252,15 @@ __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
                         d2[u] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
                     }
                 }
-                // first candidate slot from a float estimate of the distance ...
-                int e[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    float r;
-                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__double2float_rn(d2[u])));
-                    e[u] = min(__float2int_rz(r * lut_scale), LUT_N - 1);
-                }
+                // first candidate slot from the exponent and top mantissa bits of the squared distance (integer ops
+                // only: no conversion, no sqrt on the quarter-rate XU pipe) ...
                 int sl[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) sl[u] = s_lut[e[u]];
+                for (int u = 0; u < U; ++u) {
+                    int idx = (__double2hiint(d2[u]) - base_hi) >> LUT2_SHIFT;
+                    idx = min(max(idx, 0), lut_last);
+                    sl[u] = s_lut[idx];
+                }
                 // ... then the exact fix-up on the bit pattern of the fp64 squared distance
                 if (FIX > 0) {
 #pragma unroll
@@ -372,8 +369,6 @@ __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
 //    squared distance (integer ops only, no conversion / sqrt on the quarter-rate XU pipe); one or two
 //    64-bit integer compares against the exact thresholds finish the assignment.
 // ---------------------------------------------------------------------------------------------
-constexpr int LUT2_MAX = 4096;
-constexpr int LUT2_SHIFT = 13;                 // keep 7 of the 20 mantissa bits of the high word: 128 cells per octave
 
 template <int RING, int NT, int FIX, bool ELLIPSE>
 __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
@@ -1069,8 +1064,8 @@ template <int NT, bool ELLIPSE>
 static int launch_pair_kernel(const PairParams &p, int fix_steps, int grid, cudaStream_t stream)
 {
     const size_t smem = pair_smem_bytes<NT>(p.n_slots);
+    if (fix_steps <= 1) return launch_pair_kernel_fix<NT, ELLIPSE, 1>(p, smem, grid, stream);
     if (fix_steps <= 2) return launch_pair_kernel_fix<NT, ELLIPSE, 2>(p, smem, grid, stream);
-    if (fix_steps <= 4) return launch_pair_kernel_fix<NT, ELLIPSE, 4>(p, smem, grid, stream);
     return launch_pair_kernel_fix<NT, ELLIPSE, 0>(p, smem, grid, stream);
 }
 
@@ -1145,32 +1140,39 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             PIB_CUDA(cudaGetLastError());
         }
     } else {
-        // distance -> first candidate slot: cell e covers r in [e, e+1) / scale; start from the slot of
-        // (e - 0.5) / scale so float rounding can never start above the true slot
-        const double rmax = edges[n_lags - 1];
-        const double scale = (LUT_N - 2) / rmax;
-        std::vector<uint16_t> lut(LUT_N);
-        int fix_steps = 0;                 // most threshold steps any table cell can need
-        for (int e = 0; e < LUT_N; ++e) {
-            const double r_lo = std::max(0.0, (e - 0.5) / scale);
-            const double t = r_lo * r_lo * (1.0 - 1e-6);
-            int s = 0;
-            while (s < n_slots - 1 && t > up[s]) ++s;
-            lut[e] = (uint16_t)s;
-            int s_hi = s;
-            if (e == LUT_N - 1) s_hi = n_slots - 1;
-            else {
-                const double r_hi = (e + 1.5) / scale;
-                const double t_hi = r_hi * r_hi * (1.0 + 1e-6);
-                while (s_hi < n_slots - 1 && t_hi > up[s_hi]) ++s_hi;
-            }
-            fix_steps = std::max(fix_steps, s_hi - s);
-        }
         double *d_upper;
-        uint16_t *d_lut;
-        PIB_TRY(ws.alloc(&d_upper, n_slots)); PIB_TRY(ws.alloc(&d_lut, LUT_N));
+        PIB_TRY(ws.alloc(&d_upper, n_slots));
         PIB_CUDA(cudaMemcpyAsync(d_upper, up.data(), n_slots * sizeof(double), cudaMemcpyHostToDevice, stream));
-        PIB_CUDA(cudaMemcpyAsync(d_lut, lut.data(), LUT_N * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
+        // slot table indexed by (high word of d2 - base) >> 13, 128 cells per octave; fix_steps = most thresholds any
+        // cell straddles (the kernels make that many exact threshold steps after the lookup)
+        std::vector<uint16_t> lut2;
+        int lut2_base = 0, fix_steps = 0;
+        uint16_t *d_lut2 = nullptr;
+        {
+            auto hiword = [](double v) { long long b; std::memcpy(&b, &v, 8); return (int)(b >> 32); };
+            auto from_hi = [](int hi) { long long b = (long long)hi << 32; double v; std::memcpy(&v, &b, 8); return v; };
+            const int cell = 1 << LUT2_SHIFT;
+            const int hi_max = hiword(up[n_slots - 2]);
+            lut2_base = hiword(up[1] / 4.0) & ~(cell - 1);
+            int n_cells = ((hi_max - lut2_base) >> LUT2_SHIFT) + 3;
+            if (n_cells > LUT2_MAX) {                          // very wide lag range: coarser start, more fix-up steps
+                n_cells = LUT2_MAX;
+                lut2_base = (hi_max & ~(cell - 1)) - (LUT2_MAX - 3) * cell;
+            }
+            lut2.resize(n_cells);
+            auto slot_of = [&](double v) { int q = 0; while (q < n_slots - 1 && v > up[q]) ++q; return q; };
+            for (int e = 0; e < n_cells; ++e) {
+                const double v_lo = e == 0 ? 0.0 : from_hi(lut2_base + e * cell);
+                const int q_lo = slot_of(v_lo);
+                const int q_hi = e == n_cells - 1 ? n_slots - 1
+                                                  : slot_of(std::nextafter(from_hi(lut2_base + (e + 1) * cell), 0.0));
+                lut2[e] = (uint16_t)q_lo;
+                fix_steps = std::max(fix_steps, q_hi - q_lo);
+            }
+            PIB_TRY(ws.alloc(&d_lut2, lut2.size()));
+            PIB_CUDA(cudaMemcpyAsync(d_lut2, lut2.data(), lut2.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
+        }
+        const int fix2 = fix_steps;
 
         const int n_tiles = (int)(sp.n_pad / TILE);
         const int n_chunks = (n_tiles + CHUNK - 1) / CHUNK;
@@ -1211,35 +1213,7 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         // latency) when tile pairs are narrow enough
         int ring = 32, ring_nt = 256;
         if (use_ring && ring16_ok) { ring = 16; ring_nt = 512; }
-        // ring kernel's slot table: indexed by (high word of d2 - base) >> 13, 128 cells per octave
-        std::vector<uint16_t> lut2;
-        int lut2_base = 0, fix2 = 0;
-        uint16_t *d_lut2 = nullptr;
-        if (use_ring) {
-            auto hiword = [](double v) { long long b; std::memcpy(&b, &v, 8); return (int)(b >> 32); };
-            auto from_hi = [](int hi) { long long b = (long long)hi << 32; double v; std::memcpy(&v, &b, 8); return v; };
-            const int cell = 1 << LUT2_SHIFT;
-            const int hi_max = hiword(up[n_slots - 2]);
-            lut2_base = hiword(up[1] / 4.0) & ~(cell - 1);
-            int n_cells = ((hi_max - lut2_base) >> LUT2_SHIFT) + 3;
-            if (n_cells > LUT2_MAX) {                          // very wide lag range: coarser start, more fix-up steps
-                n_cells = LUT2_MAX;
-                lut2_base = (hi_max & ~(cell - 1)) - (LUT2_MAX - 3) * cell;
-            }
-            lut2.resize(n_cells);
-            auto slot_of = [&](double v) { int q = 0; while (q < n_slots - 1 && v > up[q]) ++q; return q; };
-            for (int e = 0; e < n_cells; ++e) {
-                const double v_lo = e == 0 ? 0.0 : from_hi(lut2_base + e * cell);
-                const int q_lo = slot_of(v_lo);
-                const int q_hi = e == n_cells - 1 ? n_slots - 1
-                                                  : slot_of(std::nextafter(from_hi(lut2_base + (e + 1) * cell), 0.0));
-                lut2[e] = (uint16_t)q_lo;
-                fix2 = std::max(fix2, q_hi - q_lo);
-            }
-            PIB_TRY(ws.alloc(&d_lut2, lut2.size()));
-            PIB_CUDA(cudaMemcpyAsync(d_lut2, lut2.data(), lut2.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
-            nt = ring_nt;
-        }
+        if (use_ring) nt = ring_nt;
         const int64_t a_tiles = use_ring ? (n_tiles + ring_nt / TILE - 1) / (ring_nt / TILE) : (int64_t)n_tiles * (TILE / nt);
         const int64_t n_items = (a_tiles * n_chunks + shard_count - 1) / shard_count;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sm_count(), n_items));
@@ -1250,7 +1224,7 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
 
         PairParams p;
         p.xy = sp.xy; p.z = sp.z; p.tile_box = sp.tile_box; p.n = n; p.n_tiles = n_tiles; p.n_slots = n_slots;
-        p.upper = d_upper; p.lut = d_lut; p.lut_scale = (float)scale; p.max_d2 = up_lag[n_lags - 1];
+        p.upper = d_upper; p.max_d2 = up_lag[n_lags - 1];
         p.shard_index = shard_index; p.shard_count = shard_count; p.partial = d_partial;
         p.pairs_evaluated = d_evaluated;
         p.lut2 = d_lut2; p.lut2_base = lut2_base; p.lut2_n = (int)lut2.size();
