@@ -816,15 +816,21 @@ __global__ void __launch_bounds__(solve_reg_threads<K>(), solve_reg_min_ctas<K>(
                     for (int c = 0; c < K; ++c)
                         if (c >= j) S.prow[c] = a[c];
                     S.prow[K] = ab; S.prow[K + 1] = rhs;
+                    // two-warp systems: the owner computes the reciprocal once, ahead of the barrier, instead of
+                    // all 64 threads after it (it sits on every thread's dependent chain)
+                    if (WARPS > 1) S.prow[K + 2] = __drcp_rn(j < K ? a[j < K ? j : 0] : ab);
                     row_active = false; my_step = j;
                 }
             } else {
                 if (t < K) S.prow[t] = S.brow[t];
-                if (t == 0) { S.prow[K] = S.brow[K]; S.prow[K + 1] = S.brow[K + 1]; }
+                if (t == 0) {
+                    S.prow[K] = S.brow[K]; S.prow[K + 1] = S.brow[K + 1];
+                    if (WARPS > 1) S.prow[K + 2] = __drcp_rn(S.brow[j]);
+                }
                 border_active = false; border_step = j;
             }
             sys_sync<TPS>(sid);
-            const double inv = __drcp_rn(S.prow[j]);
+            const double inv = WARPS > 1 ? S.prow[K + 2] : __drcp_rn(S.prow[j]);
             if (my_step == j) my_inv = inv;
             if (border_step == j) border_inv = inv;
             {
