@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpyinterp_b200.so")
+# PIB_LIB_PATH: load another build of the same library (kernel A/B measurements)
+LIB_PATH = os.environ.get("PIB_LIB_PATH") or os.path.join(_HERE, "libpyinterp_b200.so")
 
 MODEL_IDS = {"circular": 0, "cubic": 1, "exponential": 2, "gaussian": 3,
              "linear": 4, "power": 5, "spherical": 6}

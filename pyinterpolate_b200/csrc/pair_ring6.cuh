@@ -1,0 +1,551 @@
+// pair_ring6_kernel — the ring-window pair kernel, second formulation (included by variogram.cu).
+//
+// Same job and same exact lag assignment as pair_ring_kernel (reference: distance/point.py:56, :86-92 and
+// semivariogram/experimental/functions/general.py:235-303; ellipse: distance/angular.py:641-681), rebuilt around what
+// ncu showed for that kernel (profiles/r1_pair_ring_kernel_ncu_full_v5.md): 23.8 warp instructions and 6.7 shared-memory
+// wavefronts per warp-wide pair step, shared-memory pipe 73 % busy — the wavefronts alone capped it below 50 % of the
+// FP64 peak.  What changed:
+//   * z_j FORM.  A ring slot of a thread holds (count, sum z_j, sum z_j^2) of the pairs (i, j) it saw instead of
+//     (count, sum dz, sum dz^2): per pair the values cost one select (high word of z_j under the predicate "second lag of
+//     the group"), one DADD and one DFMA — no dz.  The fold forms sum dz^2 = c z_i^2 - 2 z_i sum z_j + sum z_j^2,
+//     sum z_i z_j = z_i sum z_j, sum (z_i + z_j) = c z_i + sum z_j.  z is centred (mean removed), so the cancellation
+//     costs eps * var(z) / (2 gamma(h)) relative; the host side re-runs the dz-form kernel when a lag has
+//     gamma(h) < 1e-6 var(z) (variogram_device).
+//   * the second-lag predicate can be a 64-bit INTEGER compare of the squared distance's bit pattern (two ALU
+//     instructions) instead of a DSETP, which takes that work off the fp64 pipe (PIB_V6_CMP).
+//   * ONE 16-byte table entry per lag slot {threshold, high word of the next threshold, both ring offsets} replaces the
+//     threshold loads and the ring-slot arithmetic (13 integer instructions per group in the old kernel); the ring size
+//     is any number <= 32 (the offsets come from the table, not from a mask).
+//   * PER-WARP ring windows: every warp tracks the lag window of ITS 32 * APT A points against the B tile, folds on its
+//     own, and skips B tiles none of its points can reach (finer culling than the CTA-wide box).
+//   * APT (A points per thread: 1 or 2) and U (pairs per group: 8 or 16) are template parameters: APT = 2 halves the
+//     B-point loads per pair, U = 16 halves the ring traffic per pair — the two levers on the shared-memory wavefronts.
+//   * two groups in flight per thread (distances + table lookup of group g + 1 are issued ahead of the sums and ring
+//     updates of group g): the lookup is a chain of three dependent shared-memory loads.
+#pragma once
+
+namespace pib {
+
+struct __align__(16) SlotInfo {
+    long long T;        // upper threshold of this slot on the squared distance (bit pattern; d2 >= 0 so integer order = fp order)
+    int next_hi;        // high word of the next slot's threshold
+    uint32_t offs;      // ring block of this slot (low half) and of the next slot (high half), in 16-byte units
+};
+
+template <int RING, int NT, int APT>
+static size_t ring6_smem_bytes(int n_slots, int lut_n)
+{
+    const size_t na = (size_t)NT * APT;
+    size_t b = (size_t)(RING + 1) * na * 20;                    // ring: per slot NA x (double2 sums) then NA x u32 counts
+    b += (size_t)(n_slots + 1) * sizeof(SlotInfo);
+    b += (size_t)(NT / 32) * CHUNK * sizeof(short2);
+    b += ((size_t)lut_n * 2 + 15) / 16 * 16;
+    return b;
+}
+
+#ifndef PIB_V6_CMP
+#define PIB_V6_CMP 0
+#endif
+#ifndef PIB_V6_PIPE
+#define PIB_V6_PIPE 1
+#endif
+
+template <int RING, int NT, int APT, int U, bool MULTI_FIX, bool ELLIPSE>
+__global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
+{
+    constexpr int NA = NT * APT;                   // A points per CTA
+    constexpr int A_TILES = NA / TILE;
+    constexpr int NW = NT / 32;
+    constexpr int WA = 32 * APT;                   // A points per warp (consecutive on the Hilbert curve)
+    constexpr int SLOT_BYTES = NA * 20;
+    constexpr int SB16 = SLOT_BYTES / 16;
+    constexpr int CNT_OFF = NA * 16;               // counts follow the sums inside a slot block
+    constexpr uint32_t TRASH16 = RING * SB16;
+    constexpr int CMP = PIB_V6_CMP;
+    constexpr bool PIPE = PIB_V6_PIPE != 0;      // two groups in flight per thread (needs the registers)
+    constexpr int NG = TILE / U;
+    static_assert(NA % TILE == 0 && RING <= 32 && RING >= 4, "A sub-tile is whole tiles; one lane folds one ring slot");
+    static_assert(U == 8 || U == 16, "groups of 8 or 16 pairs");
+    static_assert((RING + 1) * SB16 < 65536, "ring offsets are 16-bit");
+    __shared__ __align__(16) double2 s_txy[2][TILE];
+    __shared__ __align__(16) double s_tz[2][TILE];
+    __shared__ __align__(16) double2 s_gs[2][TILE / 8];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint64_t s_live;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_slots = p.n_slots, n_lags = n_slots - 2;
+
+    unsigned char *const ring = smem_raw;
+    SlotInfo *const s_slot = reinterpret_cast<SlotInfo *>(smem_raw + (size_t)(RING + 1) * SLOT_BYTES);
+    short2 *const s_range = reinterpret_cast<short2 *>(s_slot + n_slots + 1) + warp * CHUNK;    // my warp's row
+    const uint16_t *const s_lut = reinterpret_cast<const uint16_t *>(reinterpret_cast<short2 *>(s_slot + n_slots + 1) + NW * CHUNK);
+    const uint32_t slot_sa = smem_u32(s_slot), lut_sa = smem_u32(s_lut);
+
+    // my ring entries: sums at ring + 16 * off + my_acc[k], counts at ring + 16 * off + my_cnt[k]
+    int my_acc[APT], my_cnt[APT];
+#pragma unroll
+    for (int k = 0; k < APT; ++k) {
+        my_acc[k] = (k * NT + tid) * 16;
+        my_cnt[k] = CNT_OFF + (k * NT + tid) * 4;
+    }
+    for (int s = 0; s <= RING; ++s) {
+#pragma unroll
+        for (int k = 0; k < APT; ++k) {
+            *reinterpret_cast<double2 *>(ring + s * SLOT_BYTES + my_acc[k]) = make_double2(0.0, 0.0);
+            *reinterpret_cast<uint32_t *>(ring + s * SLOT_BYTES + my_cnt[k]) = 0u;
+        }
+    }
+    for (int s = tid; s <= n_slots; s += NT) {
+        SlotInfo e;
+        e.T = s < n_slots ? __double_as_longlong(p.upper[s]) : 0x7ff0000000000000ll;
+        e.next_hi = (int)(__double_as_longlong(p.upper[min(s + 1, n_slots - 1)]) >> 32);
+        const uint32_t o_lo = (s >= 1 && s <= n_lags) ? (uint32_t)(s % RING) * SB16 : TRASH16;
+        const uint32_t o_hi = (s + 1 >= 1 && s + 1 <= n_lags) ? (uint32_t)((s + 1) % RING) * SB16 : TRASH16;
+        e.offs = o_lo | (o_hi << 16);
+        s_slot[s] = e;
+    }
+    {
+        uint16_t *lut_w = const_cast<uint16_t *>(s_lut);
+        for (int s = tid; s < p.lut2_n; s += NT) lut_w[s] = p.lut2[s];
+    }
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int n_tiles = p.n_tiles;
+    const int n_atiles = (n_tiles + A_TILES - 1) / A_TILES;
+    const int n_chunks = (n_tiles + CHUNK - 1) / CHUNK;
+    const int64_t n_items = (int64_t)n_atiles * n_chunks;
+    uint32_t seq = 0;
+    unsigned long long evaluated = 0;              // lane 0 of every warp counts its warp's pairs
+    double *my_partial = p.partial + ((size_t)blockIdx.x * NW + warp) * n_slots * 4;
+    const int base_hi = p.lut2_base, lut_last = p.lut2_n - 1;
+    const double w00 = p.w00, w01 = p.w01, w10 = p.w10, w11 = p.w11;
+    const double slack = p.box_slack;
+    constexpr uint32_t TILE_TX = TILE * (sizeof(double2) + sizeof(double)) + (TILE / U) * sizeof(double2);
+
+    const int64_t n_work = p.item_list ? (int64_t)*p.n_live_items : n_items;
+    for (int64_t kk = ((int64_t)blockIdx.x) * p.shard_count + p.shard_index; kk < n_work;
+         kk += (int64_t)gridDim.x * p.shard_count) {
+        const int64_t item = p.item_list ? (int64_t)p.item_list[kk] : kk;
+        const int64_t a0 = (item / n_chunks) * NA;            // first point of the CTA's A sub-tile
+        const int ta = (int)(a0 / TILE);
+        const int ta_last = min(ta + A_TILES, n_tiles) - 1;
+        const int tb0 = (int)(item % n_chunks) * CHUNK;
+        const int tb1 = min(tb0 + CHUNK, n_tiles);
+        if (tb1 <= ta || a0 >= p.n) continue;
+        const int tb_first = max(tb0, ta);
+
+        // ---- my A points -----------------------------------------------------------------------
+        int ig[APT];
+        double xi[APT], yi[APT], zi[APT];
+        double bx0 = INFINITY, by0 = INFINITY, bx1 = -INFINITY, by1 = -INFINITY;     // my warp's box
+#pragma unroll
+        for (int k = 0; k < APT; ++k) {
+            ig[k] = (int)a0 + warp * WA + k * 32 + lane;
+            const double2 pa = p.xy[ig[k]];
+            xi[k] = pa.x; yi[k] = pa.y; zi[k] = p.z[ig[k]];
+            if (ig[k] < p.n) {
+                const double u = ELLIPSE ? w00 * pa.x + w01 * pa.y : pa.x, v = ELLIPSE ? w10 * pa.x + w11 * pa.y : pa.y;
+                bx0 = fmin(bx0, u); bx1 = fmax(bx1, u); by0 = fmin(by0, v); by1 = fmax(by1, v);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            bx0 = fmin(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); bx1 = fmax(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+            by0 = fmin(by0, __shfl_xor_sync(0xffffffffu, by0, o)); by1 = fmax(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+        }
+
+        // ---- CTA: which B tiles of the chunk are loaded at all (box of the whole A sub-tile) -----------
+        if (warp == 0) {
+            double4 abox = p.tile_box[ta];
+            for (int t = ta + 1; t <= ta_last; ++t) {
+                const double4 o = p.tile_box[t];
+                abox.x = fmin(abox.x, o.x); abox.y = fmin(abox.y, o.y);
+                abox.z = fmax(abox.z, o.z); abox.w = fmax(abox.w, o.w);
+            }
+            uint64_t m = 0;
+            for (int h = 0; h < CHUNK / 32; ++h) {
+                const int tb = tb0 + h * 32 + lane;
+                bool live = false;
+                if (tb >= tb_first && tb < tb1) {
+                    const double4 bbox = p.tile_box[tb];
+                    double dmin;
+                    if (ELLIPSE) {
+                        const double gx = fmax(0.0, fmax(abox.x - bbox.z, bbox.x - abox.z) - slack);
+                        const double gy = fmax(0.0, fmax(abox.y - bbox.w, bbox.y - abox.w) - slack);
+                        dmin = (gx * gx + gy * gy) * (1.0 - 1e-12);
+                    } else dmin = box_min_d2(abox, bbox);
+                    live = dmin <= p.max_d2;
+                }
+                m |= (uint64_t)__ballot_sync(0xffffffffu, live) << (32 * h);
+            }
+            if (lane == 0) s_live = m;
+        }
+        // ---- my warp: the lag slots each B tile can touch for MY A points (empty = skip the tile) ----------
+        for (int h = 0; h < CHUNK / 32; ++h) {
+            const int tb = tb0 + h * 32 + lane;
+            short2 r = make_short2(1, 0);                     // empty
+            if (tb >= tb_first && tb < tb1) {
+                const double4 bbox = p.tile_box[tb];
+                const double sl = ELLIPSE ? slack : 0.0;
+                const double gx = fmax(0.0, fmax(bx0 - bbox.z, bbox.x - bx1) - sl);
+                const double gy = fmax(0.0, fmax(by0 - bbox.w, bbox.y - by1) - sl);
+                // every pair of the two boxes has dmin <= d2 <= dmax in the kernel's own arithmetic (fp subtraction,
+                // multiplication and addition are monotone; the whitened bounds carry slack and a relative margin)
+                const double dmin = ELLIPSE ? (gx * gx + gy * gy) * (1.0 - 1e-12) : __dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy));
+                if (dmin <= p.max_d2) {
+                    const double dxm = fmax(bx1 - bbox.x, bbox.z - bx0) + sl, dym = fmax(by1 - bbox.y, bbox.w - by0) + sl;
+                    const double dmax = ELLIPSE ? (dxm * dxm + dym * dym) * (1.0 + 1e-12)
+                                                : __dadd_rn(__dmul_rn(dxm, dxm), __dmul_rn(dym, dym));
+                    int a = 0, b = n_slots - 1;               // first slot whose threshold is >= dmin
+                    const long long v = __double_as_longlong(dmin);
+                    while (a < b) { const int mid = (a + b) >> 1; if (v <= s_slot[mid].T) b = mid; else a = mid + 1; }
+                    const int lo = max(a, 1);
+                    a = 0; b = n_slots - 1;
+                    const long long w = __double_as_longlong(dmax);
+                    while (a < b) { const int mid = (a + b) >> 1; if (w <= s_slot[mid].T) b = mid; else a = mid + 1; }
+                    r = make_short2((short)lo, (short)min(a, n_lags));
+                }
+            }
+            s_range[h * 32 + lane] = r;
+        }
+        __syncthreads();
+        uint64_t live = s_live;
+        if (live == 0) { __syncthreads(); continue; }
+
+        int win_lo = 0x7fff, win_hi = 0;                      // lag slots my warp touched since its last fold (empty)
+
+        // fold the rings of my warp into its global partials (lane l owns ring block l)
+        auto fold = [&]() {
+            __syncwarp();
+            if (win_hi >= win_lo) {
+                // the window's slot that lives in ring block `lane`
+                const int abs_slot = win_lo + ((lane - win_lo % RING) + RING) % RING;
+                double v_sq = 0.0, v_prod = 0.0, v_val = 0.0;
+                unsigned long long v_cnt = 0;
+#pragma unroll
+                for (int k = 0; k < APT; ++k) {
+                    unsigned char *blk = ring + min(lane, RING - 1) * SLOT_BYTES + (k * NT + warp * 32) * 16;
+                    unsigned char *cblk = ring + min(lane, RING - 1) * SLOT_BYTES + CNT_OFF + (k * NT + warp * 32) * 4;
+                    for (int t = 0; t < 32; ++t) {
+                        const int tt = (t + lane) & 31;       // rotate so the lanes of a quarter-warp hit different banks
+                        const double z = __shfl_sync(0xffffffffu, zi[k], tt);
+                        if (lane < RING) {
+                            const uint32_t c = *reinterpret_cast<const uint32_t *>(cblk + tt * 4);
+                            if (c) {
+                                const double2 a = *reinterpret_cast<const double2 *>(blk + tt * 16);
+                                const double cd = (double)c;
+                                // sum dz^2 = c z^2 - 2 z S1 + S2;  sum z_i z_j = z S1;  sum (z_i + z_j) = c z + S1
+                                v_sq += __fma_rn(z, __fma_rn(cd, z, -2.0 * a.x), a.y);
+                                v_prod = __fma_rn(z, a.x, v_prod);
+                                v_val += __fma_rn(cd, z, a.x);
+                                v_cnt += c;
+                                *reinterpret_cast<double2 *>(blk + tt * 16) = make_double2(0.0, 0.0);
+                                *reinterpret_cast<uint32_t *>(cblk + tt * 4) = 0u;
+                            }
+                        }
+                    }
+                }
+                if (lane < RING && v_cnt && abs_slot <= win_hi) {
+                    double *dst = my_partial + (size_t)abs_slot * 4;
+                    dst[0] += v_sq; dst[1] += v_prod; dst[2] += v_val;
+                    reinterpret_cast<unsigned long long *>(dst)[3] += v_cnt;
+                }
+            }
+            __syncwarp();
+            win_lo = 0x7fff; win_hi = 0;
+        };
+
+        int tb = tb0 + __ffsll((long long)live) - 1;
+        live &= live - 1;
+        if (tid == 0) {
+            const uint32_t b = seq & 1;
+            mbar_expect_tx(&s_bar[b], TILE_TX);
+            tma_load_1d(s_txy[b], p.xy + (size_t)tb * TILE, TILE * sizeof(double2), &s_bar[b]);
+            tma_load_1d(s_tz[b], p.z + (size_t)tb * TILE, TILE * sizeof(double), &s_bar[b]);
+            tma_load_1d(s_gs[b], p.gsum + (size_t)tb * (TILE / U), (TILE / U) * sizeof(double2), &s_bar[b]);
+        }
+        while (true) {
+            const uint32_t b = seq & 1, phase = (seq >> 1) & 1;
+            const int tb_next = live ? tb0 + __ffsll((long long)live) - 1 : -1;
+            live &= live - 1;
+            if (tid == 0 && tb_next >= 0) {
+                const uint32_t nb = b ^ 1;
+                mbar_expect_tx(&s_bar[nb], TILE_TX);
+                tma_load_1d(s_txy[nb], p.xy + (size_t)tb_next * TILE, TILE * sizeof(double2), &s_bar[nb]);
+                tma_load_1d(s_tz[nb], p.z + (size_t)tb_next * TILE, TILE * sizeof(double), &s_bar[nb]);
+                tma_load_1d(s_gs[nb], p.gsum + (size_t)tb_next * (TILE / U), (TILE / U) * sizeof(double2), &s_bar[nb]);
+            }
+            // ---- my warp's ring window (warp-uniform) ---------------------------------------------------
+            const short2 rng = s_range[tb - tb0];
+            const bool mine = rng.y >= rng.x;                 // can any of my warp's points reach this tile?
+            const bool wide = mine && (rng.y - rng.x >= RING);
+            if (mine && !wide) {
+                const int nlo = min(win_lo, (int)rng.x), nhi = max(win_hi, (int)rng.y);
+                if (nhi - nlo >= RING) { fold(); win_lo = rng.x; win_hi = rng.y; }
+                else { win_lo = nlo; win_hi = nhi; }
+            }
+            mbar_wait(&s_bar[b], phase);
+            ++seq;
+
+            if (mine) {
+                const double2 *bxy = s_txy[b];
+                const double *bz = s_tz[b];
+                const double2 *bgs = s_gs[b];
+                const bool diagonal = (tb <= ta_last);
+                const int jbase = tb * TILE;
+                {
+                    // pairs (i, j) with j > i of my warp against this tile
+                    const int jend = (int)min((int64_t)jbase + TILE, p.n);
+                    unsigned np = 0;
+#pragma unroll
+                    for (int k = 0; k < APT; ++k)
+                        if (ig[k] < p.n) np += (unsigned)max(0, jend - max(ig[k] + 1, jbase));
+                    np = __reduce_add_sync(0xffffffffu, np);
+                    evaluated += np;
+                }
+                int wlo = 1;                                  // wide sweeps: lag slots the ring accepts, [wlo, wlo + wlen)
+                unsigned wlen = (unsigned)n_lags;
+
+                // squared distance in the reference's operation order
+                auto dist2 = [&](const double2 pj, int k) __attribute__((always_inline)) -> double {
+                    if (ELLIPSE) {
+                        // vector_distance = other - centre (angular.py:448); W @ d as OpenBLAS dgemm evaluates it:
+                        // fma(W[r][1], dy, W[r][0]*dx); einsum: n0*n0 + n1*n1 un-fused (angular.py:666-668)
+                        const double dx = __dsub_rn(pj.x, xi[k]), dy = __dsub_rn(pj.y, yi[k]);
+                        const double n0 = __fma_rn(w01, dy, __dmul_rn(w00, dx));
+                        const double n1 = __fma_rn(w11, dy, __dmul_rn(w10, dx));
+                        return __dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1));
+                    } else {
+                        // scipy cdist euclidean: sqrt(dx*dx + dy*dy), nothing fused (distance/point.py:56)
+                        const double dx = __dsub_rn(xi[k], pj.x), dy = __dsub_rn(yi[k], pj.y);
+                        return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                    }
+                };
+                // exact slot of one squared distance: table cell, then threshold steps on the full bit pattern
+                auto slot_of = [&](long long bits) __attribute__((always_inline)) -> int {
+                    int idx = ((int)(bits >> 32) - base_hi) >> LUT2_SHIFT;
+                    idx = min(max(idx, 0), lut_last);
+                    int q = s_lut[idx];
+                    while (bits > s_slot[q].T) ++q;
+                    return q;
+                };
+                // one pair into the ring (slow paths)
+                auto add_pair = [&](int q, int k, double z, bool wide_mode) __attribute__((always_inline)) {
+                    uint32_t off = s_slot[q].offs & 0xffffu;
+                    if (wide_mode && !((unsigned)(q - wlo) < wlen)) off = TRASH16;
+                    double2 *ap = reinterpret_cast<double2 *>(ring + off * 16 + my_acc[k]);
+                    uint32_t *cp = reinterpret_cast<uint32_t *>(ring + off * 16 + my_cnt[k]);
+                    double2 a = *ap;
+                    a.x += z; a.y = __fma_rn(z, z, a.y);
+                    *ap = a;
+                    *cp += 1u;
+                };
+
+                // ---- one group of U B points, in two stages so that two groups are in flight ----------------------
+                struct Grp {
+                    long long d2[APT][U];
+                    long long T[APT];          // threshold between the group's first and second lag
+                    uint32_t offs[APT];        // ring blocks of the two lags
+                    uint32_t ea[APT];          // shared address of the first lag's table entry
+                    bool beyond;               // a pair may lie beyond the second lag
+                };
+                // stage A: the U squared distances of every A point, the group's first lag slot and its table entry
+                auto stage_a = [&](int g, Grp &s) __attribute__((always_inline)) {
+                    const int j0 = g * U;
+                    int mn[APT], mx[APT];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const double2 pj = bxy[j0 + u];
+#pragma unroll
+                        for (int k = 0; k < APT; ++k) {
+                            s.d2[k][u] = __double_as_longlong(dist2(pj, k));
+                            const int h = (int)(s.d2[k][u] >> 32);
+                            mn[k] = u ? min(mn[k], h) : h;
+                            mx[k] = u ? max(mx[k], h) : h;
+                        }
+                    }
+                    // the smallest high word with a zero low word is a lower bound of all U squared distances; its slot is
+                    // <= every pair's slot (== the smallest unless a threshold falls into the 2^-20 relative gap, which
+                    // only sends more pairs to the slow path)
+                    s.beyond = false;
+#pragma unroll
+                    for (int k = 0; k < APT; ++k) {
+                        int idx = (mn[k] - base_hi) >> LUT2_SHIFT;
+                        idx = min(max(idx, 0), lut_last);
+                        unsigned short q0;
+                        asm("ld.shared.u16 %0, [%1];" : "=h"(q0) : "r"(lut_sa + 2u * (uint32_t)idx));
+                        uint32_t ea = slot_sa + 16u * (uint32_t)q0;
+                        int thi;
+                        if (MULTI_FIX) {
+                            while (true) {
+                                asm volatile("ld.shared.s32 %0, [%1+4];" : "=r"(thi) : "r"(ea));
+                                if (!(mn[k] > thi)) break;
+                                ea += 16u;
+                            }
+                        } else {
+                            asm("ld.shared.s32 %0, [%1+4];" : "=r"(thi) : "r"(ea));
+                            ea += (mn[k] > thi) ? 16u : 0u;
+                        }
+                        int e_tlo, e_thi, e_next;
+                        asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(e_tlo), "=r"(e_thi), "=r"(e_next), "=r"(s.offs[k]) : "r"(ea));
+                        s.T[k] = ((long long)e_thi << 32) | (unsigned)e_tlo;
+                        s.ea[k] = ea;
+                        s.beyond |= (mx[k] >= e_next);
+                    }
+                };
+                // second-lag sums of one group for A point k and the two ring updates; g1, g2, n_in = sums of z, z^2 and
+                // the number of pairs the ring still has to take (the slow path removes pairs it added on its own)
+                auto finish_group = [&](int k, int j0, const long long (&d2k)[U], long long T, uint32_t offs, int q, double g1,
+                                        double g2, int n_in, const bool wide_mode) __attribute__((always_inline)) {
+                    uint32_t o_lo = offs & 0xffffu, o_hi = offs >> 16;
+                    if (wide_mode) {
+                        if (!((unsigned)(q - wlo) < wlen)) o_lo = TRASH16;
+                        if (!((unsigned)(q + 1 - wlo) < wlen)) o_hi = TRASH16;
+                    }
+                    double h1a = 0.0, h1b = 0.0, h2a = 0.0, h2b = 0.0;
+                    int ch = 0;
+#pragma unroll
+                    for (int u = 0; u < U; u += 2) {
+                        const double2 zz = *reinterpret_cast<const double2 *>(bz + j0 + u);
+                        // "second lag" predicate on the bit patterns (d2 >= 0: integer order == fp64 order); one select per
+                        // pair: a first-lag pair keeps the low word of z under a zero high word, a subnormal below 1e-308
+                        // whose contribution to the fp64 sums is far below one ulp; predicated count
+                        int za_hi, zb_hi;
+                        if (CMP == 1)
+                            asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %3, %4;\n\tselp.b32 %0, %2, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
+                                : "=r"(za_hi), "+r"(ch) : "r"(__double2hiint(zz.x)), "d"(__longlong_as_double(d2k[u])), "d"(__longlong_as_double(T)));
+                        else
+                            asm("{\n\t.reg .pred p;\n\tsetp.gt.s64 p, %3, %4;\n\tselp.b32 %0, %2, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
+                                : "=r"(za_hi), "+r"(ch) : "r"(__double2hiint(zz.x)), "l"(d2k[u]), "l"(T));
+                        if (CMP >= 1)
+                            asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %3, %4;\n\tselp.b32 %0, %2, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
+                                : "=r"(zb_hi), "+r"(ch) : "r"(__double2hiint(zz.y)), "d"(__longlong_as_double(d2k[u + 1])), "d"(__longlong_as_double(T)));
+                        else
+                            asm("{\n\t.reg .pred p;\n\tsetp.gt.s64 p, %3, %4;\n\tselp.b32 %0, %2, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
+                                : "=r"(zb_hi), "+r"(ch) : "r"(__double2hiint(zz.y)), "l"(d2k[u + 1]), "l"(T));
+                        const double za = __hiloint2double(za_hi, __double2loint(zz.x));
+                        const double zb = __hiloint2double(zb_hi, __double2loint(zz.y));
+                        h1a += za; h2a = __fma_rn(za, za, h2a);
+                        h1b += zb; h2b = __fma_rn(zb, zb, h2b);
+                    }
+                    const double h1 = h1a + h1b, h2 = h2a + h2b;
+                    double2 *alo = reinterpret_cast<double2 *>(ring + o_lo * 16 + my_acc[k]);
+                    double2 *ahi = reinterpret_cast<double2 *>(ring + o_hi * 16 + my_acc[k]);
+                    uint32_t *clo = reinterpret_cast<uint32_t *>(ring + o_lo * 16 + my_cnt[k]);
+                    uint32_t *chi = reinterpret_cast<uint32_t *>(ring + o_hi * 16 + my_cnt[k]);
+                    double2 v_lo = *alo, v_hi = *ahi;
+                    const uint32_t c_lo = *clo, c_hi = *chi;
+                    v_lo.x += g1 - h1; v_lo.y += g2 - h2;
+                    v_hi.x += h1;      v_hi.y += h2;
+                    *alo = v_lo; *ahi = v_hi;               // both blocks are the trash block when they coincide: never read
+                    *clo = c_lo + (uint32_t)(n_in - ch);
+                    *chi = c_hi + (uint32_t)ch;
+                };
+                // stage B: sums and ring updates
+                auto stage_b = [&](int g, const Grp &s, const bool wide_mode) __attribute__((always_inline)) {
+                    const int j0 = g * U;
+                    const double2 gs = bgs[g];
+                    if (!__any_sync(0xffffffffu, s.beyond)) {
+                        // fast path: every pair of the warp is in the group's first or second lag
+#pragma unroll
+                        for (int k = 0; k < APT; ++k)
+                            finish_group(k, j0, s.d2[k], s.T[k], s.offs[k], wide_mode ? (int)((s.ea[k] - slot_sa) >> 4) : 0, gs.x, gs.y,
+                                         U, wide_mode);
+                    } else {
+                        // rare: a pair may lie beyond the second lag — those pairs are added on their own, leave the group's
+                        // sums and get a zero distance (never above a threshold: they stay out of the second-lag sums)
+#pragma unroll
+                        for (int k = 0; k < APT; ++k) {
+                            const int q = (int)((s.ea[k] - slot_sa) >> 4);
+                            const long long t1 = s_slot[q + 1].T;
+                            double g1 = gs.x, g2 = gs.y;
+                            int n_in = U;
+                            long long d2k[U];
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                d2k[u] = s.d2[k][u];
+                                if (d2k[u] > t1) {
+                                    int sx = q + 2;
+                                    while (d2k[u] > s_slot[sx].T) ++sx;
+                                    const double zj = bz[j0 + u];
+                                    add_pair(sx, k, zj, wide_mode);
+                                    g1 -= zj; g2 = __fma_rn(-zj, zj, g2);
+                                    d2k[u] = 0; --n_in;
+                                }
+                            }
+                            finish_group(k, j0, d2k, s.T[k], s.offs[k], q, g1, g2, n_in, wide_mode);
+                        }
+                    }
+                };
+
+                auto sweep = [&](const bool wide_mode) __attribute__((always_inline)) {
+                    if (diagonal || !p.group_path) {
+                        // tiles that overlap my CTA's own points: per-pair slots, keep i < j only
+#pragma unroll 1
+                        for (int j0 = 0; j0 < TILE; j0 += 4) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const double2 pj = bxy[j0 + u];
+                                const double zj = bz[j0 + u];
+#pragma unroll
+                                for (int k = 0; k < APT; ++k) {
+                                    int q = slot_of(__double_as_longlong(dist2(pj, k)));
+                                    if (!(jbase + j0 + u > ig[k])) q = 0;
+                                    add_pair(q, k, zj, wide_mode);
+                                }
+                            }
+                        }
+                        return;
+                    }
+                    if (PIPE) {
+                        Grp sa, sb;
+                        stage_a(0, sa);
+#pragma unroll 1
+                        for (int g = 0; g < NG - 2; g += 2) {
+                            stage_a(g + 1, sb);
+                            stage_b(g, sa, wide_mode);
+                            stage_a(g + 2, sa);
+                            stage_b(g + 1, sb, wide_mode);
+                        }
+                        stage_a(NG - 1, sb);
+                        stage_b(NG - 2, sa, wide_mode);
+                        stage_b(NG - 1, sb, wide_mode);
+                    } else {
+#pragma unroll 2
+                        for (int g = 0; g < NG; ++g) {
+                            Grp s;
+                            stage_a(g, s);
+                            stage_b(g, s, wide_mode);
+                        }
+                    }
+                };
+                if (!wide) {
+                    sweep(false);
+                } else {
+                    // this tile alone spans >= RING lags for my warp: sweep it once per window of RING lags, folding in
+                    // between (no atomics, so the result stays deterministic)
+                    fold();
+                    for (int w0 = rng.x; w0 <= rng.y; w0 += RING) {
+                        wlo = w0; wlen = (unsigned)(min(w0 + RING - 1, (int)rng.y) - w0 + 1);
+                        sweep(true);
+                        win_lo = w0; win_hi = w0 + (int)wlen - 1;
+                        fold();
+                    }
+                }
+            }
+            __syncthreads();                                  // everyone is done with buffer b
+            if (tb_next < 0) break;
+            tb = tb_next;
+        }
+        fold();                                               // my z_i changes with the next item
+    }
+    if (lane == 0 && evaluated) atomicAdd(p.pairs_evaluated, evaluated);
+}
+
+}  // namespace pib

@@ -25,6 +25,7 @@
 //     and a last kernel adds the partials in a fixed order: results are deterministic
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -59,6 +60,7 @@ struct PairParams {
     const double2 *gsum;         // [n_pad / 8] (sum z, sum z^2) over each group of 8 consecutive (sorted) points; z centred
     const int32_t *item_list;    // ring kernel: work items ordered by descending cost (NULL: natural order)
     const unsigned *n_live_items;  // number of items with at least one live tile pair (device scalar)
+    const int *run_flag;           // NULL, or device flag: the kernel returns at once when it is 0 (conditional re-run)
 };
 
 // ---- PTX helpers: mbarrier + 1D TMA bulk copy -------------------------------------------------
@@ -121,6 +123,7 @@ template <int NT, bool ELLIPSE, int FIX>
 __global__ void __launch_bounds__(NT, 1) pair_kernel(const PairParams p)
 {
     static_assert(TILE % NT == 0, "an A sub-tile is NT consecutive points of one tile");
+    if (p.run_flag && *p.run_flag == 0) return;    // conditional re-run (cancellation guard): nothing to do
     constexpr int A_PER_TILE = TILE / NT;          // thread t owns point t of the A sub-tile
     constexpr int U = 8;                           // pairs per batch
     static_assert(TILE % (2 * U) == 0, "tile must hold an even number of batches");
@@ -827,6 +830,10 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
     if (tid == 0 && evaluated) atomicAdd(p.pairs_evaluated, evaluated);
 }
 
+}  // namespace pib
+#include "pair_ring6.cuh"
+namespace pib {
+
 // Cost of every ring-kernel work item = number of B tiles of its chunk that can hold a pair within range
 // (the same box test as the kernel's).  One warp per item; key = CHUNK - cost so that an ascending radix sort
 // puts the most expensive items first.
@@ -904,26 +911,29 @@ __global__ void __launch_bounds__(256) mean_final_kernel(const double *__restric
     if (threadIdx.x == 0) *mean = sh[0] / (double)n;
 }
 
-// centred copy of z and, per group of 8 consecutive sorted points (pads included, as the pair kernel sees them),
+// centred copy of z and, per group of G consecutive sorted points (pads included, as the pair kernel sees them),
 // the sums of the centred values and of their squares
+template <int G>
 __global__ void group_sum_kernel(const double *__restrict__ z, const double *__restrict__ mean, int64_t n,
                                  int64_t n_groups, double *__restrict__ zc, double2 *__restrict__ gsum)
 {
     const int64_t gidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (gidx >= n_groups) return;
     const double m = *mean;
-    double v[8];
+    double v[G];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < G; ++u) {
         // padding rows sit at the mean (centred 0): their pairs only ever reach the trash slots, but the two-lag
-        // sums form "all 8 minus second lag", and a huge padding dz would cancel there (data with a large offset)
-        v[u] = (gidx * 8 + u < n) ? z[gidx * 8 + u] - m : 0.0;
-        zc[gidx * 8 + u] = v[u];
+        // sums form "all minus second lag", and a huge padding value would cancel there (data with a large offset)
+        v[u] = (gidx * G + u < n) ? z[gidx * G + u] - m : 0.0;
+        zc[gidx * G + u] = v[u];
     }
-    const double s1 = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-    double qe = v[0] * v[0], qo = v[1] * v[1];
+    double s1 = 0.0, qe = 0.0, qo = 0.0;
 #pragma unroll
-    for (int u = 2; u < 8; u += 2) { qe = __fma_rn(v[u], v[u], qe); qo = __fma_rn(v[u + 1], v[u + 1], qo); }
+    for (int u = 0; u < G; u += 8)
+        s1 += ((v[u] + v[u + 1]) + (v[u + 2] + v[u + 3])) + ((v[u + 4] + v[u + 5]) + (v[u + 6] + v[u + 7]));
+#pragma unroll
+    for (int u = 0; u < G; u += 2) { qe = __fma_rn(v[u], v[u], qe); qo = __fma_rn(v[u + 1], v[u + 1], qo); }
     gsum[gidx] = make_double2(s1, qe + qo);
 }
 
@@ -959,8 +969,9 @@ __global__ void __launch_bounds__(128) reduce_partials_kernel(const double *__re
                                                               int n_lags, const double *__restrict__ mean,
                                                               double *__restrict__ sum_sq,
                                                               double *__restrict__ sum_prod, double *__restrict__ sum_val,
-                                                              int64_t *__restrict__ count)
+                                                              int64_t *__restrict__ count, const int *__restrict__ run_flag = nullptr)
 {
+    if (run_flag && *run_flag == 0) return;
     __shared__ double sh[3][128];
     __shared__ unsigned long long shc[128];
     const int b = blockIdx.x, t = threadIdx.x;
@@ -991,6 +1002,30 @@ __global__ void __launch_bounds__(128) reduce_partials_kernel(const double *__re
         }
         sum_sq[b] = sh[0][0]; sum_prod[b] = prod; sum_val[b] = val; count[b] = (int64_t)shc[0];
     }
+}
+
+// Cancellation guard of the z_j-form / group-sum kernels: they form sum dz^2 from sums of (centred) z and z^2, which
+// costs eps * var(z) / (2 gamma(h)) relative.  flag = 1 when some lag has gamma(h) = sum_sq / (2 count) < 1e-6 var(z):
+// the host side has then already queued a conditional re-run with the per-pair dz-form kernel (pair_kernel).
+__global__ void __launch_bounds__(1024) cancellation_guard_kernel(const double2 *__restrict__ gsum, int64_t n_groups, int64_t n,
+                                                                  const double *__restrict__ sum_sq,
+                                                                  const int64_t *__restrict__ count, int n_lags,
+                                                                  int *__restrict__ flag)
+{
+    __shared__ double sh[1024];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n_groups; i += 1024) s += gsum[i].y;      // sum of the squared centred values
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    const double var = sh[0] / (double)n;
+    bool bad = false;
+    for (int b = threadIdx.x; b < n_lags; b += 1024)
+        if (count[b] > 0 && sum_sq[b] < 1e-6 * var * 2.0 * (double)count[b]) bad = true;
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *flag = 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1067,6 +1102,56 @@ static int launch_pair_kernel(const PairParams &p, int fix_steps, int grid, cuda
     if (fix_steps <= 1) return launch_pair_kernel_fix<NT, ELLIPSE, 1>(p, smem, grid, stream);
     if (fix_steps <= 2) return launch_pair_kernel_fix<NT, ELLIPSE, 2>(p, smem, grid, stream);
     return launch_pair_kernel_fix<NT, ELLIPSE, 0>(p, smem, grid, stream);
+}
+
+// ALL = every (multi-step threshold fix-up, ellipse) combination; experiment variants are only built for the
+// plain omnidirectional case
+template <int RING, int NT, int APT, int U, bool ALL>
+static int launch_pair_ring6_t(const PairParams &p, bool multi_fix, bool ellipse, int grid, cudaStream_t stream)
+{
+    const size_t smem = ring6_smem_bytes<RING, NT, APT>(p.n_slots, p.lut2_n);
+    PIB_CHECK(smem + 8192 <= (size_t)MAX_SMEM, PIB_ERR_UNSUPPORTED, "pair_ring6_kernel: tables do not fit in shared memory");
+#define PIB_L6(M, E)                                                                                                          \
+    do {                                                                                                                      \
+        PIB_CUDA(cudaFuncSetAttribute(pair_ring6_kernel<RING, NT, APT, U, M, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem));                                                                            \
+        pair_ring6_kernel<RING, NT, APT, U, M, E><<<grid, NT, smem, stream>>>(p);                                             \
+    } while (0)
+    if constexpr (ALL) {
+        if (multi_fix) { if (ellipse) PIB_L6(true, true); else PIB_L6(true, false); }
+        else { if (ellipse) PIB_L6(false, true); else PIB_L6(false, false); }
+    } else {
+        PIB_CHECK(!multi_fix && !ellipse, PIB_ERR_UNSUPPORTED, "pair_ring6_kernel: experiment variant, plain omnidirectional only");
+        PIB_L6(false, false);
+    }
+#undef PIB_L6
+    PIB_CUDA(cudaGetLastError());
+    return PIB_OK;
+}
+
+static int launch_pair_ring6(const PairParams &p, int ring, int nt, int apt, int u, bool multi_fix, bool ellipse, int grid,
+                             cudaStream_t stream)
+{
+#ifdef PIB_V6_VARIANTS
+#define PIB_V6_TRY(R, T, A, UU) \
+    if (ring == R && nt == T && apt == A && u == UU) return launch_pair_ring6_t<R, T, A, UU, false>(p, multi_fix, ellipse, grid, stream)
+    PIB_V6_TRY(16, 512, 1, 8);
+    PIB_V6_TRY(16, 512, 1, 16);
+    PIB_V6_TRY(16, 256, 2, 8);
+    PIB_V6_TRY(12, 384, 2, 8);
+    PIB_V6_TRY(10, 384, 2, 8);
+    PIB_V6_TRY(16, 384, 1, 8);
+    PIB_V6_TRY(12, 640, 1, 8);
+    PIB_V6_TRY(10, 768, 1, 8);
+    PIB_V6_TRY(8, 768, 1, 8);
+    PIB_V6_TRY(8, 896, 1, 8);
+#undef PIB_V6_TRY
+#else
+    if (ring == 16 && nt == 512 && apt == 1 && u == 8) return launch_pair_ring6_t<16, 512, 1, 8, true>(p, multi_fix, ellipse, grid, stream);
+    if (ring == 32 && nt == 256 && apt == 1 && u == 8) return launch_pair_ring6_t<32, 256, 1, 8, true>(p, multi_fix, ellipse, grid, stream);
+#endif
+    set_error("pair_ring6_kernel: variant not built");
+    return PIB_ERR_UNSUPPORTED;
 }
 
 int variogram_device(const double *d_xyz, int64_t n, const double *edges, const double *lower, int n_lags,
@@ -1187,6 +1272,8 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             const double frob = w[0] * w[0] + w[1] * w[1] + w[2] * w[2] + w[3] * w[3], det = w[0] * w[3] - w[1] * w[2];
             stretch = std::max(stretch, std::sqrt(0.5 * (frob + std::sqrt(std::max(0.0, frob * frob - 4.0 * det * det)))));
         }
+        double d90_scaled = INFINITY, min_width = edges[0];
+        for (int b = 1; b < n_lags; ++b) min_width = std::min(min_width, edges[b] - edges[b - 1]);
         if (n_lags <= MAX_SLOTS - 2 && !(force_full && force_full[0] == '1')) {
             std::vector<double4> boxes(n_tiles);
             PIB_CUDA(cudaMemcpyAsync(boxes.data(), sp.tile_box, sizeof(double4) * n_tiles, cudaMemcpyDeviceToHost, stream));
@@ -1195,11 +1282,10 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             diag.reserve(n_tiles);
             for (auto &b : boxes)
                 if (b.z >= b.x) diag.push_back(std::hypot(b.z - b.x, b.w - b.y));
-            double min_width = edges[0];
-            for (int b = 1; b < n_lags; ++b) min_width = std::min(min_width, edges[b] - edges[b - 1]);
             if (!diag.empty()) {
                 std::sort(diag.begin(), diag.end());
                 const double d90 = stretch * diag[(size_t)(0.9 * (diag.size() - 1))];
+                d90_scaled = d90;
                 use_ring = (2.5 * d90 / min_width + 2.0) <= 24.0;
                 ring16_ok = (3.0 * d90 / min_width + 2.0) <= 16.0;       // A sub-tile = 4 tiles (~2x the diagonal)
             }
@@ -1209,12 +1295,42 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             const char *ring_env = std::getenv("PIB_RING");
             if (ring_env) ring16_ok = (ring_env[0] == '1' && ring_env[1] == '6');
         }
-        // two instantiations: 32-slot ring / 256 threads, or 16-slot ring / 512 threads (more warps to hide
-        // latency) when tile pairs are narrow enough
+        // old formulation (pair_ring_kernel): 32-slot ring / 256 threads, or 16-slot ring / 512 threads (more warps to
+        // hide latency) when tile pairs are narrow enough; CTA-wide ring window
         int ring = 32, ring_nt = 256;
         if (use_ring && ring16_ok) { ring = 16; ring_nt = 512; }
+        // new formulation (pair_ring6_kernel, the default): per-warp ring windows, so the window only has to cover the
+        // lags between ONE warp's 32 * APT points and a B tile
+        const char *ver_env = std::getenv("PIB_PAIR_V");
+        bool v6 = !(ver_env && ver_env[0] == '5');
+        int v6_apt = 1, v6_u = 8;
+        if (v6 && !(force_full && force_full[0] == '1') && n_lags <= MAX_SLOTS - 2) {
+            const double span1 = 1.5 * d90_scaled / min_width + 2.0;     // A points per warp = 32: box ~ half a tile's diagonal
+            if (span1 <= 16.0) { ring = 16; ring_nt = 512; use_ring = true; }
+            else if (span1 <= 30.0) { ring = 32; ring_nt = 256; use_ring = true; }
+            else use_ring = false;
+            const char *force_ring = std::getenv("PIB_FORCE_RING");
+            if (force_ring && force_ring[0] == '1') {
+                use_ring = true;
+                if (force_ring[1] == '6') { ring = 16; ring_nt = 512; }
+            }
+            const char *ring_env = std::getenv("PIB_RING");
+            if (ring_env && use_ring) {
+                if (ring_env[0] == '1' && ring_env[1] == '6') { ring = 16; ring_nt = 512; } else { ring = 32; ring_nt = 256; }
+            }
+            // PIB_V6 = "apt,u,threads,ring" picks another build of the kernel for A/B measurements, e.g. "2,8,384,12"
+            const char *v6_env = std::getenv("PIB_V6");
+            if (v6_env && use_ring) {
+                int e_apt = 1, e_u = 8, e_nt = ring_nt, e_ring = ring;
+                if (std::sscanf(v6_env, "%d,%d,%d,%d", &e_apt, &e_u, &e_nt, &e_ring) >= 2) {
+                    v6_apt = e_apt; v6_u = e_u; ring_nt = e_nt; ring = e_ring;
+                }
+            }
+        } else v6 = false;
+        if (!use_ring) v6 = false;
+        const int a_per_cta = use_ring ? ring_nt * (v6 ? v6_apt : 1) : nt;
         if (use_ring) nt = ring_nt;
-        const int64_t a_tiles = use_ring ? (n_tiles + ring_nt / TILE - 1) / (ring_nt / TILE) : (int64_t)n_tiles * (TILE / nt);
+        const int64_t a_tiles = use_ring ? (n_tiles + a_per_cta / TILE - 1) / (a_per_cta / TILE) : (int64_t)n_tiles * (TILE / nt);
         const int64_t n_items = (a_tiles * n_chunks + shard_count - 1) / shard_count;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sm_count(), n_items));
         const int warps = nt / 32;
@@ -1231,7 +1347,8 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         p.box_slack = 0.0;
         p.gsum = nullptr;
         double *d_mean = nullptr;                  // ring kernel: mean of z (its sums come out centred)
-        p.item_list = nullptr; p.n_live_items = nullptr;
+        int64_t guard_groups = 0;                  // ring kernel: number of group sums (cancellation guard)
+        p.item_list = nullptr; p.n_live_items = nullptr; p.run_flag = nullptr;
         const int64_t n_items_all = a_tiles * n_chunks;            // over all ranks
         const char *bal_env = std::getenv("PIB_BALANCE");
         const bool balance = use_ring && n_items_all < ((int64_t)1 << 31) && !(bal_env && bal_env[0] == '0');
@@ -1244,27 +1361,38 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             PIB_TRY(ws.alloc(&d_nlive, 1));
         }
         if (use_ring) {
-            const int64_t n_groups = (int64_t)n_tiles * (TILE / 8);
+            const int gsz = v6 ? v6_u : 8;                     // points per group (the group sums ride along with every B tile)
+            const int64_t n_groups = (int64_t)n_tiles * (TILE / gsz);
             double2 *d_gsum;
             double *d_zc;
             PIB_TRY(ws.alloc(&d_gsum, (size_t)n_groups));
-            PIB_TRY(ws.alloc(&d_zc, (size_t)n_groups * 8 + 1024));
+            PIB_TRY(ws.alloc(&d_zc, (size_t)n_tiles * TILE + 1024));
             PIB_TRY(ws.alloc(&d_mean, 1));
-            PIB_CUDA(cudaMemsetAsync(d_zc, 0, ((size_t)n_groups * 8 + 1024) * sizeof(double), stream));
+            PIB_CUDA(cudaMemsetAsync(d_zc, 0, ((size_t)n_tiles * TILE + 1024) * sizeof(double), stream));
             double *d_mpart;
             PIB_TRY(ws.alloc(&d_mpart, 256));
             mean_partial_kernel<<<256, 256, 0, stream>>>(sp.z, n, d_mpart);
             mean_final_kernel<<<1, 256, 0, stream>>>(d_mpart, 256, n, d_mean);
-            group_sum_kernel<<<(int)((n_groups + 255) / 256), 256, 0, stream>>>(sp.z, d_mean, n, n_groups, d_zc, d_gsum);
+            if (gsz == 16)
+                group_sum_kernel<16><<<(int)((n_groups + 255) / 256), 256, 0, stream>>>(sp.z, d_mean, n, n_groups, d_zc, d_gsum);
+            else
+                group_sum_kernel<8><<<(int)((n_groups + 255) / 256), 256, 0, stream>>>(sp.z, d_mean, n, n_groups, d_zc, d_gsum);
             p.z = d_zc;
             PIB_CUDA(cudaGetLastError());
             p.gsum = d_gsum;
+            guard_groups = n_groups;
         }
         {
             const char *gp = std::getenv("PIB_GROUP_PATH");
             p.group_path = (gp && gp[0] == '0') ? 0 : 1;
         }
         double4 *d_boxw = nullptr;                 // ellipse: bounding boxes of the whitened coordinates, per direction
+        int *d_guard_flag = nullptr;               // cancellation guard: flag, fallback partials and a scratch pair counter
+        double *d_partial_fb = nullptr;
+        size_t fb_part_n = 0;
+        int fb_grid = 0;
+        unsigned long long *d_evaluated_fb = nullptr;
+        PIB_TRY(ws.alloc(&d_evaluated_fb, 1));
         if (n_dirs > 0) PIB_TRY(ws.alloc(&d_boxw, n_tiles));
         for (int t = 0; t < out_dirs; ++t) {
             PIB_CUDA(cudaMemsetAsync(d_partial, 0, part_n * sizeof(double), stream));
@@ -1283,15 +1411,17 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
                 PIB_CUDA(cudaMemsetAsync(d_nlive, 0, sizeof(unsigned), stream));
                 const int cgrid = (int)((n_items_all * 32 + 255) / 256);
                 if (n_dirs > 0)
-                    item_cost_kernel<true><<<cgrid, 256, 0, stream>>>(p, ring_nt / TILE, n_items_all, d_keys, d_items, d_nlive);
+                    item_cost_kernel<true><<<cgrid, 256, 0, stream>>>(p, a_per_cta / TILE, n_items_all, d_keys, d_items, d_nlive);
                 else
-                    item_cost_kernel<false><<<cgrid, 256, 0, stream>>>(p, ring_nt / TILE, n_items_all, d_keys, d_items, d_nlive);
+                    item_cost_kernel<false><<<cgrid, 256, 0, stream>>>(p, a_per_cta / TILE, n_items_all, d_keys, d_items, d_nlive);
                 PIB_CUDA(cudaGetLastError());
                 PIB_TRY(sort_pairs_u32(d_keys, d_keys2, d_items, d_items2, n_items_all, 7, ws, stream));
                 p.item_list = d_items2; p.n_live_items = d_nlive;
             }
             timing_begin(PIB_T_PAIR, stream);
-            if (use_ring) {
+            if (use_ring && v6) {
+                rc = launch_pair_ring6(p, ring, ring_nt, v6_apt, v6_u, fix2 > 1, n_dirs > 0, grid, stream);
+            } else if (use_ring) {
                 const size_t smem = (size_t)(ring + 2) * ring_nt * (sizeof(double2) + sizeof(uint32_t));
 #define PIB_LAUNCH_RING(R, T, F, E)                                                                                     \
     do {                                                                                                                \
@@ -1332,6 +1462,45 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
                 d_partial, grid * warps + 1, n_slots, n_lags, d_mean, d_sum_sq + (size_t)t * n_lags, d_sum_prod + (size_t)t * n_lags,
                 d_sum_val + (size_t)t * n_lags, d_count + (size_t)t * n_lags);
             PIB_CUDA(cudaGetLastError());
+            if (use_ring) {
+                // Cancellation guard (no host round trip): a flag kernel looks at the finished lags; the per-pair dz-form
+                // kernel and a second reduction are queued behind it and return at once unless the flag is set.
+                // (A sharded call guards its own slice of every lag: the bound holds for each rank's partial sums.)
+                int nt_fb = 0;
+                if (pair_smem_bytes<128>(n_slots) <= dyn_max) nt_fb = 128;
+                else if (pair_smem_bytes<64>(n_slots) <= dyn_max) nt_fb = 64;
+                else if (pair_smem_bytes<32>(n_slots) <= dyn_max) nt_fb = 32;
+                if (nt_fb) {
+                    if (!d_guard_flag) {
+                        PIB_TRY(ws.alloc(&d_guard_flag, 1));
+                        const int64_t fb_items = ((int64_t)n_tiles * (TILE / nt_fb)) * n_chunks;
+                        fb_grid = (int)std::max<int64_t>(1, std::min<int64_t>(sm_count(), fb_items));
+                        fb_part_n = ((size_t)fb_grid * (nt_fb / 32) + 1) * n_slots * 4;
+                        PIB_TRY(ws.alloc(&d_partial_fb, fb_part_n));
+                    }
+                    PIB_CUDA(cudaMemsetAsync(d_guard_flag, 0, sizeof(int), stream));
+                    PIB_CUDA(cudaMemsetAsync(d_partial_fb, 0, fb_part_n * sizeof(double), stream));
+                    cancellation_guard_kernel<<<1, 1024, 0, stream>>>(p.gsum, guard_groups, n, d_sum_sq + (size_t)t * n_lags,
+                                                                      d_count + (size_t)t * n_lags, n_lags, d_guard_flag);
+                    PIB_CUDA(cudaGetLastError());
+                    PairParams pf = p;
+                    pf.z = sp.z; pf.gsum = nullptr; pf.item_list = nullptr; pf.n_live_items = nullptr;
+                    pf.partial = d_partial_fb; pf.run_flag = d_guard_flag; pf.pairs_evaluated = d_evaluated_fb;
+                    if (n_dirs > 0)
+                        rc = nt_fb == 128 ? launch_pair_kernel<128, true>(pf, fix_steps, fb_grid, stream)
+                           : nt_fb == 64 ? launch_pair_kernel<64, true>(pf, fix_steps, fb_grid, stream)
+                                         : launch_pair_kernel<32, true>(pf, fix_steps, fb_grid, stream);
+                    else
+                        rc = nt_fb == 128 ? launch_pair_kernel<128, false>(pf, fix_steps, fb_grid, stream)
+                           : nt_fb == 64 ? launch_pair_kernel<64, false>(pf, fix_steps, fb_grid, stream)
+                                         : launch_pair_kernel<32, false>(pf, fix_steps, fb_grid, stream);
+                    PIB_TRY(rc);
+                    reduce_partials_kernel<<<n_lags, 128, 0, stream>>>(
+                        d_partial_fb, fb_grid * (nt_fb / 32) + 1, n_slots, n_lags, nullptr, d_sum_sq + (size_t)t * n_lags,
+                        d_sum_prod + (size_t)t * n_lags, d_sum_val + (size_t)t * n_lags, d_count + (size_t)t * n_lags, d_guard_flag);
+                    PIB_CUDA(cudaGetLastError());
+                }
+            }
         }
     }
     if (pairs_evaluated) {
