@@ -14,8 +14,10 @@ One step = one full variogram pass over the field with the points already reside
 pair; this implementation skips tile pairs farther apart than the last lag, `pairs_evaluated` says how
 many distances were really computed, and only those count as achieved FLOPs in `roofline`).
 `e2e` = the same pass through the host-buffer entry point (pinned host points in, per-lag sums out).
-The kriging half of the metric (kriged points/s) is measured after the timed region and reported
-under `extra` (it does not enter `value`).
+The kriging half of the metric (kriged points/s) is measured after the timed region: the top-level `kriging` block
+is BASELINE config 4 (1M known points, 10M unknown locations, no_neighbors=64, ordinary + simple kriging) through the
+public call with host arrays, the locations strong-scaled over the ranks, with its own roofline / e2e / cpu_baseline;
+device-resident rates per kernel sit under `extra` (none of it enters `value`).
 """
 import argparse
 import json
@@ -35,6 +37,7 @@ N_POINTS = 1_000_000
 EXTENT = 100_000.0
 STEP, MAX_RANGE = 500.0, 40500.0          # np.arange(500, 40500, 500) -> 80 lags
 FLOP_PER_PAIR = 13                        # semivariance + covariance per evaluated pair
+COUNT_CHECKSUM_CONFIG2 = 172371810095     # sum over the 80 lags of the unordered pair counts of the seed-2 field (1 GPU = oracle)
 METRIC = "variogram_point_pairs_per_s"
 UNIT = "pairs/s"
 
@@ -47,6 +50,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--no-extra", action="store_true", help="skip the kriging measurements")
+    ap.add_argument("--krige-points", type=int, default=10_000_000, help="unknown locations of the config-4 kriging block")
     return ap.parse_args()
 
 
@@ -80,6 +84,39 @@ def cpu_variogram_sample(pts, lags, target_s=12.0):
     return pairs / dt, oracle.num_threads(), f"rows [0, {rows}) of the {n}-point pair triangle = {pairs:.3e} pairs in {dt:.1f} s"
 
 
+def reference_python_config1():
+    """The UNMODIFIED reference (oracle/_ref, a git-ignored copy made by oracle/make_ref.py; or /root/reference in the
+    build container) on BASELINE config 1 in full, nothing extrapolated: ExperimentalVariogram(step 500, max_range 40000)
+    on 10k points, then ordinary_kriging(no_neighbors=32) of a bounded sample of locations."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import ref_import
+        ref = ref_import.import_reference()
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    from pyinterpolate_b200.synthetic import dem_like_field, uniform_locations
+    pts = dem_like_field(10_000, extent=EXTENT, seed=0)
+    t0 = time.perf_counter()
+    ev = ref.ExperimentalVariogram(pts, step_size=500, max_range=40000)
+    dt_v = time.perf_counter() - t0
+    n = len(pts)
+    out = {"config": "BASELINE config 1: 10k points, step 500, max_range 40000 (79 lags), semivariance + covariance",
+           "variogram_s": dt_v, "pairs_per_s": (n * (n - 1) / 2) / dt_v, "cores": os.cpu_count(),
+           "lags": int(len(ev.lags))}
+    try:
+        model = ref.TheoreticalVariogram()
+        model.from_dict({"variogram_model_type": "linear", "nugget": 0.0, "sill": float(np.var(pts[:, 2])), "rang": 8000.0})
+        unk = uniform_locations(300, extent=EXTENT, seed=1)
+        t0 = time.perf_counter()
+        ref.ordinary_kriging(theoretical_model=model, known_locations=pts, unknown_locations=unk, no_neighbors=32,
+                             progress_bar=False)
+        dt_k = time.perf_counter() - t0
+        out.update({"kriging_sample_locations": len(unk), "kriging_s": dt_k, "kriged_points_per_s_ok_k32": len(unk) / dt_k})
+    except Exception as e:  # noqa: BLE001
+        out["kriging_unavailable"] = f"{type(e).__name__}: {e}"
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -100,7 +137,8 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(n, 1),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": sample + " per step; ms_per_step is the extrapolation to the full triangle"},
+                             "sample": sample + " per step; ms_per_step is the extrapolation to the full triangle",
+                             "reference_python": reference_python_config1()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -254,6 +292,10 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms, pair_kernel_ms = float(t[0]), float(t[1])
     ms_per_step = elapsed_ms / args.steps
+    # every rank holds the reduced histogram: its pair-count checksum must be the single-GPU one
+    count_checksum = int(sums["count"].sum().item())
+    if n == N_POINTS:
+        assert count_checksum == COUNT_CHECKSUM_CONFIG2, f"rank {rank}: pair-count checksum {count_checksum} != {COUNT_CHECKSUM_CONFIG2}"
     value = total_pairs / (ms_per_step * 1e-3)
 
     # ---- end to end: pinned host buffers through the host entry point ------------------------------
@@ -274,7 +316,7 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (pair kernel) --------------------------------------------
     evaluated_per_rank = evaluated / world                              # evaluated is the all-reduced total
     achieved = FLOP_PER_PAIR * evaluated_per_rank / (pair_kernel_ms * 1e-3) / 1e12
-    roofline = {"bound": "fp64", "kernel": "pair_ring_kernel<16,512>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+    roofline = {"bound": "fp64", "kernel": _lib.last_kernel_name(_lib.KERNEL_PAIR), "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak,
                 "peak_source": "DFMA-saturation probe run in this process (pib_fp64_peak_tflops); MEASURED_PEAKS.json "
                                "has no FP64 figure (its HBM %.0f GB/s / bf16 figures do not bound this kernel)"
@@ -284,6 +326,7 @@ def run_b200(args):
                 "traffic": profile_traffic("pair_ring_kernel")}
 
     extra = {"pairs_evaluated": evaluated, "evaluated_pairs_per_s": evaluated / (ms_per_step * 1e-3),
+             "pair_count_checksum": count_checksum,
              "fp64_peak_tflops_probe": fp64_peak}
     cpu_baseline = None
     if rank == 0:
@@ -309,17 +352,19 @@ def run_b200(args):
                                         "direction_pairs_per_s": 4 * (200_000 * 199_999 / 2) / (ms3 * 1e-3),
                                         "pairs_evaluated": r3["pairs_evaluated"]}
 
-    # ---- kriging half of the metric (outside the timed region; every rank kriges its own locations) ----
+    # ---- kriging half of the metric (outside the variogram's timed region) ------------------------------------------
+    kriging = None
     if not args.no_extra:
-        var = float(np.var(pts[:, 2]))
-        for name, k, m, model, params in (
-                ("ok_k32", 32, 1_000_000, "linear", [0.0, var, 8000.0]),
-                ("ok_k64", 64, 1_000_000, "spherical", [1.0, var, 20000.0]),
-                ("sk_k64", 64, 1_000_000, "spherical", [1.0, var, 20000.0])):
+        import pyinterpolate_b200 as pib
+        var, mean = float(np.var(pts[:, 2])), float(pts[:, 2].mean())
+        # (1) device-resident rates per kernel: every rank kriges 1M locations of its own (weak scaling)
+        for name, k, m, model, params, mode in (
+                ("ok_k32", 32, 1_000_000, "linear", [0.0, var, 8000.0], _lib.KRIGE_ORDINARY),
+                ("ok_k64", 64, 1_000_000, "spherical", [1.0, var, 20000.0], _lib.KRIGE_ORDINARY),
+                ("sk_k64", 64, 1_000_000, "spherical", [1.0, var, 20000.0], _lib.KRIGE_SIMPLE),
+                ("ok_sk_k64", 64, 1_000_000, "spherical", [1.0, var, 20000.0], _lib.KRIGE_BOTH)):
             unk = torch.from_numpy(uniform_locations(m, extent=EXTENT, seed=5 + rank)).to(dev)
-            mode = _lib.KRIGE_SIMPLE if name.startswith("sk") else _lib.KRIGE_ORDINARY
-            call = lambda: _lib.krige_device(d_pts, unk, _lib.MODEL_IDS[model], np.array([params]), mode, k,
-                                             process_mean=float(pts[:, 2].mean()))
+            call = lambda: _lib.krige_device(d_pts, unk, _lib.MODEL_IDS[model], np.array([params]), mode, k, process_mean=mean)
             call()
             barrier()
             k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -333,40 +378,96 @@ def run_b200(args):
                 dist.all_reduce(tk, op=dist.ReduceOp.MAX)
             knn_ms, _ = _lib.last_kernel_ms(_lib.KERNEL_KNN)
             solve_ms, _ = _lib.last_kernel_ms(_lib.KERNEL_SOLVE)
-            dim = k + 1 if mode == _lib.KRIGE_ORDINARY else k
-            solve_flop = (2 * dim ** 3 / 3 + 2 * dim ** 2) * m
+            # LU 2n^3/3 + 2n^2 per system, n = k + 1 (ordinary) or k (simple); both = the sum of the two
+            flop_ok, flop_sk = 2 * (k + 1) ** 3 / 3 + 2 * (k + 1) ** 2, 2 * k ** 3 / 3 + 2 * k ** 2
+            solve_flop = m * (flop_ok if mode == _lib.KRIGE_ORDINARY else flop_sk if mode == _lib.KRIGE_SIMPLE else flop_ok + flop_sk)
+            knn_bytes = m * (16 + 24 * k + 32)                                # algorithmic bytes per query (section 8d)
             extra[f"kriged_points_per_s_{name}"] = world * m / (float(tk) * 1e-3)
             extra[f"kriging_{name}"] = {"known": n, "unknown_per_gpu": m, "model": model, "ms": float(tk),
                                         "knn_kernel_ms": knn_ms, "solve_kernel_ms": solve_ms,
+                                        "solve_kernel": _lib.last_kernel_name(_lib.KERNEL_SOLVE),
                                         "solve_fp64_tflops": solve_flop / (solve_ms * 1e-3) / 1e12,
                                         "solve_frac_of_fp64_peak": solve_flop / (solve_ms * 1e-3) / 1e12 / fp64_peak,
+                                        "knn_algorithmic_gbs": knn_bytes / (knn_ms * 1e-3) / 1e9,
                                         "scaling": "weak"}
+        del unk
 
-    # kriging end to end through the public Python call (host arrays in, host array out), rank 0 only
-    if rank == 0 and not args.no_extra:
-        import pyinterpolate_b200 as pib
-        var = float(np.var(pts[:, 2]))
-        unk_h = uniform_locations(1_000_000, extent=EXTENT, seed=5)
-        mdl = {"variogram_model_type": "linear", "nugget": 0.0, "sill": var, "rang": 8000.0}
-        pib.ordinary_kriging(mdl, pts, unk_h[:1000], no_neighbors=32)
+        # (2) BASELINE config 4 through the PUBLIC call with host arrays: 1M known (seed 4), 10M unknown (seed 5),
+        # no_neighbors = 64, spherical {nugget 1, sill var, rang 20000}, ordinary + simple kriging from one pass.
+        # Strong scaling: the locations are split over the ranks (no data-path collective); time = max over ranks.
+        known4 = dem_like_field(1_000_000, extent=EXTENT, seed=4)
+        m4 = args.krige_points
+        unk4 = uniform_locations(m4, extent=EXTENT, seed=5)
+        b4, e4 = (rank * m4) // world, ((rank + 1) * m4) // world
+        mdl4 = {"variogram_model_type": "spherical", "nugget": 1.0, "sill": float(np.var(known4[:, 2])), "rang": 20000.0}
+        mean4 = float(known4[:, 2].mean())
+        pib.ordinary_and_simple_kriging(mdl4, known4, unk4[b4:b4 + 4096], process_mean=mean4, no_neighbors=64)     # warm-up
+        times = []
+        for _ in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            ok4, sk4 = pib.ordinary_and_simple_kriging(mdl4, known4, unk4[b4:e4], process_mean=mean4, no_neighbors=64)
+            torch.cuda.synchronize()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            times.append(float(tt))
+        dt4 = min(times)
+        knn_ms4, _ = _lib.last_kernel_ms(_lib.KERNEL_KNN)
+        solve_ms4, _ = _lib.last_kernel_ms(_lib.KERNEL_SOLVE)
+        ms4 = torch.tensor([knn_ms4, solve_ms4], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms4, op=dist.ReduceOp.MAX)
+        knn_ms4, solve_ms4 = float(ms4[0]), float(ms4[1])
+        m_rank = e4 - b4
+        flop4 = m_rank * ((2 * 65 ** 3 / 3 + 2 * 65 ** 2) + (2 * 64 ** 3 / 3 + 2 * 64 ** 2))
+        finite = bool(np.isfinite(ok4[:, 0]).all() and np.isfinite(sk4[:, 0]).all())
+        kriging = {"metric": "kriged_points_per_s", "value": m4 / dt4, "unit": "points/s (each location: ordinary AND simple kriging)",
+                   "n_gpus": world, "scaling": "strong", "seconds": dt4, "all_finite": finite,
+                   "config": {"workload": "BASELINE config 4: ordinary + simple kriging of %d unknown locations from 1M known points, "
+                                          "no_neighbors=64, spherical model (nugget 1, sill var(z), rang 20000); public call "
+                                          "ordinary_and_simple_kriging with host arrays, locations split over the ranks" % m4,
+                              "known": 1_000_000, "unknown": m4, "no_neighbors": 64},
+                   "e2e": {"value": m4 / dt4, "unit": "points/s",
+                           "h2d_bytes_per_step": int(known4.nbytes * world + unk4.nbytes),
+                           "d2h_bytes_per_step": int(2 * m4 * 4 * 8 + 2 * m4)},
+                   "roofline": {"solve": {"bound": "fp64", "kernel": _lib.last_kernel_name(_lib.KERNEL_SOLVE),
+                                          "achieved": flop4 / (solve_ms4 * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                                          "frac": flop4 / (solve_ms4 * 1e-3) / 1e12 / fp64_peak, "kernel_ms_per_rank": solve_ms4,
+                                          "flop_per_location": flop4 / m_rank},
+                                "knn": {"bound": "hbm", "achieved": m_rank * (16 + 24 * 64 + 32) / (knn_ms4 * 1e-3) / 1e9,
+                                        "peak": measured_peaks().get("hbm_gbs"), "unit": "GB/s (algorithmic bytes: 16 + 24 k + 32 per location)",
+                                        "frac": m_rank * (16 + 24 * 64 + 32) / (knn_ms4 * 1e-3) / 1e9 / (measured_peaks().get("hbm_gbs") or float("nan")),
+                                        "kernel_ms_per_rank": knn_ms4},
+                                "kernel_share_of_call": (knn_ms4 + solve_ms4) * 1e-3 / dt4}}
+        del ok4, sk4
+        # the k = 32 public call of config 1's shape (ordinary kriging, linear model), same strong-scaled split
+        mdl1 = {"variogram_model_type": "linear", "nugget": 0.0, "sill": var, "rang": 8000.0}
+        m1 = min(m4, 4_000_000)
+        b1, e1 = (rank * m1) // world, ((rank + 1) * m1) // world
+        pib.ordinary_kriging(mdl1, pts, unk4[b1:b1 + 4096], no_neighbors=32)
+        barrier()
         t0 = time.perf_counter()
-        res = pib.ordinary_kriging(mdl, pts, unk_h, no_neighbors=32)
-        dt = time.perf_counter() - t0
-        extra["kriged_points_per_s_ok_k32_public_api_host_buffers"] = {
-            "value": len(unk_h) / dt, "h2d_bytes": int(pts.nbytes + unk_h.nbytes), "d2h_bytes": int(res.nbytes + len(unk_h))}
+        res1 = pib.ordinary_kriging(mdl1, pts, unk4[b1:e1], no_neighbors=32)
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        kriging["ok_k32_public_call"] = {"value": m1 / float(tt), "unit": "points/s", "unknown": m1, "known": n, "seconds": float(tt),
+                                         "h2d_bytes": int(pts.nbytes * world + unk4[:m1].nbytes), "d2h_bytes": int(m1 * 4 * 8 + m1)}
+        del res1
 
-    # CPU restatement of the kriging path on the host cores (bounded sample), for context next to the GPU numbers
-    if rank == 0 and not args.no_extra:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import oracle
-        oracle.set_threads(os.cpu_count() or 1)
-        var = float(np.var(pts[:, 2]))
-        sample = uniform_locations(64 * max(1, oracle.num_threads()), extent=EXTENT, seed=99)
-        t0 = time.perf_counter()
-        oracle.krige(pts, sample, "linear", 0.0, var, 8000.0, 32, "ok")
-        dt = time.perf_counter() - t0
-        extra["cpu_port_kriged_points_per_s_ok_k32"] = {"value": len(sample) / dt, "cores": oracle.num_threads(),
-                                                         "sample": f"{len(sample)} locations against {n} known points in {dt:.1f} s"}
+        # CPU restatement of the kriging path on the host cores (bounded sample), rank 0 only
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle
+            oracle.set_threads(os.cpu_count() or 1)
+            sample = unk4[: 48 * max(1, oracle.num_threads())]
+            t0 = time.perf_counter()
+            oracle.krige(known4, sample, "spherical", 1.0, mdl4["sill"], 20000.0, 64, "ok")
+            oracle.krige(known4, sample, "spherical", 1.0, mdl4["sill"], 20000.0, 64, "sk", process_mean=mean4)
+            dtc = time.perf_counter() - t0
+            kriging["cpu_baseline"] = {"value": len(sample) / dtc, "unit": "points/s (ordinary + simple)", "cores": oracle.num_threads(),
+                                       "kind": "port", "sample": f"{len(sample)} locations against 1M known points, k=64, in {dtc:.1f} s"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -374,10 +475,12 @@ def run_b200(args):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n, world),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 24), "d2h_bytes_per_step": out_bytes},
-                "gpu_launches": 8 * args.steps,
-                "gpu_launches_note": "per step: bbox_partial, curve_key, gather_soa, tile_box, group_sum, item_cost, pair_ring, "
-                                     "reduce_partials (+ CUB radix-sort passes and memsets, not counted)",
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "extra": extra}
+                "gpu_launches": 14 * args.steps,
+                "gpu_launches_note": "per step: bbox_partial, bbox_final, curve_key, gather_soa, tile_box, mean_partial, mean_final, "
+                                     "group_sum, item_cost, pair_ring6, reduce_partials, cancellation_guard, pair_kernel + "
+                                     "reduce_partials (conditional re-run: both return at once unless the guard fired) "
+                                     "(+ CUB radix-sort passes and memsets, not counted)",
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "kriging": kriging, "extra": extra}
     if world > 1:
         dist.destroy_process_group()
     sys.stdout.flush()

@@ -51,6 +51,8 @@ extern "C" {
 
 #define PIB_KRIGE_ORDINARY 0    /* kriging/point/ordinary.py:30-131  (ok_calc)  */
 #define PIB_KRIGE_SIMPLE 1      /* kriging/point/simple.py:26-126    (sk_calc)  */
+#define PIB_KRIGE_BOTH 2        /* both from ONE neighbour search, assembly and elimination: the outputs hold the ordinary-kriging
+                                   block [n_sets][m][..] first, then the simple-kriging block */
 
 /* per-location status written by the kriging entry points */
 #define PIB_STATUS_OK 0
@@ -66,6 +68,9 @@ PIB_API const char *pib_last_error(void);
 PIB_API int pib_version(void);
 /* number of SMs of the current device (grid sizing evidence for callers / tests) */
 PIB_API int pib_device_sm_count(void);
+/* The library takes its scratch from the device's stream-ordered default memory pool and keeps up to 4 GiB of it between
+ * calls; pib_trim() synchronises the device and returns all cached scratch to it. */
+PIB_API int pib_trim(void);
 
 /* ------------------------------------------------------------------------------------------
  * Experimental variogram — one fused pass over point pairs.
@@ -181,9 +186,9 @@ PIB_API int pib_variogram_cloud_host(const double *xyz, int64_t n,
  * model      PIB_MODEL_*; mode PIB_KRIGE_*; process_mean only used by simple kriging
  * k          no_neighbors; the k nearest known points by (distance, index) are used, all n when
  *            n < k (select_points.py:95-101 with use_all_neighbors_in_range=False)
- * out        [n_sets][m][4] rows [zhat, sigma^2 (NaN if negative), x, y]
+ * out        [n_sets][m][4] rows [zhat, sigma^2 (NaN if negative), x, y]   ([2][n_sets][m][4] for PIB_KRIGE_BOTH)
  * nbr_idx    NULL, or [m][k] indices into `known`, ascending distance, -1 padded
- * status     NULL, or [n_sets][m] PIB_STATUS_*
+ * status     NULL, or [n_sets][m] PIB_STATUS_*                               ([2][n_sets][m] for PIB_KRIGE_BOTH)
  * shard: locations are independent, so multi-GPU callers simply pass their own slice of `unknown`.
  * ---------------------------------------------------------------------------------------- */
 PIB_API int pib_krige_device(const double *d_known, int64_t n,
@@ -241,6 +246,10 @@ PIB_API int pib_gamma_host(int model, double nugget, double sill, double rang,
  * 2 assemble+solve kernel.  launches_out (may be NULL) receives how many times it was launched.
  * Synchronises on the recorded events. */
 PIB_API int pib_last_kernel_ms(int which, double *ms_out, int *launches_out);
+
+/* Name of the kernel variant behind pib_last_kernel_ms(which) in the last call (e.g. "pair_ring6_kernel<16,512,1,8>"),
+ * copied into buf (NUL terminated, at most len bytes). */
+PIB_API int pib_last_kernel_name(int which, char *buf, int len);
 
 /* FP64 throughput probe: runs a dependent-chain-free DFMA kernel and returns TFLOP/s
  * (2 flop per DFMA) measured with CUDA events.  Used by bench.py for the roofline

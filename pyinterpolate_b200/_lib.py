@@ -14,13 +14,13 @@ LIB_PATH = os.environ.get("PIB_LIB_PATH") or os.path.join(_HERE, "libpyinterp_b2
 
 MODEL_IDS = {"circular": 0, "cubic": 1, "exponential": 2, "gaussian": 3,
              "linear": 4, "power": 5, "spherical": 6}
-KRIGE_ORDINARY, KRIGE_SIMPLE = 0, 1
+KRIGE_ORDINARY, KRIGE_SIMPLE, KRIGE_BOTH = 0, 1, 2
 STATUS_OK, STATUS_SINGULAR, STATUS_NEGATIVE_VARIANCE = 0, 1, 2
 
 STATUS_TOO_MANY_NEIGHBORS = 3
 STATUS_LSA, STATUS_ZERO_MATRIX = 4, 5
 
-EXPORTS = ("pib_krige_loo_host", "pib_krige_ex_device", "pib_krige_ex_host", "pib_last_error", "pib_version", "pib_device_sm_count", "pib_variogram_device",
+EXPORTS = ("pib_trim", "pib_last_kernel_name", "pib_krige_loo_host", "pib_krige_ex_device", "pib_krige_ex_host", "pib_last_error", "pib_version", "pib_device_sm_count", "pib_variogram_device",
            "pib_variogram_host", "pib_krige_device", "pib_krige_host", "pib_gamma_host",
            "pib_fp64_peak_tflops", "pib_last_kernel_ms", "pib_variogram_cloud_host",
            "pib_variogram_weighted_host", "pib_variogram_triangle_host")
@@ -59,6 +59,7 @@ def load():
     L.pib_gamma_host.argtypes = [i32, f64, f64, f64, dp, i64, dp]
     L.pib_fp64_peak_tflops.argtypes = [dp]
     L.pib_last_kernel_ms.argtypes = [i32, dp, dp]
+    L.pib_last_kernel_name.argtypes = [i32, ctypes.c_char_p, i32]
     L.pib_variogram_cloud_host.argtypes = [dp, i64, dp, dp, i32, dp, i32, dp, dp]
     L.pib_variogram_weighted_host.argtypes = [dp, dp, i64, dp, dp, i32, dp, i32, dp, dp]
     L.pib_variogram_triangle_host.argtypes = [dp, i64, dp, i32, f64, f64, f64, dp, dp]
@@ -181,14 +182,16 @@ def krige_host(known, unknown, model, params, mode, k, process_mean=0.0, values=
     """Host-buffer call. ``params`` is ``[n_sets, 3]`` (nugget, sill, rang).  ``direction`` (degrees) switches to
     the directional neighbour selection within ``neighbors_range``; ``allow_lsa`` solves singular systems by least
     squares (status 4) instead of leaving them marked singular (status 1).
-    Returns (out[n_sets, m, 4], nbr_idx[m, k] or None, status[n_sets, m])."""
+    Returns (out[n_sets, m, 4], nbr_idx[m, k] or None, status[n_sets, m]); with ``mode=KRIGE_BOTH`` the arrays get a
+    leading axis of 2: ordinary kriging first, then simple kriging (one neighbour search and one elimination for both)."""
     L = load()
     known, unknown = _f64(known), _f64(unknown).reshape(-1, 2)
     params = _f64(params).reshape(-1, 3)
     n, m, n_sets = known.shape[0], unknown.shape[0], params.shape[0]
     values_c = None if values is None else _f64(values).reshape(n_sets, n)
-    out = np.zeros((n_sets, m, 4))
-    status = np.zeros((n_sets, m), dtype=np.uint8)
+    lead = (2,) if int(mode) == KRIGE_BOTH else ()
+    out = np.empty(lead + (n_sets, m, 4))
+    status = np.zeros(lead + (n_sets, m), dtype=np.uint8)
     idx = np.full((m, k), -1, dtype=np.int32) if want_neighbors else None
     rc = L.pib_krige_ex_host(_host_ptr(known), n, _host_ptr(values_c), n_sets, _host_ptr(params), _host_ptr(unknown), m,
                              int(model), int(mode), float(process_mean), int(k), float(neighbors_range),
@@ -225,8 +228,9 @@ def krige_device(known_t, unknown_t, model, params, mode, k, process_mean=0.0, v
     params = _f64(params).reshape(-1, 3)
     n, m, n_sets = known_t.shape[0], unknown_t.shape[0], params.shape[0]
     dev = known_t.device
-    out = torch.empty((n_sets, m, 4), dtype=torch.float64, device=dev)
-    status = torch.empty((n_sets, m), dtype=torch.uint8, device=dev) if want_status else None
+    lead = (2,) if int(mode) == KRIGE_BOTH else ()
+    out = torch.empty(lead + (n_sets, m, 4), dtype=torch.float64, device=dev)
+    status = torch.empty(lead + (n_sets, m), dtype=torch.uint8, device=dev) if want_status else None
     idx = torch.empty((m, k), dtype=torch.int32, device=dev) if want_neighbors else None
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
@@ -264,3 +268,16 @@ def last_kernel_ms(which):
     check(L.pib_last_kernel_ms(int(which), ctypes.cast(ctypes.byref(ms), ctypes.c_void_p),
                                ctypes.cast(ctypes.byref(launches), ctypes.c_void_p)), "pib_last_kernel_ms")
     return float(ms.value), int(launches.value)
+
+
+def last_kernel_name(which):
+    """Name of the kernel variant the last library call launched for timing slot ``which``."""
+    L = load()
+    buf = ctypes.create_string_buffer(128)
+    check(L.pib_last_kernel_name(int(which), buf, 128), "pib_last_kernel_name")
+    return buf.value.decode()
+
+
+def trim():
+    """Return the library's cached device scratch to the device (synchronises)."""
+    check(load().pib_trim(), "pib_trim")

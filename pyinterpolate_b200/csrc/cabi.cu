@@ -1,5 +1,9 @@
 // extern "C" surface of libpyinterp_b200.so — see include/pyinterp_b200.h for the contract.
+#include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 
@@ -10,16 +14,23 @@ namespace pib {
 static thread_local std::string g_error;
 void set_error(const std::string &msg) { g_error = msg; }
 
-// keep the stream-ordered pool's memory across synchronisations (the default trims it to zero at
-// every sync, which turns each call's scratch allocation into a driver allocation)
+// Keep the stream-ordered pool's memory across synchronisations (the default trims it to zero at every sync, which
+// turns each call's scratch allocation into a driver allocation) — but only up to a bound, so that the peak scratch of one
+// large call is handed back to the device instead of starving another allocator in the same process (PyTorch's);
+// pib_trim() releases everything at once.
+static std::mutex g_device_mutex;
+static const unsigned long long POOL_KEEP_BYTES = 4ull << 30;
+
 void init_device_pool()
 {
     static bool done[64] = {false};
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    if (done[dev]) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
+        unsigned long long keep = POOL_KEEP_BYTES;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     done[dev] = true;
@@ -27,17 +38,23 @@ void init_device_pool()
 
 int sm_count()
 {
-    static int cached = 0;
-    if (!cached) {
-        int dev = 0, sms = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) {
-            cached = sms;
-        }
-        else
-            return 148;
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    if (!cached[dev]) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
+        cached[dev] = sms;
     }
-    return cached;
+    return cached[dev];
+}
+
+static std::string g_kernel_name[PIB_T_COUNT];
+void set_kernel_name(int which, const char *name)
+{
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    if (which >= 0 && which < PIB_T_COUNT) g_kernel_name[which] = name;
 }
 
 struct Segment { cudaEvent_t a, b; };
@@ -79,7 +96,9 @@ int variogram_triangle_device(const double *d_xyz, int64_t n, const double *tri_
 int krige_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
                  const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
                  double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
-                 const int32_t *d_exclude, double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, cudaStream_t stream);
+                 const int32_t *d_exclude, double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, cudaStream_t stream,
+                 const GridIndex *prebuilt = nullptr);
+int krige_build_index(const double *d_known, int64_t n, Scratch &ws, cudaStream_t stream, GridIndex *out);
 int gamma_device(int model, double nugget, double sill, double rang, const double *d_h, int64_t n, double *d_out,
                  cudaStream_t stream);
 
@@ -106,6 +125,17 @@ extern "C" {
 const char *pib_last_error(void) { return g_error.c_str(); }
 int pib_version(void) { return 100; }
 int pib_device_sm_count(void) { return sm_count(); }
+
+int pib_trim(void)
+{
+    int dev = 0;
+    PIB_CUDA(cudaGetDevice(&dev));
+    PIB_CUDA(cudaDeviceSynchronize());
+    cudaMemPool_t pool;
+    PIB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    PIB_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return PIB_OK;
+}
 
 int pib_variogram_device(const double *d_xyz, int64_t n, const double *edges, const double *lower, int n_lags,
                          const double *W, int n_dirs, int shard_index, int shard_count, double *d_sum_sq,
@@ -275,6 +305,26 @@ int pib_krige_host(const double *known, int64_t n, const double *values, int n_s
                              0.0, 0, 0, out, nbr_idx, status);
 }
 
+// Pinned staging buffers of the chunked host path, kept for the life of the process (one set per calling thread):
+// allocating pinned memory costs milliseconds, far more than a chunk of work.
+struct HostStage {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    ~HostStage() { if (ptr) cudaFreeHost(ptr); }
+    int reserve(size_t want)
+    {
+        if (want <= bytes) return PIB_OK;
+        if (ptr) { cudaFreeHost(ptr); ptr = nullptr; bytes = 0; }
+        PIB_CUDA(cudaMallocHost(&ptr, want));
+        bytes = want;
+        return PIB_OK;
+    }
+};
+
+// Host-buffer kriging: the known points go to the device once, the locations stream through in chunks on TWO lanes
+// (stream + pinned staging each): while lane A computes chunk i, lane B's results of chunk i-1 travel back and the
+// host refills B's input — host<->device copies overlap the kernels instead of bracketing them
+// (reference loop: kriging/point/ordinary.py:205-219; SURVEY.md section 8e asks for per-chunk pipelining).
 int pib_krige_ex_host(const double *known, int64_t n, const double *values, int n_sets, const double *params,
                       const double *unknown, int64_t m, int model, int mode, double process_mean, int k,
                       double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
@@ -282,42 +332,111 @@ int pib_krige_ex_host(const double *known, int64_t n, const double *values, int 
 {
     PIB_CHECK(known && (unknown || m == 0) && (out || m == 0), PIB_ERR_INVALID, "krige: NULL pointer");
     PIB_CHECK(n >= 1 && m >= 0 && k >= 1 && n_sets >= 1, PIB_ERR_INVALID, "krige: need n >= 1, m >= 0, k >= 1");
+    PIB_CHECK(mode == PIB_KRIGE_ORDINARY || mode == PIB_KRIGE_SIMPLE || mode == PIB_KRIGE_BOTH, PIB_ERR_INVALID, "krige: unknown mode");
     if (m == 0) return PIB_OK;
-    cudaStream_t stream;
-    PIB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    int rc;
-    {
-        Scratch ws(stream);
-        double *d_known, *d_values = nullptr, *d_unknown, *d_out;
-        int32_t *d_idx = nullptr;
-        uint8_t *d_status = nullptr;
+    const int n_modes = mode == PIB_KRIGE_BOTH ? 2 : 1;
+    const size_t blocks = (size_t)n_modes * n_sets;               // output blocks of m rows each
+    // chunk: ~1M locations, fewer when the per-location output is wide (indicator kriging) or few locations are asked
+    int64_t chunk = std::max<int64_t>(65536, ((int64_t)1 << 22) / (int64_t)(blocks * 4));
+    const char *chunk_env = std::getenv("PIB_KRIGE_CHUNK");
+    if (chunk_env && std::atoll(chunk_env) > 0) chunk = std::atoll(chunk_env);
+    chunk = std::min(chunk, m);
+    const int n_lanes = m > chunk ? 2 : 1;
+
+    static thread_local HostStage stage[2];
+    const size_t in_bytes = (size_t)chunk * 2 * sizeof(double);
+    const size_t out_bytes = blocks * chunk * 4 * sizeof(double);
+    const size_t idx_bytes = nbr_idx ? (size_t)chunk * k * sizeof(int32_t) : 0;
+    const size_t st_bytes = status ? blocks * chunk : 0;
+    auto align256 = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t lane_bytes = align256(in_bytes) + align256(out_bytes) + align256(idx_bytes) + align256(st_bytes);
+    for (int b = 0; b < n_lanes; ++b) PIB_TRY(stage[b].reserve(lane_bytes));
+
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t index_ready = nullptr;
+    int rc = PIB_OK;
+    for (int b = 0; b < n_lanes && rc == PIB_OK; ++b)
+        if (cudaStreamCreateWithFlags(&s[b], cudaStreamNonBlocking) != cudaSuccess) { set_error("krige: stream creation failed"); rc = PIB_ERR_CUDA; }
+    if (rc == PIB_OK && cudaEventCreateWithFlags(&index_ready, cudaEventDisableTiming) != cudaSuccess) { set_error("krige: event creation failed"); rc = PIB_ERR_CUDA; }
+    if (rc == PIB_OK) {
+        Scratch ws(s[0]);                                         // known points, value columns and the grid index: shared by both lanes
+        double *d_known = nullptr, *d_values = nullptr;
+        GridIndex grid;
         rc = ws.alloc(&d_known, (size_t)n * 3);
-        if (rc == PIB_OK) rc = ws.alloc(&d_unknown, (size_t)m * 2);
-        if (rc == PIB_OK) rc = ws.alloc(&d_out, (size_t)n_sets * m * 4);
         if (rc == PIB_OK && values) rc = ws.alloc(&d_values, (size_t)n_sets * n);
-        if (rc == PIB_OK && nbr_idx) rc = ws.alloc(&d_idx, (size_t)m * k);
-        if (rc == PIB_OK && status) rc = ws.alloc(&d_status, (size_t)n_sets * m);
         cudaError_t e = cudaSuccess;
         if (rc == PIB_OK) {
-            e = cudaMemcpyAsync(d_known, known, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(d_unknown, unknown, sizeof(double) * 2 * m, cudaMemcpyHostToDevice, stream);
-            if (e == cudaSuccess && values)
-                e = cudaMemcpyAsync(d_values, values, sizeof(double) * n_sets * n, cudaMemcpyHostToDevice, stream);
+            e = cudaMemcpyAsync(d_known, known, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s[0]);
+            if (e == cudaSuccess && values) e = cudaMemcpyAsync(d_values, values, sizeof(double) * n_sets * n, cudaMemcpyHostToDevice, s[0]);
             if (e != cudaSuccess) { set_error(std::string("krige: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; }
         }
-        if (rc == PIB_OK)
-            rc = krige_device(d_known, n, d_values, n_sets, params, d_unknown, m, model, mode, process_mean, k,
-                              neighbors_range, direction, max_tick, use_all, allow_lsa, nullptr, d_out, d_idx, d_status, stream);
-        if (rc == PIB_OK) {
-            e = cudaMemcpyAsync(out, d_out, sizeof(double) * 4 * n_sets * m, cudaMemcpyDeviceToHost, stream);
-            if (e == cudaSuccess && nbr_idx) e = cudaMemcpyAsync(nbr_idx, d_idx, sizeof(int32_t) * m * k, cudaMemcpyDeviceToHost, stream);
-            if (e == cudaSuccess && status) e = cudaMemcpyAsync(status, d_status, (size_t)n_sets * m, cudaMemcpyDeviceToHost, stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-            if (e != cudaSuccess) { set_error(std::string("krige: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; }
+        if (rc == PIB_OK) rc = krige_build_index(d_known, n, ws, s[0], &grid);
+        if (rc == PIB_OK && (cudaEventRecord(index_ready, s[0]) != cudaSuccess ||
+                             (n_lanes > 1 && cudaStreamWaitEvent(s[1], index_ready, 0) != cudaSuccess))) {
+            set_error("krige: event failed"); rc = PIB_ERR_CUDA;
         }
+        timing_reset(PIB_T_KNN);
+        timing_reset(PIB_T_SOLVE);
+
+        struct Lane { Scratch *ws = nullptr; double *d_unk = nullptr, *d_out = nullptr; int32_t *d_idx = nullptr; uint8_t *d_st = nullptr;
+                      int64_t begin = -1, count = 0; };
+        Lane lane[2];
+        // copy a finished chunk out of the lane's pinned staging into the caller's arrays
+        auto drain = [&](int b) -> int {
+            Lane &L = lane[b];
+            if (L.begin < 0) return PIB_OK;
+            if (cudaStreamSynchronize(s[b]) != cudaSuccess) { set_error("krige: chunk failed"); return PIB_ERR_CUDA; }
+            char *base = static_cast<char *>(stage[b].ptr);
+            const double *h_out = reinterpret_cast<const double *>(base + align256(in_bytes));
+            for (size_t blk = 0; blk < blocks; ++blk)
+                std::memcpy(out + (blk * (size_t)m + L.begin) * 4, h_out + blk * (size_t)L.count * 4, sizeof(double) * 4 * L.count);
+            if (nbr_idx)
+                std::memcpy(nbr_idx + (size_t)L.begin * k, base + align256(in_bytes) + align256(out_bytes), sizeof(int32_t) * L.count * k);
+            if (status) {
+                const uint8_t *h_st = reinterpret_cast<const uint8_t *>(base + align256(in_bytes) + align256(out_bytes) + align256(idx_bytes));
+                for (size_t blk = 0; blk < blocks; ++blk) std::memcpy(status + blk * (size_t)m + L.begin, h_st + blk * (size_t)L.count, L.count);
+            }
+            delete L.ws; L.ws = nullptr; L.begin = -1;             // the chunk's device buffers go back to the pool (stream ordered)
+            return PIB_OK;
+        };
+        int64_t begin = 0;
+        for (int i = 0; begin < m && rc == PIB_OK; ++i, begin += chunk) {
+            const int b = i % n_lanes;
+            rc = drain(b);
+            if (rc != PIB_OK) break;
+            Lane &L = lane[b];
+            L.begin = begin; L.count = std::min(chunk, m - begin);
+            L.ws = new Scratch(s[b]);
+            rc = L.ws->alloc(&L.d_unk, (size_t)L.count * 2);
+            if (rc == PIB_OK) rc = L.ws->alloc(&L.d_out, blocks * L.count * 4);
+            if (rc == PIB_OK && nbr_idx) rc = L.ws->alloc(&L.d_idx, (size_t)L.count * k);
+            if (rc == PIB_OK && status) rc = L.ws->alloc(&L.d_st, blocks * L.count);
+            if (rc != PIB_OK) break;
+            char *base = static_cast<char *>(stage[b].ptr);
+            std::memcpy(base, unknown + (size_t)begin * 2, sizeof(double) * 2 * L.count);
+            e = cudaMemcpyAsync(L.d_unk, base, sizeof(double) * 2 * L.count, cudaMemcpyHostToDevice, s[b]);
+            if (e != cudaSuccess) { set_error(std::string("krige: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; break; }
+            rc = krige_device(d_known, n, d_values, n_sets, params, L.d_unk, L.count, model, mode, process_mean, k, neighbors_range,
+                              direction, max_tick, use_all, allow_lsa, nullptr, L.d_out, L.d_idx, L.d_st, s[b], &grid);
+            if (rc != PIB_OK) break;
+            e = cudaMemcpyAsync(base + align256(in_bytes), L.d_out, sizeof(double) * 4 * blocks * L.count, cudaMemcpyDeviceToHost, s[b]);
+            if (e == cudaSuccess && nbr_idx)
+                e = cudaMemcpyAsync(base + align256(in_bytes) + align256(out_bytes), L.d_idx, sizeof(int32_t) * L.count * k, cudaMemcpyDeviceToHost, s[b]);
+            if (e == cudaSuccess && status)
+                e = cudaMemcpyAsync(base + align256(in_bytes) + align256(out_bytes) + align256(idx_bytes), L.d_st, blocks * L.count,
+                                    cudaMemcpyDeviceToHost, s[b]);
+            if (e != cudaSuccess) { set_error(std::string("krige: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; break; }
+        }
+        for (int b = 0; b < n_lanes; ++b) {
+            const int r2 = drain(b);
+            if (rc == PIB_OK) rc = r2;
+            if (lane[b].ws) { cudaStreamSynchronize(s[b]); delete lane[b].ws; lane[b].ws = nullptr; }
+        }
+        for (int b = 0; b < n_lanes; ++b) if (s[b]) cudaStreamSynchronize(s[b]);
     }
-    cudaStreamSynchronize(stream);
-    cudaStreamDestroy(stream);
+    if (index_ready) cudaEventDestroy(index_ready);
+    for (int b = 0; b < 2; ++b)
+        if (s[b]) { cudaStreamSynchronize(s[b]); cudaStreamDestroy(s[b]); }
     return rc;
 }
 
@@ -403,6 +522,14 @@ int pib_last_kernel_ms(int which, double *ms_out, int *launches_out)
     }
     *ms_out = total;
     if (launches_out) *launches_out = (int)g_segments[which].size();
+    return PIB_OK;
+}
+
+int pib_last_kernel_name(int which, char *buf, int len)
+{
+    PIB_CHECK(which >= 0 && which < PIB_T_COUNT && buf && len > 0, PIB_ERR_INVALID, "last_kernel_name: bad argument");
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    std::snprintf(buf, (size_t)len, "%s", g_kernel_name[which].c_str());
     return PIB_OK;
 }
 

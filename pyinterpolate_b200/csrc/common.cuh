@@ -71,6 +71,8 @@ enum { PIB_T_PAIR = 0, PIB_T_KNN = 1, PIB_T_SOLVE = 2, PIB_T_COUNT = 3 };
 void timing_reset(int which);
 void timing_begin(int which, cudaStream_t stream);
 void timing_end(int which, cudaStream_t stream);
+// name of the kernel variant the last call launched for a timing slot (bench.py reports it beside the roofline)
+void set_kernel_name(int which, const char *name);
 
 // ---- spatial preprocessing (spatial.cu) --------------------------------------------------
 // Morton-ordered structure-of-arrays copy of the points, padded to a multiple of `pad_to`
@@ -82,7 +84,11 @@ struct SortedPoints {
     int32_t *orig = nullptr;                           // [n_pad] original row, -1 for padding
     double4 *tile_box = nullptr;                       // [n_pad / tile]  (xmin, ymin, xmax, ymax)
     int tile = 0;
-    double box[4] = {0, 0, 0, 0};                      // xmin, ymin, xmax, ymax of all points
+    double4 *d_box = nullptr;                          // xmin, ymin, xmax, ymax of all points (device)
+    double box[4] = {0, 0, 0, 0};                      // the same on the host — valid after wait_box()
+    double *h_box = nullptr;
+    cudaEvent_t box_ready = nullptr;
+    int wait_box();                                    // waits for the host copy of the box; checks that it is finite
 };
 int build_sorted_points(const double *d_xyz, int64_t n, int tile, int pad_to, Scratch &ws,
                         cudaStream_t stream, SortedPoints *out);

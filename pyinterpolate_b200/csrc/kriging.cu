@@ -492,6 +492,8 @@ struct SolveParams {
     int warps;                  // warps per CTA
     int stride;                 // row stride of the augmented matrix in doubles (odd)
     const int32_t *nbr_count;   // NULL, or [count] neighbours actually selected (<= kk; directional selection)
+    int only_status;            // 0: every system; else only the (set, location) entries whose status byte equals it
+    size_t mode_stride;         // PIB_KRIGE_BOTH: offset (in systems) of the simple-kriging block behind the ordinary one
 };
 
 // per-warp shared memory: A[dim][stride] | rhs0[dim] | dinv[dim] | nx[kk] ny[kk] nd[kk] | npos[kk] (int)
@@ -520,7 +522,8 @@ __global__ void solve_kernel(const SolveParams p)
 
     const int32_t q = p.order[slot];
     const double ux = p.unknown[2 * (int64_t)q], uy = p.unknown[2 * (int64_t)q + 1];
-    const int kk = p.nbr_count ? p.nbr_count[slot] : kmax;      // neighbours of THIS location
+    // a non-finite location has no neighbours (every candidate distance is NaN): same NaN row as an empty selection
+    const int kk = !(isfinite(ux) && isfinite(uy)) ? 0 : p.nbr_count ? p.nbr_count[slot] : kmax;      // neighbours of THIS location
     const int dim = (mode == PIB_KRIGE_ORDINARY) ? kk + 1 : kk;
     if (kk <= 0) {                       // 0: no neighbour qualified, the reference kriges a NaN row; -1: too many
         if (lane == 0)
@@ -541,6 +544,7 @@ __global__ void solve_kernel(const SolveParams p)
     __syncwarp();
 
     for (int set = 0; set < p.n_sets; ++set) {
+        if (p.only_status && p.status[(size_t)set * p.m + q] != p.only_status) continue;     // warp-uniform
         const double nugget = p.params[3 * set], sill = p.params[3 * set + 1], rang = p.params[3 * set + 2];
         // ---- assemble [Gamma 1; 1^T 0 | k 1] in the reference's row order (ordinary.py:108-115) ----
         bool dup = false;
@@ -700,10 +704,10 @@ __global__ void __launch_bounds__(solve_reg_threads<K>(), solve_reg_min_ctas<K>(
     if (slot >= p.count) return;                   // whole systems leave together (barriers are per system)
     RegSysSmem<K, ORD> &S = smem[sid];
     const GridIndex &g = p.g;
-    const int kk = p.nbr_count ? p.nbr_count[slot] : p.kk;      // neighbours of THIS location (<= p.kk <= K)
-
     const int32_t q = p.order[slot];
     const double ux = p.unknown[2 * (int64_t)q], uy = p.unknown[2 * (int64_t)q + 1];
+    // neighbours of THIS location (<= p.kk <= K); a non-finite location has none (every candidate distance is NaN)
+    const int kk = !(isfinite(ux) && isfinite(uy)) ? 0 : p.nbr_count ? p.nbr_count[slot] : p.kk;
     if (kk <= 0) {                       // 0: no neighbour qualified, the reference kriges a NaN row; -1: too many
         if (t == 0)
             for (int set = 0; set < p.n_sets; ++set) {
@@ -730,6 +734,7 @@ __global__ void __launch_bounds__(solve_reg_threads<K>(), solve_reg_min_ctas<K>(
     const double2 me = (t < K) ? S.nxy[t] : make_double2(0.0, 0.0);
 
     for (int set = 0; set < p.n_sets; ++set) {
+        if (p.only_status && p.status[(size_t)set * p.m + q] != p.only_status) continue;     // uniform over the system
         const double nugget = p.params[3 * set], sill = p.params[3 * set + 1], rang = p.params[3 * set + 2];
         // ---- my row of [Gamma | 1 | k] (ordinary.py:108-115 row order: neighbours by ascending distance) ----
         // Gamma is symmetric: thread t evaluates the K/2 entries (t, t+1 .. t+K/2) cyclically and writes both
@@ -920,6 +925,269 @@ static int launch_solve_reg(const SolveParams &sp, int mode, cudaStream_t stream
     }
     PIB_CUDA(cudaGetLastError());
     return PIB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gauss-Jordan solver on Gamma alone (k <= 64) — the default.
+//
+// solve_reg_kernel spends ~250 warp instructions per elimination step, 200 of them bookkeeping on one dependent
+// chain (two barriers, the ones border kept in shared memory, reciprocal and pivot exchange after the barrier), and
+// needs a 65-step back substitution: 5.5 % of the FP64 peak at k = 64 (profiles/r1_kriging_kernels_ncu_full.md).
+// Here the same data layout (ONE THREAD OWNS ONE ROW in registers, fully unrolled) runs a leaner recurrence:
+//   * Gamma only, two right-hand sides.  The ordinary system [Gamma 1; 1^T 0][w; mu] = [g0; 1] (ordinary.py:108-123) is
+//     solved through its Schur complement: Gamma u = g0, Gamma v = 1, mu = (1^T u - 1) / (1^T v), w = u - mu v.
+//     Simple kriging (simple.py:102-118) IS Gamma w = g0.  One elimination therefore serves ordinary kriging, simple
+//     kriging, or both at once (PIB_KRIGE_BOTH: BASELINE config 4 asks for both).
+//   * Gauss-Jordan with partial pivoting: retired rows keep eliminating, so the solution is rhs / pivot per row and
+//     there is no back substitution.  In this layout that is free — the retired rows executed the DFMAs of every
+//     step anyway (with a zero multiplier, to avoid divergence).
+//   * ONE barrier per column: every warp publishes its own best candidate row (with |pivot| and the reciprocal,
+//     computed by the row's owner BEFORE the barrier) into a double-buffered slot; after the barrier every thread
+//     picks the winner from two loads.
+// The pivot order is dgetf2's (largest |a|, lowest row on ties) applied to Gamma; results agree with the reference's
+// bordered LU to rounding (checked against the fixtures at 1e-9).  Systems this route cannot decide — Gamma singular
+// although the bordered matrix may not be (k = 1 with a zero nugget), 1^T v = 0 — are marked PIB_STATUS_RETRY and
+// re-solved by solve_reg_kernel on the bordered matrix.
+// ---------------------------------------------------------------------------------------------
+#define PIB_STATUS_RETRY 255
+
+template <int K>
+struct GjSmem {
+    static constexpr int W = (K < 32 ? 32 : K) / 32;
+    static constexpr int CS = K + 6;                       // candidate slot: row[K], rhs0, rhs1, |pivot|, 1/pivot, row id
+    // Gamma (row stride K + 2: 16-byte aligned rows, conflict-free LDS.128 by row) is only needed until every thread
+    // has its row in registers; the candidate slots reuse the same memory afterwards
+    double G[K * (K + 2) > 2 * W * CS ? K * (K + 2) : 2 * W * CS];
+    double2 nxy[K];
+    double g0[K];                                          // gamma(distance to the location) per neighbour
+    double zv[K];                                          // neighbour values of the current set
+    double red[4 * W];
+    int dup;
+};
+
+template <int K>
+__host__ __device__ constexpr int gj_threads() { return K == 64 ? 384 : 256; }
+
+template <int K, int MODE>      // MODE: PIB_KRIGE_ORDINARY, PIB_KRIGE_SIMPLE or PIB_KRIGE_BOTH
+__global__ void __launch_bounds__(gj_threads<K>(), K == 32 ? 2 : 1) solve_gj_kernel(const SolveParams p)
+{
+    constexpr int TPS = K < 32 ? 32 : K;          // threads per system
+    constexpr int SPC = gj_threads<K>() / TPS;    // systems per CTA
+    constexpr int WARPS = TPS / 32;
+    constexpr int CS = GjSmem<K>::CS;
+    constexpr bool WANT_OK = MODE != PIB_KRIGE_SIMPLE, WANT_SK = MODE != PIB_KRIGE_ORDINARY;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GjSmem<K> *smem = reinterpret_cast<GjSmem<K> *>(smem_raw);
+    const int sid = threadIdx.x / TPS, t = threadIdx.x % TPS, lane = threadIdx.x & 31, wis = t >> 5;
+    const int64_t slot = (int64_t)blockIdx.x * SPC + sid;
+    if (slot >= p.count) return;                   // whole systems leave together (barriers are per system)
+    GjSmem<K> &S = smem[sid];
+    const GridIndex &g = p.g;
+    const int32_t q = p.order[slot];
+    const double ux = p.unknown[2 * (int64_t)q], uy = p.unknown[2 * (int64_t)q + 1];
+    // neighbours of THIS location (<= p.kk <= K); a non-finite location has none (every candidate distance is NaN)
+    const int kk = !(isfinite(ux) && isfinite(uy)) ? 0 : p.nbr_count ? p.nbr_count[slot] : p.kk;
+    const size_t sk_off = MODE == PIB_KRIGE_BOTH ? p.mode_stride : 0;       // where the simple-kriging rows go
+    if (kk <= 1) {
+        // 0 / -1: no (too many) neighbours; 1: Gamma = [gamma(0)] may be singular although the bordered matrix is not —
+        // all of them go to the bordered solver
+        if (t == 0)
+            for (int set = 0; set < p.n_sets; ++set) {
+                if (WANT_OK) p.status[(size_t)set * p.m + q] = PIB_STATUS_RETRY;
+                if (WANT_SK) p.status[sk_off + (size_t)set * p.m + q] = PIB_STATUS_RETRY;
+            }
+        return;
+    }
+    int my_pos = -1;
+    double my_d = 0.0;
+    if (t < kk) {
+        my_pos = p.nbr_pos[slot * p.kk + t];
+        my_d = p.nbr_d[slot * p.kk + t];
+        S.nxy[t] = make_double2(g.x[my_pos], g.y[my_pos]);
+    } else if (t < K) {
+        S.nxy[t] = make_double2(0.0, 0.0);
+    }
+    if (t == 0) S.dup = 0;
+    sys_sync<TPS>(sid);
+    const double2 me = (t < K) ? S.nxy[t] : make_double2(0.0, 0.0);
+
+    for (int set = 0; set < p.n_sets; ++set) {
+        const double nugget = p.params[3 * set], sill = p.params[3 * set + 1], rang = p.params[3 * set + 2];
+        // ---- Gamma, every entry evaluated once: thread t takes (t, t+1 .. t+K/2) cyclically and writes both halves ----
+        if (t < K) {
+            for (int i = 0; i < K / 2; ++i) {
+                int c = t + 1 + i;
+                if (c >= K) c -= K;
+                double v;
+                if (t < kk && c < kk) {
+                    const double2 o = S.nxy[c];
+                    const double dx = __dsub_rn(me.x, o.x), dy = __dsub_rn(me.y, o.y);
+                    const double h = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                    if (h == 0.0) S.dup = 1;
+                    v = gamma_model(p.model, h, nugget, sill, rang);
+                } else v = 0.0;                                                 // identity padding (off diagonal)
+                S.G[t * (K + 2) + c] = v;
+                S.G[c * (K + 2) + t] = v;
+            }
+            S.G[t * (K + 2) + t] = (t < kk) ? nugget : 1.0;                     // gamma(0) / identity padding
+            const double kv = (t < kk) ? gamma_model(p.model, my_d, nugget, sill, rang) : 0.0;
+            S.g0[t] = kv;
+            double zv = 0.0;
+            if (t < kk) zv = p.values ? p.values[(size_t)set * p.n + g.orig[my_pos]] : g.z[my_pos];
+            S.zv[t] = zv;
+        }
+        sys_sync<TPS>(sid);
+        double a[K];
+#pragma unroll
+        for (int c = 0; c < K; c += 2) {
+            const double2 v = (t < K) ? *reinterpret_cast<const double2 *>(&S.G[t * (K + 2) + c]) : make_double2(0.0, 0.0);
+            a[c] = v.x; a[c + 1] = v.y;
+        }
+        double r0 = (t < K) ? S.g0[t] : 0.0;                                    // right-hand side g0
+        double r1 = (WANT_OK && t < kk) ? 1.0 : 0.0;                            // right-hand side 1 (ordinary kriging)
+        bool active = (t < K);
+        int my_step = -1;
+        double my_inv = 0.0;
+        // two identical rows: singular in exact arithmetic.  LAPACK only notices when rounding happens to leave an
+        // exact zero pivot (about half of such systems with OpenBLAS, garbage for the rest); here it is always caught
+        const bool dup = S.dup != 0;
+        bool singular = false;
+        sys_sync<TPS>(sid);                                                     // G is dead: the candidate slots take its place
+        double *const cand = S.G;
+
+        if (!dup) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                // ---- my warp's candidate for column j: largest |a[j]| among its rows not yet used, lowest row on ties ----
+                const double av = fabs(a[j]);
+                // |v| >= 0, so the fp64 order is the order of the bit pattern: high words first (inactive rows 0, NaN on top)
+                const unsigned hi = active ? (unsigned)__double2hiint(av) + 1u : 0u;
+                const unsigned hmax = __reduce_max_sync(0xffffffffu, hi);
+                unsigned lead = __ballot_sync(0xffffffffu, hi == hmax);
+                if (__popc(lead) > 1 && hmax != 0u) {                           // rare: equal high words, look at the low words
+                    const unsigned lo = (hi == hmax) ? (unsigned)__double2loint(av) : 0u;
+                    const unsigned lmax = __reduce_max_sync(0xffffffffu, lo);
+                    lead = __ballot_sync(0xffffffffu, hi == hmax && lo == lmax);
+                }
+                const int src = __ffs(lead) - 1;
+                double *const C = cand + ((j & 1) * WARPS + wis) * CS;
+                if (lane == src) {
+#pragma unroll
+                    for (int c = 0; c < K; ++c)
+                        if (c > j) C[c] = a[c];
+                    C[K] = r0; C[K + 1] = r1;
+                    C[K + 2] = hmax ? av : -1.0;
+                    C[K + 3] = __drcp_rn(a[j]);                                 // dgetf2 scales by the reciprocal of the pivot
+                    reinterpret_cast<int *>(C + K + 4)[0] = t;
+                }
+                sys_sync<TPS>(sid);
+                // ---- the winner among the warps' candidates (rows of warp 0 come first: it wins ties) ----
+                const double *P = cand + ((j & 1) * WARPS) * CS;
+                double pv = P[K + 2];
+                if (WARPS > 1) {
+#pragma unroll
+                    for (int w = 1; w < WARPS; ++w) {
+                        const double *Pw = cand + ((j & 1) * WARPS + w) * CS;
+                        const double ov = Pw[K + 2];
+                        if (ov > pv || (ov != ov && pv == pv)) { pv = ov; P = Pw; }
+                    }
+                }
+                if (!(pv > 0.0) || isinf(pv)) { singular = true; break; }       // zero / NaN pivot column (uniform over the system)
+                const double inv = P[K + 3];
+                const bool is_p = (t == reinterpret_cast<const int *>(P + K + 4)[0]);
+                if (is_p) { active = false; my_step = j; my_inv = inv; }
+                // Gauss-Jordan: EVERY other row eliminates column j, the rows already used included
+                const double l = is_p ? 0.0 : a[j] * inv;
+#pragma unroll
+                for (int c = 0; c < K; ++c)
+                    if (c > j) a[c] = __fma_rn(-l, P[c], a[c]);
+                r0 = __fma_rn(-l, P[K], r0);
+                if (WANT_OK) r1 = __fma_rn(-l, P[K + 1], r1);
+            }
+        }
+        sys_sync<TPS>(sid);
+
+        // ---- solution: row t was the pivot of column my_step, so u[my_step] = r0 / pivot, v[my_step] = r1 / pivot ----
+        const bool real = (my_step >= 0 && my_step < kk);
+        const double u = real ? r0 * my_inv : 0.0, v = real ? r1 * my_inv : 0.0;
+        const double zn = real ? S.zv[my_step] : 0.0, gn = real ? S.g0[my_step] : 0.0;
+        // sums over the system: 1^T u, 1^T v, u.z, v.z, u.g0, v.g0
+        double s[6] = {u, v, u * zn, v * zn, u * gn, v * gn};
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+        if (WARPS > 1) {
+            double *red = cand + 2 * WARPS * CS;                                // behind the candidate slots (G is larger)
+            if (lane == 0)
+#pragma unroll
+                for (int i = 0; i < 6; ++i) red[wis * 6 + i] = s[i];
+            sys_sync<TPS>(sid);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double acc = red[i];
+#pragma unroll
+                for (int w = 1; w < WARPS; ++w) acc += red[w * 6 + i];
+                s[i] = acc;
+            }
+        }
+        if (t == 0) {
+            if (WANT_OK) {
+                // mu = (1^T u - 1) / (1^T v), w = u - mu v:  zhat = w.z (ordinary.py:121), sigma^2 = w.g0 + mu (:123)
+                double zhat = nan(""), sigma = nan("");
+                uint8_t stat = PIB_STATUS_SINGULAR;
+                if (!dup) {
+                    const double mu = (s[0] - 1.0) / s[1];
+                    if (singular || !(fabs(s[1]) > 0.0) || !isfinite(mu)) stat = PIB_STATUS_RETRY;       // decide on the bordered matrix
+                    else {
+                        zhat = s[2] - mu * s[3];
+                        sigma = (s[4] - mu * s[5]) + mu;
+                        stat = PIB_STATUS_OK;
+                        if (sigma < 0.0) { sigma = nan(""); stat = PIB_STATUS_NEGATIVE_VARIANCE; }       // ordinary.py:125-126
+                    }
+                }
+                double *o = p.out + ((size_t)set * p.m + q) * 4;
+                o[0] = zhat; o[1] = sigma; o[2] = ux; o[3] = uy;
+                p.status[(size_t)set * p.m + q] = stat;
+            }
+            if (WANT_SK) {
+                // w = u:  zhat = (z - mean).w + mean (simple.py:114-116), sigma^2 = w.g0 (:118)
+                double zhat = nan(""), sigma = nan("");
+                uint8_t stat = PIB_STATUS_SINGULAR;
+                if (!dup && !singular) {
+                    zhat = (s[2] - p.process_mean * s[0]) + p.process_mean;
+                    sigma = s[4];
+                    stat = PIB_STATUS_OK;
+                    if (sigma < 0.0) { sigma = nan(""); stat = PIB_STATUS_NEGATIVE_VARIANCE; }
+                }
+                double *o = p.out + (sk_off + (size_t)set * p.m + q) * 4;
+                o[0] = zhat; o[1] = sigma; o[2] = ux; o[3] = uy;
+                p.status[sk_off + (size_t)set * p.m + q] = stat;
+            }
+        }
+        sys_sync<TPS>(sid);
+    }
+}
+
+template <int K, int MODE>
+static int launch_solve_gj_m(const SolveParams &sp, cudaStream_t stream)
+{
+    constexpr int NT = gj_threads<K>();
+    constexpr int SPC = NT / (K < 32 ? 32 : K);
+    const int grid = (int)((sp.count + SPC - 1) / SPC);
+    const size_t bytes = sizeof(GjSmem<K>) * SPC;
+    PIB_CUDA(cudaFuncSetAttribute(solve_gj_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    solve_gj_kernel<K, MODE><<<grid, NT, bytes, stream>>>(sp);
+    PIB_CUDA(cudaGetLastError());
+    return PIB_OK;
+}
+
+template <int K>
+static int launch_solve_gj(const SolveParams &sp, int mode, cudaStream_t stream)
+{
+    if (mode == PIB_KRIGE_ORDINARY) return launch_solve_gj_m<K, PIB_KRIGE_ORDINARY>(sp, stream);
+    if (mode == PIB_KRIGE_SIMPLE) return launch_solve_gj_m<K, PIB_KRIGE_SIMPLE>(sp, stream);
+    return launch_solve_gj_m<K, PIB_KRIGE_BOTH>(sp, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1120,7 +1388,8 @@ __global__ void __launch_bounds__(32) singular_kernel(const SingularParams sp)
 int krige_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
                  const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
                  double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
-                 const int32_t *d_exclude, double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, cudaStream_t stream)
+                 const int32_t *d_exclude, double *d_out, int32_t *d_nbr_idx, uint8_t *d_status, cudaStream_t stream,
+                 const GridIndex *prebuilt)
 {
     const bool directional = !std::isnan(direction);
     const bool ranged = directional || use_all;                 // the selection depends on neighbors_range
@@ -1129,7 +1398,8 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
     PIB_CHECK(n >= 1 && m >= 0 && k >= 1, PIB_ERR_INVALID, "krige: need n >= 1, m >= 0, k >= 1");
     PIB_CHECK(n_sets >= 1 && params != nullptr, PIB_ERR_INVALID, "krige: need at least one parameter set");
     PIB_CHECK(model >= 0 && model <= 6, PIB_ERR_INVALID, "krige: unknown model id");
-    PIB_CHECK(mode == PIB_KRIGE_ORDINARY || mode == PIB_KRIGE_SIMPLE, PIB_ERR_INVALID, "krige: unknown mode");
+    PIB_CHECK(mode == PIB_KRIGE_ORDINARY || mode == PIB_KRIGE_SIMPLE || mode == PIB_KRIGE_BOTH, PIB_ERR_INVALID,
+              "krige: unknown mode");
     PIB_CHECK(m < ((int64_t)1 << 31) && n < ((int64_t)1 << 31), PIB_ERR_UNSUPPORTED, "krige: more than 2^31-1 rows");
     PIB_CHECK(std::min<int64_t>(k, n) <= MAX_K, PIB_ERR_UNSUPPORTED, "krige: no_neighbors above 128 is not supported");
     const int64_t n_avail = d_exclude ? n - 1 : n;              // leave-one-out: every location loses one row
@@ -1140,13 +1410,16 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
         last_tol = std::max(2, (int)std::floor(max_tick) + 1);   // 1, 2, ... until the tolerance exceeds max_tick
         PIB_CHECK(last_tol <= MAX_TOL, PIB_ERR_UNSUPPORTED, "krige: max_tick above 63 degrees is not supported");
     }
-    timing_reset(PIB_T_KNN);
-    timing_reset(PIB_T_SOLVE);
+    if (!prebuilt) {                   // (a chunked host call accumulates the kernel times of all its chunks)
+        timing_reset(PIB_T_KNN);
+        timing_reset(PIB_T_SOLVE);
+    }
     if (m == 0) return PIB_OK;
 
     Scratch ws(stream);
     GridIndex g;
-    PIB_TRY(build_grid_index(d_known, n, 4.0, ws, stream, &g));
+    if (prebuilt) g = *prebuilt;
+    else PIB_TRY(build_grid_index(d_known, n, 4.0, ws, stream, &g));
     int32_t *order;
     PIB_TRY(sort_queries_by_cell(d_unknown, m, g, ws, stream, &order));
     double *d_params;
@@ -1159,9 +1432,11 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
     int r0 = (int)std::ceil(std::sqrt(1.3 * kk / (3.14159265358979 * std::max(per_cell, 1e-9))));
     r0 = std::max(1, std::min(r0, std::max(g.gx, g.gy)));
 
-    const int dim = (mode == PIB_KRIGE_ORDINARY) ? kk + 1 : kk;
+    const int dim = (mode != PIB_KRIGE_SIMPLE) ? kk + 1 : kk;           // the old solvers' (bordered) system; BOTH: the larger one
     const int stride = (dim + 1) | 1;
     const size_t per_warp = solve_smem_per_warp(kk, dim, stride);
+    const int n_modes = mode == PIB_KRIGE_BOTH ? 2 : 1;
+    const size_t mode_stride = (size_t)n_sets * m;                        // BOTH: the simple-kriging block follows the ordinary one
     int solve_warps = (int)std::min<size_t>(8, (size_t)(MAX_SMEM_K - 1024) / per_warp);
     PIB_CHECK(solve_warps >= 1, PIB_ERR_UNSUPPORTED, "krige: system does not fit in shared memory");
     PIB_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * solve_warps)));
@@ -1175,6 +1450,8 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
 
     const char *force_smem = std::getenv("PIB_FORCE_SMEM_SOLVE");
     const bool use_reg = kk <= 64 && !(force_smem && force_smem[0] == '1');
+    const char *solve_env = std::getenv("PIB_SOLVE_V");              // "1": the round-1 bordered LU instead of Gauss-Jordan
+    const bool use_gj = use_reg && !(solve_env && solve_env[0] == '1');
     const int64_t chunk = std::min<int64_t>(m, (int64_t)1 << 21);
     int32_t *nbr_pos;
     double *nbr_d;
@@ -1184,7 +1461,7 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
     if (ranged) PIB_TRY(ws.alloc(&nbr_count, (size_t)chunk));
     const int ksel = (int)std::min<int64_t>(k, n_avail);        // what the plain k-nearest search selects
     if (!d_status) {                                            // the singular-system pass needs the status bytes
-        PIB_TRY(ws.alloc(&d_status, (size_t)n_sets * m));
+        PIB_TRY(ws.alloc(&d_status, (size_t)n_modes * n_sets * m));
     }
     // singular-system pass: one warp per CTA; V next to A in shared memory when both fit, else in global scratch
     const size_t mat_bytes = (size_t)dim * stride * 8;
@@ -1225,19 +1502,42 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
         sp.nbr_pos = nbr_pos; sp.nbr_d = nbr_d; sp.values = d_values; sp.params = d_params; sp.n_sets = n_sets;
         sp.model = model; sp.mode = mode; sp.process_mean = process_mean; sp.out = d_out; sp.status = d_status;
         sp.warps = solve_warps; sp.stride = stride; sp.nbr_count = nbr_count;
+        sp.only_status = 0; sp.mode_stride = mode_stride;
         timing_begin(PIB_T_SOLVE, stream);
         int rc = PIB_OK;
-        if (use_reg && kk <= 8) rc = launch_solve_reg<8>(sp, mode, stream);
-        else if (use_reg && kk <= 16) rc = launch_solve_reg<16>(sp, mode, stream);
-        else if (use_reg && kk <= 32) rc = launch_solve_reg<32>(sp, mode, stream);
-        else if (use_reg && kk <= 64) rc = launch_solve_reg<64>(sp, mode, stream);
-        else {
-            solve_kernel<<<(int)((count + solve_warps - 1) / solve_warps), solve_warps * 32, per_warp * solve_warps, stream>>>(sp);
-            if (cudaGetLastError() != cudaSuccess) { set_error("solve_kernel launch failed"); rc = PIB_ERR_CUDA; }
+        // the round-1 solvers on the bordered matrix, one kriging mode at a time (`only` = just the flagged systems)
+        auto bordered = [&](int one_mode, int only) -> int {
+            SolveParams so = sp;
+            so.mode = one_mode; so.only_status = only;
+            if (mode == PIB_KRIGE_BOTH && one_mode == PIB_KRIGE_SIMPLE) { so.out = d_out + mode_stride * 4; so.status = d_status + mode_stride; }
+            if (use_reg && kk <= 8) return launch_solve_reg<8>(so, one_mode, stream);
+            if (use_reg && kk <= 16) return launch_solve_reg<16>(so, one_mode, stream);
+            if (use_reg && kk <= 32) return launch_solve_reg<32>(so, one_mode, stream);
+            if (use_reg && kk <= 64) return launch_solve_reg<64>(so, one_mode, stream);
+            // shared-memory solver: the layout is sized for the larger (ordinary) system when both modes run
+            solve_kernel<<<(int)((count + solve_warps - 1) / solve_warps), solve_warps * 32, per_warp * solve_warps, stream>>>(so);
+            if (cudaGetLastError() != cudaSuccess) { set_error("solve_kernel launch failed"); return PIB_ERR_CUDA; }
+            return PIB_OK;
+        };
+        set_kernel_name(PIB_T_SOLVE, use_gj ? "solve_gj_kernel" : use_reg ? "solve_reg_kernel" : "solve_kernel");
+        if (use_gj) {
+            if (kk <= 8) rc = launch_solve_gj<8>(sp, mode, stream);
+            else if (kk <= 16) rc = launch_solve_gj<16>(sp, mode, stream);
+            else if (kk <= 32) rc = launch_solve_gj<32>(sp, mode, stream);
+            else rc = launch_solve_gj<64>(sp, mode, stream);
+            // systems Gauss-Jordan on Gamma could not decide (marked PIB_STATUS_RETRY): bordered LU; returns at once otherwise
+            if (rc == PIB_OK && mode != PIB_KRIGE_SIMPLE) rc = bordered(PIB_KRIGE_ORDINARY, PIB_STATUS_RETRY);
+            if (rc == PIB_OK && mode != PIB_KRIGE_ORDINARY) rc = bordered(PIB_KRIGE_SIMPLE, PIB_STATUS_RETRY);
+        } else {
+            if (mode != PIB_KRIGE_SIMPLE) rc = bordered(PIB_KRIGE_ORDINARY, 0);
+            if (rc == PIB_OK && mode != PIB_KRIGE_ORDINARY) rc = bordered(PIB_KRIGE_SIMPLE, 0);
         }
-        if (rc == PIB_OK) {
+        for (int one = 0; one < 2 && rc == PIB_OK; ++one) {
+            const int one_mode = one == 0 ? PIB_KRIGE_ORDINARY : PIB_KRIGE_SIMPLE;
+            if (mode != PIB_KRIGE_BOTH && mode != one_mode) continue;
             SingularParams sg;
-            sg.s = sp; sg.s.status = d_status; sg.allow_lsa = allow_lsa; sg.vglobal = vglobal;
+            sg.s = sp; sg.s.mode = one_mode; sg.allow_lsa = allow_lsa; sg.vglobal = vglobal;
+            if (mode == PIB_KRIGE_BOTH && one_mode == PIB_KRIGE_SIMPLE) { sg.s.out = d_out + mode_stride * 4; sg.s.status = d_status + mode_stride; }
             singular_kernel<<<sing_grid, 32, sing_smem, stream>>>(sg);
             if (cudaGetLastError() != cudaSuccess) { set_error("singular_kernel launch failed"); rc = PIB_ERR_CUDA; }
         }
@@ -1256,4 +1556,13 @@ int gamma_device(int model, double nugget, double sill, double rang, const doubl
     return PIB_OK;
 }
 
+}  // namespace pib
+
+namespace pib {
+// the grid index of the known points alone (a chunked host call builds it once and hands it to krige_device per chunk)
+int krige_build_index(const double *d_known, int64_t n, Scratch &ws, cudaStream_t stream, GridIndex *out)
+{
+    PIB_CHECK(n >= 1 && n < ((int64_t)1 << 31), PIB_ERR_INVALID, "krige: need 1 <= n < 2^31 known points");
+    return build_grid_index(d_known, n, 4.0, ws, stream, out);
+}
 }  // namespace pib

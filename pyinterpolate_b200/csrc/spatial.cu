@@ -45,6 +45,35 @@ __global__ void bbox_partial_kernel(const double *__restrict__ pts, int64_t n, i
     }
 }
 
+__global__ void __launch_bounds__(32) bbox_final_kernel(const double4 *__restrict__ partial, int n_partial, double4 *__restrict__ box)
+{
+    double xmin = INFINITY, ymin = INFINITY, xmax = -INFINITY, ymax = -INFINITY;
+    for (int i = threadIdx.x; i < n_partial; i += 32) {
+        const double4 p = partial[i];
+        xmin = fmin(xmin, p.x); ymin = fmin(ymin, p.y); xmax = fmax(xmax, p.z); ymax = fmax(ymax, p.w);
+    }
+    for (int o = 16; o; o >>= 1) {
+        xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    if (threadIdx.x == 0) *box = make_double4(xmin, ymin, xmax, ymax);
+}
+
+// bounding box left on the device (no host round trip): the variogram path only needs it to scale the curve keys
+static int bounding_box_device(const double *d_pts, int64_t n, int stride, Scratch &ws, cudaStream_t stream, double4 **d_box)
+{
+    const int blocks = (int)std::min<int64_t>(296, (n + 255) / 256);
+    double4 *d_partial;
+    PIB_TRY(ws.alloc(&d_partial, blocks));
+    PIB_TRY(ws.alloc(d_box, 1));
+    bbox_partial_kernel<<<blocks, 256, 0, stream>>>(d_pts, n, stride, d_partial);
+    bbox_final_kernel<<<1, 32, 0, stream>>>(d_partial, blocks, *d_box);
+    PIB_CUDA(cudaGetLastError());
+    return PIB_OK;
+}
+
 static int bounding_box(const double *d_pts, int64_t n, int stride, Scratch &ws, cudaStream_t stream,
                         double box[4])
 {
@@ -84,11 +113,14 @@ static __device__ __forceinline__ uint32_t hilbert16(uint32_t x, uint32_t y)
     return d;
 }
 
-__global__ void curve_key_kernel(const double *__restrict__ xyz, int64_t n, double x0, double y0,
-                                  double scale, uint32_t *__restrict__ keys, int32_t *__restrict__ vals)
+__global__ void curve_key_kernel(const double *__restrict__ xyz, int64_t n, const double4 *__restrict__ box,
+                                  uint32_t *__restrict__ keys, int32_t *__restrict__ vals)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const double4 b = *box;
+    const double x0 = b.x, y0 = b.y, extent = fmax(b.z - b.x, b.w - b.y);
+    const double scale = extent > 0 ? 65535.999 / extent : 0.0;
     const int ix = clampi((int)((xyz[3 * i] - x0) * scale), 0, 65535);
     const int iy = clampi((int)((xyz[3 * i + 1] - y0) * scale), 0, 65535);
     keys[i] = hilbert16((uint32_t)ix, (uint32_t)iy);
@@ -163,23 +195,29 @@ int sort_pairs_u32(const uint32_t *keys_in, uint32_t *keys_out, const int32_t *v
 int build_sorted_points(const double *d_xyz, int64_t n, int tile, int pad_to, Scratch &ws,
                         cudaStream_t stream, SortedPoints *out)
 {
-    double box[4];
-    PIB_TRY(bounding_box(d_xyz, n, 3, ws, stream, box));
-    const double extent = std::max(box[2] - box[0], box[3] - box[1]);
-    const double scale = extent > 0 ? 65535.999 / extent : 0.0;
+    // the bounding box stays on the device (the keys are scaled there); a copy travels to a pinned host slot behind an
+    // event, and SortedPoints::wait_box() is only called by the few callers that need the numbers on the host
+    double4 *d_box;
+    PIB_TRY(bounding_box_device(d_xyz, n, 3, ws, stream, &d_box));
 
     uint32_t *keys, *keys_s;
     int32_t *vals, *vals_s;
     PIB_TRY(ws.alloc(&keys, n)); PIB_TRY(ws.alloc(&keys_s, n));
     PIB_TRY(ws.alloc(&vals, n)); PIB_TRY(ws.alloc(&vals_s, n));
     const int blocks = (int)((n + 255) / 256);
-    curve_key_kernel<<<blocks, 256, 0, stream>>>(d_xyz, n, box[0], box[1], scale, keys, vals);
+    curve_key_kernel<<<blocks, 256, 0, stream>>>(d_xyz, n, d_box, keys, vals);
     PIB_CUDA(cudaGetLastError());
     PIB_TRY(radix_sort_pairs(keys, keys_s, vals, vals_s, n, 32, ws, stream));
 
     SortedPoints sp;
     sp.n = n; sp.tile = tile;
-    for (int i = 0; i < 4; ++i) sp.box[i] = box[i];
+    sp.d_box = d_box;
+    static thread_local double *h_box = nullptr;              // pinned, one slot per calling thread
+    if (!h_box) PIB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h_box), 4 * sizeof(double)));
+    PIB_CUDA(cudaMemcpyAsync(h_box, d_box, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    PIB_CUDA(cudaEventCreateWithFlags(&sp.box_ready, cudaEventDisableTiming));
+    PIB_CUDA(cudaEventRecord(sp.box_ready, stream));
+    sp.h_box = h_box;
     sp.n_pad = (n + pad_to - 1) / pad_to * pad_to;
     // the pair kernels read whole A sub-tiles (up to 1024 points) that may start in the last tile: keep that many
     // sentinel rows behind n_pad so the reads stay inside the arrays
@@ -293,4 +331,19 @@ int sort_queries_by_cell(const double *d_unknown, int64_t m, const GridIndex &g,
     return PIB_OK;
 }
 
+}  // namespace pib
+
+namespace pib {
+int SortedPoints::wait_box()
+{
+    if (box_ready) {
+        PIB_CUDA(cudaEventSynchronize(box_ready));
+        cudaEventDestroy(box_ready);
+        box_ready = nullptr;
+        for (int i = 0; i < 4; ++i) box[i] = h_box[i];
+        PIB_CHECK(std::isfinite(box[0]) && std::isfinite(box[1]) && std::isfinite(box[2]) && std::isfinite(box[3]),
+                  PIB_ERR_INVALID, "coordinates must be finite");
+    }
+    return PIB_OK;
+}
 }  // namespace pib

@@ -31,26 +31,42 @@ def rank_world():
     return 0, 1
 
 
+def _collective_device(device=None):
+    """Where collective buffers must live: NCCL only moves CUDA tensors, so with that backend host arrays are staged
+    on the current CUDA device (gloo takes CPU tensors)."""
+    if device is not None:
+        return device
+    import torch
+    dist = _dist()
+    if dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return None
+
+
 def allreduce_variogram_sums(sums, device=None, group=None):
-    """SUM-all-reduce a dict(sum_sq, sum_prod, sum_val, count[, pairs_evaluated]) of numpy arrays or
-    torch tensors in two collectives (one fp64 buffer, one int64 buffer).  Returns the same kind of
-    containers it was given."""
+    """SUM-all-reduce a dict(sum_sq, sum_prod, sum_val, count[, pairs_evaluated]) of numpy arrays or torch tensors in
+    ONE collective: the three fp64 sums, the pair counts and the evaluated-pairs counter travel in one fp64 buffer —
+    the counts are integers below 2^53, so their fp64 sum is exact whatever the reduction order.  Returns the same
+    kind of containers it was given."""
     import torch
     rank, world = rank_world()
     if world == 1:
         return sums
     dist = _dist()
     as_numpy = isinstance(sums["count"], np.ndarray)
-    to_t = (lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt)) if as_numpy else (lambda a, dt: a.to(dt))
-    f = torch.stack([to_t(sums[k], torch.float64) for k in ("sum_sq", "sum_prod", "sum_val")])
-    extra = torch.tensor([int(sums.get("pairs_evaluated", 0))], dtype=torch.int64, device=f.device if not as_numpy else None)
-    c = torch.cat([to_t(sums["count"], torch.int64).reshape(-1), extra])
-    if device is not None:
-        f, c = f.to(device), c.to(device)
-    dist.all_reduce(f, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(c, op=dist.ReduceOp.SUM, group=group)
+    device = _collective_device(device)
+    to_t = (lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64))) if as_numpy else (lambda a: a.to(torch.float64))
     shape = tuple(sums["count"].shape)
-    out = dict(sum_sq=f[0], sum_prod=f[1], sum_val=f[2], count=c[:-1].reshape(shape), pairs_evaluated=int(c[-1].item()))
+    n = int(np.prod(shape))
+    parts = [to_t(sums[k]).reshape(-1) for k in ("sum_sq", "sum_prod", "sum_val", "count")]
+    extra = torch.tensor([float(int(sums.get("pairs_evaluated", 0)))], dtype=torch.float64, device=parts[0].device)
+    buf = torch.cat(parts + [extra])
+    if device is not None:
+        buf = buf.to(device)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    cnt = buf[3 * n:4 * n].round().to(torch.int64)
+    out = dict(sum_sq=buf[:n].reshape(shape), sum_prod=buf[n:2 * n].reshape(shape), sum_val=buf[2 * n:3 * n].reshape(shape),
+               count=cnt.reshape(shape), pairs_evaluated=int(round(float(buf[-1].item()))))
     if as_numpy:
         out = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
     return out
@@ -74,6 +90,9 @@ def gather_rows(local_rows, m, group=None):
     dist = _dist()
     as_numpy = isinstance(local_rows, np.ndarray)
     t = torch.as_tensor(local_rows) if as_numpy else local_rows
+    dev = _collective_device(None if as_numpy else t.device)
+    if dev is not None:
+        t = t.to(dev)
     sizes = [shard_bounds(m, r, world) for r in range(world)]
     longest = max(e - b for b, e in sizes)
     pad = torch.zeros((longest,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)

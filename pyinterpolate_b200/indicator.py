@@ -109,22 +109,30 @@ class IndicatorKriging:
                 np.column_stack([xy[:, 0], xy[:, 1], self.variances]))
 
     def _get_expected_values(self, ccdf_density=100):
-        """indicator.py:327-380 (host-side spline per location, unchanged)."""
+        """Expected value and variance per location from the indicator predictions (what indicator.py:327-380 computes
+        with one spline fit per location).  The interpolating spline through (threshold, prediction) is LINEAR in the
+        predictions, so its values on the ``ccdf_density`` grid are one matrix product for all locations: the basis is the
+        spline of each unit vector (T small fits, same scipy call and degree rule as the reference)."""
         from scipy.interpolate import UnivariateSpline
-        expected_values, expected_variances = [], []
-        old = self.thresholds.copy()
-        new_indices = np.linspace(old.min(), old.max(), ccdf_density)
-        for row in self.indicator_predictions:
-            if len(old) >= 4:
-                spl = UnivariateSpline(old, row, s=0)
-            else:
-                spl = UnivariateSpline(old, row, k=(len(old) - 1), s=0)
-            new_tvals = spl(new_indices)
-            cdf = new_tvals.cumsum() / new_tvals.sum()
-            ccdf = 1 - cdf
-            expected_c = np.mean(ccdf)
-            idx = len(ccdf) - np.searchsorted(np.flip(ccdf), expected_c)
-            expected_value = new_indices[min(idx, len(new_indices) - 1)]
-            expected_values.append(expected_value)
-            expected_variances.append(np.mean(np.abs(new_tvals - expected_value) ** 2))
-        return np.array(expected_values), np.array(expected_variances)
+        thr = self.thresholds.astype(float)
+        grid = np.linspace(thr.min(), thr.max(), ccdf_density)
+        degree = 3 if len(thr) >= 4 else len(thr) - 1
+        basis = np.empty((len(thr), ccdf_density))
+        for t in range(len(thr)):
+            unit = np.zeros(len(thr))
+            unit[t] = 1.0
+            basis[t] = UnivariateSpline(thr, unit, k=degree, s=0)(grid)
+        curves = np.asarray(self.indicator_predictions, dtype=float) @ basis          # [M, ccdf_density]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ccdf = 1.0 - np.cumsum(curves, axis=1) / np.sum(curves, axis=1, keepdims=True)
+        level = ccdf.mean(axis=1, keepdims=True)
+        # the reference looks ``level`` up in the reversed ccdf with np.searchsorted (left side): for a non-increasing
+        # ccdf that is the number of entries >= level; rows where the spline makes the ccdf non-monotone fall back to
+        # the literal search
+        n_ge = np.sum(ccdf >= level, axis=1)
+        monotone = np.all(np.diff(ccdf, axis=1) <= 0, axis=1)
+        for r in np.nonzero(~monotone)[0]:
+            n_ge[r] = ccdf_density - np.searchsorted(ccdf[r, ::-1], level[r, 0])
+        expected = grid[np.minimum(n_ge, ccdf_density - 1)]
+        variances = np.mean((curves - expected[:, None]) ** 2, axis=1)
+        return expected, variances

@@ -37,6 +37,8 @@ def _prepare(theoretical_model, known_locations, unknown_locations, use_all_neig
         raise ValueError("known_locations must be rows of [x, y, value]")
     if unknown.ndim != 2 or unknown.shape[1] != 2:
         raise ValueError("unknown_locations must be rows of [x, y]")
+    if not (np.isfinite(known[:, :2]).all() and np.isfinite(unknown).all()):
+        raise ValueError("coordinates must be finite")
     # neighbors_range defaults to the model range (kriging/utils/point_kriging_solve.py:68-69)
     selection = dict(neighbors_range=rang if neighbors_range is None else float(neighbors_range),
                      direction=direction, max_tick=max_tick, use_all=bool(use_all_neighbors_in_range),
@@ -102,6 +104,22 @@ def simple_kriging(theoretical_model, known_locations, unknown_locations=None, p
                                        process_mean=float(process_mean), want_neighbors=return_neighbors, **sel)
     _raise_on_singular(status)
     return (out[0], idx) if return_neighbors else out[0]
+
+
+def ordinary_and_simple_kriging(theoretical_model, known_locations, unknown_locations, process_mean, neighbors_range=None,
+                                no_neighbors=4, max_tick=5., use_all_neighbors_in_range=False,
+                                allow_approximate_solutions=False):
+    """``(ordinary_kriging(...), simple_kriging(...))`` from ONE pass: the two calls of the reference
+    (kriging/point/ordinary.py:134-221, simple.py:129-223) select the same neighbours and build the same Gamma
+    (ordinary.py:100-120, simple.py:102-113), so the neighbour search, the assembly and the elimination are shared
+    (BASELINE config 4 asks for both on 10M locations).  Each result equals the single call bit for bit."""
+    mid, params, known, unknown, sel = _prepare(theoretical_model, known_locations, unknown_locations,
+                                                use_all_neighbors_in_range, allow_approximate_solutions,
+                                                neighbors_range, max_tick)
+    out, _, status = _lib.krige_host(known, unknown, mid, params, _lib.KRIGE_BOTH, int(no_neighbors),
+                                     process_mean=float(process_mean), **sel)
+    _raise_on_singular(status)
+    return out[0, 0], out[1, 0]
 
 
 def validate_kriging(points, theoretical_model, how='ok', neighbors_range=None, no_neighbors=4,

@@ -211,6 +211,11 @@ def point_cloud_semivariance(ds, step_size=None, max_range=None, direction=None,
     xyz = np.ascontiguousarray(points, dtype=np.float64)
     if direction is not None and tolerance is not None:
         _check_method(direction, dir_neighbors_selection_method, None)
+        if dir_neighbors_selection_method in ("t", "triangle"):
+            # the reference sends 't' (its default) to from_triangle_cloud (experimental_semivariogram.py:282-294); only
+            # the ellipse cloud is built here — substituting it silently would return a different point set
+            raise NotImplementedError("directional point clouds are built for dir_neighbors_selection_method='e' only; "
+                                      "the triangle-method cloud (functions/directional.py:213-273) is not implemented")
         W = core.define_whitening_matrix(direction, tolerance).reshape(4)
         clouds = _lib.variogram_cloud_host(xyz, lags64, lower=core.ellipse_lower_limits(lags64), W=W)
     else:
@@ -321,6 +326,17 @@ class DirectionalVariogram:
 
     def _build_experimental_variograms(self):
         _check_method(0, self.dir_neighbors_selection_method, self.custom_weights)
+        if self.custom_weights is not None:
+            # the reference hands custom_weights to all five ExperimentalVariograms (directional_variogram.py:126-143):
+            # the weighted path, one variogram at a time
+            self.directional_variograms['ISO'] = ExperimentalVariogram(
+                self.ds, self.step_size, self.max_range, custom_bins=self.custom_bins, custom_weights=self.custom_weights)
+            for name, angle in self.directions.items():
+                self.directional_variograms[name] = ExperimentalVariogram(
+                    self.ds, self.step_size, self.max_range, direction=angle, tolerance=self.tolerance,
+                    dir_neighbors_selection_method=self.dir_neighbors_selection_method, custom_bins=self.custom_bins,
+                    custom_weights=self.custom_weights)
+            return
         self.directional_variograms['ISO'] = ExperimentalVariogram(
             self.ds, self.step_size, self.max_range, custom_bins=self.custom_bins)
         names = list(self.directions)

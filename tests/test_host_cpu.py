@@ -209,3 +209,52 @@ def test_variogram_cloud_remove_outliers_matches_reference():
         vc.remove_outliers(z_lower_limit=1)
     assert vc.remove_outliers(method="iqr", inplace=True) is None
     np.testing.assert_array_equal(vc.semivariances[1000.0], g["cloud_iqr_1000"])
+
+
+def test_indicator_expected_values_match_per_location_splines():
+    """IndicatorKriging._get_expected_values evaluates ONE spline basis for all locations (a matrix product); the
+    reference fits a spline per location (kriging/point/indicator.py:327-380).  Same numbers, row by row."""
+    from scipy.interpolate import UnivariateSpline
+    from pyinterpolate_b200.indicator import IndicatorKriging
+    rng = np.random.default_rng(3)
+    for n_thr in (3, 4, 8):
+        thr = np.sort(rng.uniform(150.0, 250.0, n_thr))
+        preds = np.sort(rng.uniform(0.0, 1.0, (200, n_thr)), axis=1)          # indicator probabilities grow with the threshold
+        preds[:5] = rng.uniform(0.0, 1.0, (5, n_thr))                            # and a few non-monotone rows
+        obj = IndicatorKriging.__new__(IndicatorKriging)
+        obj.thresholds, obj.indicator_predictions = thr, preds
+        got_e, got_v = obj._get_expected_values()
+        grid = np.linspace(thr.min(), thr.max(), 100)
+        for r in range(len(preds)):
+            spl = UnivariateSpline(thr, preds[r], k=3 if n_thr >= 4 else n_thr - 1, s=0)
+            vals = spl(grid)
+            ccdf = 1 - vals.cumsum() / vals.sum()
+            idx = len(ccdf) - np.searchsorted(np.flip(ccdf), np.mean(ccdf))
+            want_e = grid[min(idx, len(grid) - 1)]
+            want_v = np.mean(np.abs(vals - want_e) ** 2)
+            # an exact tie of the ccdf with its mean can move the index by one between the two evaluation orders
+            assert abs(got_e[r] - want_e) <= (grid[1] - grid[0]) * 1.0000001
+            if got_e[r] == want_e:
+                np.testing.assert_allclose(got_v[r], want_v, rtol=1e-9)
+
+
+def test_directional_variogram_passes_custom_weights(monkeypatch):
+    """DirectionalVariogram hands custom_weights to all five variograms (classes/directional_variogram.py:126-143)."""
+    import pyinterpolate_b200.variogram as vg
+    seen = []
+
+    class Fake:
+        def __init__(self, *a, **k):
+            seen.append(k.get("custom_weights"))
+    monkeypatch.setattr(vg, "ExperimentalVariogram", Fake)
+    w = np.ones(10)
+    vg.DirectionalVariogram(np.zeros((10, 3)), 1.0, 4.0, custom_weights=w, dir_neighbors_selection_method="e")
+    assert len(seen) == 5 and all(s is w for s in seen)
+
+
+def test_directional_cloud_triangle_method_is_refused():
+    """The triangle-method point cloud is not built; the ellipse must not be substituted silently."""
+    from pyinterpolate_b200 import point_cloud_semivariance
+    pts = np.random.default_rng(0).uniform(0, 10, (30, 3))
+    with pytest.raises(NotImplementedError):
+        point_cloud_semivariance(pts, 1.0, 4.0, direction=45, tolerance=0.2)
