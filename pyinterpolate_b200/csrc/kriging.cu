@@ -1013,21 +1013,34 @@ __global__ void __launch_bounds__(gj_threads<K>(), K == 32 ? 2 : 1) solve_gj_ker
 
     for (int set = 0; set < p.n_sets; ++set) {
         const double nugget = p.params[3 * set], sill = p.params[3 * set + 1], rang = p.params[3 * set + 2];
-        // ---- Gamma, every entry evaluated once: thread t takes (t, t+1 .. t+K/2) cyclically and writes both halves ----
+        // ---- Gamma, every entry evaluated once: thread t takes (t, t+1 .. t+K/2) cyclically and writes both halves.
+        // Four entries per iteration: one evaluation is a chain of ~100 dependent instructions (sqrt, division, model) ----
         if (t < K) {
-            for (int i = 0; i < K / 2; ++i) {
-                int c = t + 1 + i;
-                if (c >= K) c -= K;
-                double v;
-                if (t < kk && c < kk) {
+            constexpr int AU = K >= 8 ? 4 : 1;
+#pragma unroll 1
+            for (int i0 = 0; i0 < K / 2; i0 += AU) {
+                int cc[AU];
+                double hh[AU], vv[AU];
+#pragma unroll
+                for (int u = 0; u < AU; ++u) {
+                    int c = t + 1 + i0 + u;
+                    if (c >= K) c -= K;
+                    cc[u] = c;
                     const double2 o = S.nxy[c];
                     const double dx = __dsub_rn(me.x, o.x), dy = __dsub_rn(me.y, o.y);
-                    const double h = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-                    if (h == 0.0) S.dup = 1;
-                    v = gamma_model(p.model, h, nugget, sill, rang);
-                } else v = 0.0;                                                 // identity padding (off diagonal)
-                S.G[t * (K + 2) + c] = v;
-                S.G[c * (K + 2) + t] = v;
+                    hh[u] = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                }
+#pragma unroll
+                for (int u = 0; u < AU; ++u) {
+                    const bool real = (t < kk && cc[u] < kk);
+                    if (real && hh[u] == 0.0) S.dup = 1;
+                    vv[u] = real ? gamma_model(p.model, hh[u], nugget, sill, rang) : 0.0;       // identity padding (off diagonal)
+                }
+#pragma unroll
+                for (int u = 0; u < AU; ++u) {
+                    S.G[t * (K + 2) + cc[u]] = vv[u];
+                    S.G[cc[u] * (K + 2) + t] = vv[u];
+                }
             }
             S.G[t * (K + 2) + t] = (t < kk) ? nugget : 1.0;                     // gamma(0) / identity padding
             const double kv = (t < kk) ? gamma_model(p.model, my_d, nugget, sill, rang) : 0.0;

@@ -20,8 +20,13 @@
 //     own, and skips B tiles none of its points can reach (finer culling than the CTA-wide box).
 //   * APT (A points per thread: 1 or 2) and U (pairs per group: 8 or 16) are template parameters: APT = 2 halves the
 //     B-point loads per pair, U = 16 halves the ring traffic per pair — the two levers on the shared-memory wavefronts.
-//   * two groups in flight per thread (distances + table lookup of group g + 1 are issued ahead of the sums and ring
-//     updates of group g): the lookup is a chain of three dependent shared-memory loads.
+//   * optionally (PIB_V6_PIPE) two groups in flight per thread: distances + table lookup of group g + 1 issued ahead of the
+//     sums and ring updates of group g.  Measured neutral (the kernel is bound by the shared-memory pipe, not by the
+//     latency of the lookup chain), so it is off.
+// Measured (B200, BASELINE config 2): 174 ms against 186 ms for pair_ring_kernel; 6.4 shared-memory wavefronts per
+// warp-wide pair step (B points 3.25, ring 2.5, tables 0.65) keep the shared-memory pipe at 73 % — 24 warps instead of
+// 16, U = 16 (5.2 wavefronts, but 23 % of the groups then span three lags) and APT = 2 (8-12 warps) all land within 5 %
+// of the same time; see DESIGN.md section 4.1 for the experiment table.
 #pragma once
 
 namespace pib {
@@ -47,7 +52,7 @@ static size_t ring6_smem_bytes(int n_slots, int lut_n)
 #define PIB_V6_CMP 0
 #endif
 #ifndef PIB_V6_PIPE
-#define PIB_V6_PIPE 1
+#define PIB_V6_PIPE 0
 #endif
 
 template <int RING, int NT, int APT, int U, bool MULTI_FIX, bool ELLIPSE>
@@ -327,14 +332,6 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                         return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
                     }
                 };
-                // exact slot of one squared distance: table cell, then threshold steps on the full bit pattern
-                auto slot_of = [&](long long bits) __attribute__((always_inline)) -> int {
-                    int idx = ((int)(bits >> 32) - base_hi) >> LUT2_SHIFT;
-                    idx = min(max(idx, 0), lut_last);
-                    int q = s_lut[idx];
-                    while (bits > s_slot[q].T) ++q;
-                    return q;
-                };
                 // one pair into the ring (slow paths)
                 auto add_pair = [&](int q, int k, double z, bool wide_mode) __attribute__((always_inline)) {
                     uint32_t off = s_slot[q].offs & 0xffffu;
@@ -402,7 +399,8 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                 // second-lag sums of one group for A point k and the two ring updates; g1, g2, n_in = sums of z, z^2 and
                 // the number of pairs the ring still has to take (the slow path removes pairs it added on its own)
                 auto finish_group = [&](int k, int j0, const long long (&d2k)[U], long long T, uint32_t offs, int q, double g1,
-                                        double g2, int n_in, const bool wide_mode) __attribute__((always_inline)) {
+                                        double g2, int n_in, const bool wide_mode, const bool bounded, long long t1)
+                                        __attribute__((always_inline)) {
                     uint32_t o_lo = offs & 0xffffu, o_hi = offs >> 16;
                     if (wide_mode) {
                         if (!((unsigned)(q - wlo) < wlen)) o_lo = TRASH16;
@@ -417,6 +415,12 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                         // pair: a first-lag pair keeps the low word of z under a zero high word, a subnormal below 1e-308
                         // whose contribution to the fp64 sums is far below one ulp; predicated count
                         int za_hi, zb_hi;
+                        if (bounded) {
+                            // slow variant: pairs beyond the second lag (d2 > t1) were added on their own and stay out
+                            const bool pa = d2k[u] > T && !(d2k[u] > t1), pb = d2k[u + 1] > T && !(d2k[u + 1] > t1);
+                            za_hi = pa ? __double2hiint(zz.x) : 0; zb_hi = pb ? __double2hiint(zz.y) : 0;
+                            ch += (pa ? 1 : 0) + (pb ? 1 : 0);
+                        } else {
                         if (CMP == 1)
                             asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %3, %4;\n\tselp.b32 %0, %2, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
                                 : "=r"(za_hi), "+r"(ch) : "r"(__double2hiint(zz.x)), "d"(__longlong_as_double(d2k[u])), "d"(__longlong_as_double(T)));
@@ -429,6 +433,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                         else
                             asm("{\n\t.reg .pred p;\n\tsetp.gt.s64 p, %3, %4;\n\tselp.b32 %0, %2, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
                                 : "=r"(zb_hi), "+r"(ch) : "r"(__double2hiint(zz.y)), "l"(d2k[u + 1]), "l"(T));
+                        }
                         const double za = __hiloint2double(za_hi, __double2loint(zz.x));
                         const double zb = __hiloint2double(zb_hi, __double2loint(zz.y));
                         h1a += za; h2a = __fma_rn(za, za, h2a);
@@ -456,48 +461,80 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
 #pragma unroll
                         for (int k = 0; k < APT; ++k)
                             finish_group(k, j0, s.d2[k], s.T[k], s.offs[k], wide_mode ? (int)((s.ea[k] - slot_sa) >> 4) : 0, gs.x, gs.y,
-                                         U, wide_mode);
+                                         U, wide_mode, false, 0);
                     } else {
-                        // rare: a pair may lie beyond the second lag — those pairs are added on their own, leave the group's
-                        // sums and get a zero distance (never above a threshold: they stay out of the second-lag sums)
+                        // rare: a pair may lie beyond the second lag — those pairs are added on their own and leave the group's
+                        // sums (the distances stay read-only: both branches use the same registers)
 #pragma unroll
                         for (int k = 0; k < APT; ++k) {
                             const int q = (int)((s.ea[k] - slot_sa) >> 4);
                             const long long t1 = s_slot[q + 1].T;
                             double g1 = gs.x, g2 = gs.y;
                             int n_in = U;
-                            long long d2k[U];
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
-                                d2k[u] = s.d2[k][u];
-                                if (d2k[u] > t1) {
+                                if (s.d2[k][u] > t1) {
                                     int sx = q + 2;
-                                    while (d2k[u] > s_slot[sx].T) ++sx;
+                                    while (s.d2[k][u] > s_slot[sx].T) ++sx;
                                     const double zj = bz[j0 + u];
                                     add_pair(sx, k, zj, wide_mode);
                                     g1 -= zj; g2 = __fma_rn(-zj, zj, g2);
-                                    d2k[u] = 0; --n_in;
+                                    --n_in;
                                 }
                             }
-                            finish_group(k, j0, d2k, s.T[k], s.offs[k], q, g1, g2, n_in, wide_mode);
+                            finish_group(k, j0, s.d2[k], s.T[k], s.offs[k], q, g1, g2, n_in, wide_mode, true, t1);
                         }
                     }
                 };
 
                 auto sweep = [&](const bool wide_mode) __attribute__((always_inline)) {
                     if (diagonal || !p.group_path) {
-                        // tiles that overlap my CTA's own points: per-pair slots, keep i < j only
+                        // Per-pair path: tiles that overlap my CTA's own points (keep i < j only) and data whose groups of
+                        // U points are too wide for the two-lag scheme (sparse points / fine lags / stretched ellipses:
+                        // the host clears group_path).  Batches of 4 pairs: distances and table lookups of the batch are
+                        // independent chains, the ring updates follow in order.
 #pragma unroll 1
                         for (int j0 = 0; j0 < TILE; j0 += 4) {
+                            long long d2[APT][4];
+                            uint32_t ea[APT][4];
+                            double zj[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 const double2 pj = bxy[j0 + u];
-                                const double zj = bz[j0 + u];
+                                zj[u] = bz[j0 + u];
 #pragma unroll
                                 for (int k = 0; k < APT; ++k) {
-                                    int q = slot_of(__double_as_longlong(dist2(pj, k)));
-                                    if (!(jbase + j0 + u > ig[k])) q = 0;
-                                    add_pair(q, k, zj, wide_mode);
+                                    d2[k][u] = __double_as_longlong(dist2(pj, k));
+                                    int idx = ((int)(d2[k][u] >> 32) - base_hi) >> LUT2_SHIFT;
+                                    idx = min(max(idx, 0), lut_last);
+                                    unsigned short q0;
+                                    asm("ld.shared.u16 %0, [%1];" : "=h"(q0) : "r"(lut_sa + 2u * (uint32_t)idx));
+                                    ea[k][u] = slot_sa + 16u * (uint32_t)q0;
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                                for (int k = 0; k < APT; ++k) {
+                                    // exact slot: threshold steps on the full bit pattern (the table cell is at most a few slots low)
+                                    long long T;
+                                    uint32_t offs;
+                                    while (true) {
+                                        int tlo, thi, nx;
+                                        asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(tlo), "=r"(thi), "=r"(nx), "=r"(offs) : "r"(ea[k][u]));
+                                        T = ((long long)thi << 32) | (unsigned)tlo;
+                                        if (!(d2[k][u] > T)) break;
+                                        ea[k][u] += 16u;
+                                    }
+                                    uint32_t off = offs & 0xffffu;
+                                    if (!(jbase + j0 + u > ig[k])) off = TRASH16;                   // keep i < j only
+                                    if (wide_mode && !((unsigned)((int)((ea[k][u] - slot_sa) >> 4) - wlo) < wlen)) off = TRASH16;
+                                    double2 *ap = reinterpret_cast<double2 *>(ring + off * 16 + my_acc[k]);
+                                    uint32_t *cp = reinterpret_cast<uint32_t *>(ring + off * 16 + my_cnt[k]);
+                                    double2 a = *ap;
+                                    a.x += zj[u]; a.y = __fma_rn(zj[u], zj[u], a.y);
+                                    *ap = a;
+                                    *cp += 1u;
                                 }
                             }
                         }

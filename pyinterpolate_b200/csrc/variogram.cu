@@ -1146,6 +1146,8 @@ static int launch_pair_ring6(const PairParams &p, int ring, int nt, int apt, int
     PIB_V6_TRY(10, 768, 1, 8);
     PIB_V6_TRY(8, 768, 1, 8);
     PIB_V6_TRY(8, 896, 1, 8);
+    PIB_V6_TRY(12, 640, 1, 16);
+    PIB_V6_TRY(10, 768, 1, 16);
 #undef PIB_V6_TRY
 #else
     if (ring == 16 && nt == 512 && apt == 1 && u == 8) return launch_pair_ring6_t<16, 512, 1, 8, true>(p, multi_fix, ellipse, grid, stream);
@@ -1334,7 +1336,7 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         if (v6 && !(force_full && force_full[0] == '1') && n_lags <= MAX_SLOTS - 2) {
             const double span1 = 1.5 * d90_scaled / min_width + 2.0;     // A points per warp = 32: box ~ half a tile's diagonal
             if (span1 <= 16.0) { ring = 16; ring_nt = 512; use_ring = true; }
-            else if (span1 <= 30.0) { ring = 32; ring_nt = 256; use_ring = true; }
+            else if (span1 <= 34.0) { ring = 32; ring_nt = 256; use_ring = true; }
             else use_ring = false;
             const char *force_ring = std::getenv("PIB_FORCE_RING");
             if (force_ring && force_ring[0] == '1') {
@@ -1410,6 +1412,9 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             guard_groups = n_groups;
         }
         {
+            // the two-lag group scheme stays on even when groups of 8 points are wider than a lag (sparse points, stretched
+            // ellipses): the pairs beyond the second lag take their own ring update, the rest still share two (measured on
+            // BASELINE config 3: 70 ms against 86 ms with per-pair updates only)
             const char *gp = std::getenv("PIB_GROUP_PATH");
             p.group_path = (gp && gp[0] == '0') ? 0 : 1;
         }
