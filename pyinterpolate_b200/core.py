@@ -31,7 +31,7 @@ def interpolation_points(points):
         return np.column_stack((xs, ys)) if xs.ndim else np.array([[float(xs), float(ys)]])
     if hasattr(points, "columns") and hasattr(points, "values"):
         return points.values
-    arr = np.array(points)
+    arr = points if isinstance(points, np.ndarray) else np.array(points)      # (inputs are borrowed: no copy of a large array)
     if arr.ndim == 1:
         arr = arr.reshape(1, -1)
     return arr

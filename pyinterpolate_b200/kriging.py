@@ -37,8 +37,10 @@ def _prepare(theoretical_model, known_locations, unknown_locations, use_all_neig
         raise ValueError("known_locations must be rows of [x, y, value]")
     if unknown.ndim != 2 or unknown.shape[1] != 2:
         raise ValueError("unknown_locations must be rows of [x, y]")
-    if not (np.isfinite(known[:, :2]).all() and np.isfinite(unknown).all()):
-        raise ValueError("coordinates must be finite")
+    # a finite sum means every term is finite (NaN and +-inf propagate); only an overflowing sum needs the exact scan
+    if not (np.isfinite(known[:, :2].sum()) and np.isfinite(unknown.sum())):
+        if not (np.isfinite(known[:, :2]).all() and np.isfinite(unknown).all()):
+            raise ValueError("coordinates must be finite")
     # neighbors_range defaults to the model range (kriging/utils/point_kriging_solve.py:68-69)
     selection = dict(neighbors_range=rang if neighbors_range is None else float(neighbors_range),
                      direction=direction, max_tick=max_tick, use_all=bool(use_all_neighbors_in_range),
@@ -54,6 +56,8 @@ _LSA_MSG = repr('Kriging system solution is based on the approximate solution, o
 
 def _raise_on_singular(status):
     # kriging/utils/point_kriging_solve.py:134-147
+    if not status.any():                  # one pass: every system was regular
+        return
     if (status == _lib.STATUS_ZERO_MATRIX).any():
         warnings.warn(_ZEROS_MSG)
     if (status == _lib.STATUS_LSA).any():
