@@ -42,7 +42,7 @@ static size_t ring6_smem_bytes(int n_slots, int lut_n)
 {
     const size_t na = (size_t)NT * APT;
     size_t b = (size_t)(RING + 1) * na * 20;                    // ring: per slot NA x (double2 sums) then NA x u32 counts
-    b += (size_t)(n_slots + 1) * sizeof(SlotInfo);
+    b += (size_t)(n_slots + 4) * sizeof(SlotInfo);
     b += (size_t)(NT / 32) * CHUNK * sizeof(short2);
     b += ((size_t)lut_n * 2 + 15) / 16 * 16;
     return b;
@@ -55,7 +55,7 @@ static size_t ring6_smem_bytes(int n_slots, int lut_n)
 #define PIB_V6_PIPE 0
 #endif
 
-template <int RING, int NT, int APT, int U, bool MULTI_FIX, bool ELLIPSE>
+template <int RING, int NT, int APT, int U, int NL, bool MULTI_FIX, bool ELLIPSE>
 __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
 {
     constexpr int NA = NT * APT;                   // A points per CTA
@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
     constexpr int NG = TILE / U;
     static_assert(NA % TILE == 0 && RING <= 32 && RING >= 4, "A sub-tile is whole tiles; one lane folds one ring slot");
     static_assert(U == 8 || U == 16, "groups of 8 or 16 pairs");
+    static_assert(NL == 2 || NL == 4, "a group may span two or four consecutive lags");
+    static_assert(NL == 2 || APT == 1, "the four-lag scheme is built for one A point per thread");
     static_assert((RING + 1) * SB16 < 65536, "ring offsets are 16-bit");
     __shared__ __align__(16) double2 s_txy[2][TILE];
     __shared__ __align__(16) double s_tz[2][TILE];
@@ -83,8 +85,8 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
 
     unsigned char *const ring = smem_raw;
     SlotInfo *const s_slot = reinterpret_cast<SlotInfo *>(smem_raw + (size_t)(RING + 1) * SLOT_BYTES);
-    short2 *const s_range = reinterpret_cast<short2 *>(s_slot + n_slots + 1) + warp * CHUNK;    // my warp's row
-    const uint16_t *const s_lut = reinterpret_cast<const uint16_t *>(reinterpret_cast<short2 *>(s_slot + n_slots + 1) + NW * CHUNK);
+    short2 *const s_range = reinterpret_cast<short2 *>(s_slot + n_slots + 4) + warp * CHUNK;    // my warp's row
+    const uint16_t *const s_lut = reinterpret_cast<const uint16_t *>(reinterpret_cast<short2 *>(s_slot + n_slots + 4) + NW * CHUNK);
     const uint32_t slot_sa = smem_u32(s_slot), lut_sa = smem_u32(s_lut);
 
     // my ring entries: sums at ring + 16 * off + my_acc[k], counts at ring + 16 * off + my_cnt[k]
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
             *reinterpret_cast<uint32_t *>(ring + s * SLOT_BYTES + my_cnt[k]) = 0u;
         }
     }
-    for (int s = tid; s <= n_slots; s += NT) {
+    for (int s = tid; s < n_slots + 4; s += NT) {          // (entries behind the last slot: +inf thresholds, trash block)
         SlotInfo e;
         e.T = s < n_slots ? __double_as_longlong(p.upper[s]) : 0x7ff0000000000000ll;
         e.next_hi = (int)(__double_as_longlong(p.upper[min(s + 1, n_slots - 1)]) >> 32);
@@ -350,7 +352,9 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                     long long T[APT];          // threshold between the group's first and second lag
                     uint32_t offs[APT];        // ring blocks of the two lags
                     uint32_t ea[APT];          // shared address of the first lag's table entry
-                    bool beyond;               // a pair may lie beyond the second lag
+                    bool beyond;               // a pair may lie beyond the group's last lag
+                    long long T1, T2;          // NL == 4: the thresholds behind the second and third lag
+                    uint32_t offs23;           //          ring blocks of the third and fourth lag
                 };
                 // stage A: the U squared distances of every A point, the group's first lag slot and its table entry
                 auto stage_a = [&](int g, Grp &s) __attribute__((always_inline)) {
@@ -393,6 +397,16 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                         asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(e_tlo), "=r"(e_thi), "=r"(e_next), "=r"(s.offs[k]) : "r"(ea));
                         s.T[k] = ((long long)e_thi << 32) | (unsigned)e_tlo;
                         s.ea[k] = ea;
+                        if (NL == 4) {
+                            // four lags per group: thresholds of the next two slots, the ring blocks of slots q + 2, q + 3 and
+                            // the high word of the threshold behind the fourth lag
+                            int t1lo, t1hi, t2lo, t2hi, n2;
+                            asm("ld.shared.v2.s32 {%0, %1}, [%2+16];" : "=r"(t1lo), "=r"(t1hi) : "r"(ea));
+                            asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4+32];" : "=r"(t2lo), "=r"(t2hi), "=r"(n2), "=r"(s.offs23) : "r"(ea));
+                            s.T1 = ((long long)t1hi << 32) | (unsigned)t1lo;
+                            s.T2 = ((long long)t2hi << 32) | (unsigned)t2lo;
+                            e_next = n2;
+                        }
                         s.beyond |= (mx[k] >= e_next);
                     }
                 };
@@ -452,29 +466,79 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                     *clo = c_lo + (uint32_t)(n_in - ch);
                     *chi = c_hi + (uint32_t)ch;
                 };
+                // NL == 4: cumulative sums over the pairs above each of the three thresholds; slot q + i gets the difference of
+                // two consecutive ones (q: all - H0, q + 1: H0 - H1, q + 2: H1 - H2, q + 3: H2)
+                auto finish_group4 = [&](int j0, const long long (&d2k)[U], const Grp &s, int q, double g1, double g2, int n_in,
+                                         const bool wide_mode, const bool bounded, long long t_last) __attribute__((always_inline)) {
+                    uint32_t o[4] = {s.offs[0] & 0xffffu, s.offs[0] >> 16, s.offs23 & 0xffffu, s.offs23 >> 16};
+                    if (wide_mode) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (!((unsigned)(q + i - wlo) < wlen)) o[i] = TRASH16;
+                    }
+                    const long long T[3] = {s.T[0], s.T1, s.T2};
+                    double h1[3] = {0.0, 0.0, 0.0}, h2[3] = {0.0, 0.0, 0.0};
+                    int c[3] = {0, 0, 0};
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const double zj = bz[j0 + u];
+                        const bool in = !bounded || !(d2k[u] > t_last);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            int zh;
+                            if (bounded) {
+                                const bool pr = in && d2k[u] > T[i];
+                                zh = pr ? __double2hiint(zj) : 0;
+                                c[i] += pr ? 1 : 0;
+                            } else {
+                                asm("{\n\t.reg .pred p;\n\tsetp.gt.s64 p, %3, %4;\n\tselp.b32 %0, %2, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
+                                    : "=r"(zh), "+r"(c[i]) : "r"(__double2hiint(zj)), "l"(d2k[u]), "l"(T[i]));
+                            }
+                            const double zm = __hiloint2double(zh, __double2loint(zj));
+                            h1[i] += zm; h2[i] = __fma_rn(zm, zm, h2[i]);
+                        }
+                    }
+                    const double a1[4] = {g1 - h1[0], h1[0] - h1[1], h1[1] - h1[2], h1[2]};
+                    const double a2[4] = {g2 - h2[0], h2[0] - h2[1], h2[1] - h2[2], h2[2]};
+                    const int n[4] = {n_in - c[0], c[0] - c[1], c[1] - c[2], c[2]};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        // one slot after the other: two of the four may be the trash block
+                        double2 *ap = reinterpret_cast<double2 *>(ring + o[i] * 16 + my_acc[0]);
+                        uint32_t *cp = reinterpret_cast<uint32_t *>(ring + o[i] * 16 + my_cnt[0]);
+                        double2 v = *ap;
+                        v.x += a1[i]; v.y += a2[i];
+                        *ap = v;
+                        *cp += (uint32_t)n[i];
+                    }
+                };
                 // stage B: sums and ring updates
                 auto stage_b = [&](int g, const Grp &s, const bool wide_mode) __attribute__((always_inline)) {
                     const int j0 = g * U;
                     const double2 gs = bgs[g];
                     if (!__any_sync(0xffffffffu, s.beyond)) {
-                        // fast path: every pair of the warp is in the group's first or second lag
+                        // fast path: every pair of the warp is in one of the group's NL lags
+                        if (NL == 4) {
+                            finish_group4(j0, s.d2[0], s, wide_mode ? (int)((s.ea[0] - slot_sa) >> 4) : 0, gs.x, gs.y, U, wide_mode, false, 0);
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < APT; ++k)
-                            finish_group(k, j0, s.d2[k], s.T[k], s.offs[k], wide_mode ? (int)((s.ea[k] - slot_sa) >> 4) : 0, gs.x, gs.y,
-                                         U, wide_mode, false, 0);
+                            for (int k = 0; k < APT; ++k)
+                                finish_group(k, j0, s.d2[k], s.T[k], s.offs[k], wide_mode ? (int)((s.ea[k] - slot_sa) >> 4) : 0, gs.x, gs.y,
+                                             U, wide_mode, false, 0);
+                        }
                     } else {
-                        // rare: a pair may lie beyond the second lag — those pairs are added on their own and leave the group's
-                        // sums (the distances stay read-only: both branches use the same registers)
+                        // rare: a pair may lie beyond the group's last lag — those pairs are added on their own and leave the
+                        // group's sums (the distances stay read-only: both branches use the same registers)
 #pragma unroll
                         for (int k = 0; k < APT; ++k) {
                             const int q = (int)((s.ea[k] - slot_sa) >> 4);
-                            const long long t1 = s_slot[q + 1].T;
+                            const long long t1 = s_slot[q + NL - 1].T;
                             double g1 = gs.x, g2 = gs.y;
                             int n_in = U;
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
                                 if (s.d2[k][u] > t1) {
-                                    int sx = q + 2;
+                                    int sx = q + NL;
                                     while (s.d2[k][u] > s_slot[sx].T) ++sx;
                                     const double zj = bz[j0 + u];
                                     add_pair(sx, k, zj, wide_mode);
@@ -482,7 +546,8 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                                     --n_in;
                                 }
                             }
-                            finish_group(k, j0, s.d2[k], s.T[k], s.offs[k], q, g1, g2, n_in, wide_mode, true, t1);
+                            if (NL == 4) finish_group4(j0, s.d2[k], s, q, g1, g2, n_in, wide_mode, true, t1);
+                            else finish_group(k, j0, s.d2[k], s.T[k], s.offs[k], q, g1, g2, n_in, wide_mode, true, t1);
                         }
                     }
                 };

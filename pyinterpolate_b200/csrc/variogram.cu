@@ -1107,16 +1107,16 @@ static int launch_pair_kernel(const PairParams &p, int fix_steps, int grid, cuda
 
 // ALL = every (multi-step threshold fix-up, ellipse) combination; experiment variants are only built for the
 // plain omnidirectional case
-template <int RING, int NT, int APT, int U, bool ALL>
+template <int RING, int NT, int APT, int U, int NL, bool ALL>
 static int launch_pair_ring6_t(const PairParams &p, bool multi_fix, bool ellipse, int grid, cudaStream_t stream)
 {
     const size_t smem = ring6_smem_bytes<RING, NT, APT>(p.n_slots, p.lut2_n);
     PIB_CHECK(smem + 8192 <= (size_t)MAX_SMEM, PIB_ERR_UNSUPPORTED, "pair_ring6_kernel: tables do not fit in shared memory");
-#define PIB_L6(M, E)                                                                                                          \
-    do {                                                                                                                      \
-        PIB_CUDA(cudaFuncSetAttribute(pair_ring6_kernel<RING, NT, APT, U, M, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      (int)smem));                                                                            \
-        pair_ring6_kernel<RING, NT, APT, U, M, E><<<grid, NT, smem, stream>>>(p);                                             \
+#define PIB_L6(M, E)                                                                                                              \
+    do {                                                                                                                          \
+        PIB_CUDA(cudaFuncSetAttribute(pair_ring6_kernel<RING, NT, APT, U, NL, M, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem));                                                                                \
+        pair_ring6_kernel<RING, NT, APT, U, NL, M, E><<<grid, NT, smem, stream>>>(p);                                             \
     } while (0)
     if constexpr (ALL) {
         if (multi_fix) { if (ellipse) PIB_L6(true, true); else PIB_L6(true, false); }
@@ -1130,28 +1130,24 @@ static int launch_pair_ring6_t(const PairParams &p, bool multi_fix, bool ellipse
     return PIB_OK;
 }
 
-static int launch_pair_ring6(const PairParams &p, int ring, int nt, int apt, int u, bool multi_fix, bool ellipse, int grid,
+static int launch_pair_ring6(const PairParams &p, int ring, int nt, int apt, int u, int nl, bool multi_fix, bool ellipse, int grid,
                              cudaStream_t stream)
 {
 #ifdef PIB_V6_VARIANTS
 #define PIB_V6_TRY(R, T, A, UU) \
-    if (ring == R && nt == T && apt == A && u == UU) return launch_pair_ring6_t<R, T, A, UU, false>(p, multi_fix, ellipse, grid, stream)
+    if (ring == R && nt == T && apt == A && u == UU && nl == 2) return launch_pair_ring6_t<R, T, A, UU, 2, false>(p, multi_fix, ellipse, grid, stream)
     PIB_V6_TRY(16, 512, 1, 8);
     PIB_V6_TRY(16, 512, 1, 16);
     PIB_V6_TRY(16, 256, 2, 8);
     PIB_V6_TRY(12, 384, 2, 8);
-    PIB_V6_TRY(10, 384, 2, 8);
-    PIB_V6_TRY(16, 384, 1, 8);
     PIB_V6_TRY(12, 640, 1, 8);
     PIB_V6_TRY(10, 768, 1, 8);
-    PIB_V6_TRY(8, 768, 1, 8);
-    PIB_V6_TRY(8, 896, 1, 8);
-    PIB_V6_TRY(12, 640, 1, 16);
-    PIB_V6_TRY(10, 768, 1, 16);
 #undef PIB_V6_TRY
 #else
-    if (ring == 16 && nt == 512 && apt == 1 && u == 8) return launch_pair_ring6_t<16, 512, 1, 8, true>(p, multi_fix, ellipse, grid, stream);
-    if (ring == 32 && nt == 256 && apt == 1 && u == 8) return launch_pair_ring6_t<32, 256, 1, 8, true>(p, multi_fix, ellipse, grid, stream);
+    if (ring == 16 && nt == 512 && apt == 1 && u == 8 && nl == 2) return launch_pair_ring6_t<16, 512, 1, 8, 2, true>(p, multi_fix, ellipse, grid, stream);
+    if (ring == 32 && nt == 256 && apt == 1 && u == 8 && nl == 2) return launch_pair_ring6_t<32, 256, 1, 8, 2, true>(p, multi_fix, ellipse, grid, stream);
+    if (ring == 32 && nt == 256 && apt == 1 && u == 8 && nl == 4) return launch_pair_ring6_t<32, 256, 1, 8, 4, true>(p, multi_fix, ellipse, grid, stream);
+    if (ring == 16 && nt == 512 && apt == 1 && u == 8 && nl == 4) return launch_pair_ring6_t<16, 512, 1, 8, 4, true>(p, multi_fix, ellipse, grid, stream);
 #endif
     set_error("pair_ring6_kernel: variant not built");
     return PIB_ERR_UNSUPPORTED;
@@ -1332,11 +1328,11 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         // lags between ONE warp's 32 * APT points and a B tile
         const char *ver_env = std::getenv("PIB_PAIR_V");
         bool v6 = !(ver_env && ver_env[0] == '5');
-        int v6_apt = 1, v6_u = 8;
+        int v6_apt = 1, v6_u = 8, v6_nl = 2;
         if (v6 && !(force_full && force_full[0] == '1') && n_lags <= MAX_SLOTS - 2) {
             const double span1 = 1.5 * d90_scaled / min_width + 2.0;     // A points per warp = 32: box ~ half a tile's diagonal
             if (span1 <= 16.0) { ring = 16; ring_nt = 512; use_ring = true; }
-            else if (span1 <= 34.0) { ring = 32; ring_nt = 256; use_ring = true; }
+            else if (span1 <= 40.0) { ring = 32; ring_nt = 256; use_ring = true; }      // (tile pairs wider than the ring are swept per window)
             else use_ring = false;
             const char *force_ring = std::getenv("PIB_FORCE_RING");
             if (force_ring && force_ring[0] == '1') {
@@ -1347,6 +1343,12 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             if (ring_env && use_ring) {
                 if (ring_env[0] == '1' && ring_env[1] == '6') { ring = 16; ring_nt = 512; } else { ring = 32; ring_nt = 256; }
             }
+            // lags per group: a group of 8 consecutive points spans about a quarter of its tile's diagonal; when that is more
+            // than ~1.3 lag widths (sparse points, fine lags, stretched ellipses) most groups straddle three lags or more
+            // and the four-lag scheme (three cumulative masks per pair, four ring updates per group) pays
+            v6_nl = (0.25 * d90_scaled <= 1.3 * min_width) ? 2 : 4;
+            const char *nl_env = std::getenv("PIB_LAGS_PER_GROUP");
+            if (nl_env && (nl_env[0] == '2' || nl_env[0] == '4')) v6_nl = nl_env[0] - '0';
             // PIB_V6 = "apt,u,threads,ring" picks another build of the kernel for A/B measurements, e.g. "2,8,384,12"
             const char *v6_env = std::getenv("PIB_V6");
             if (v6_env && use_ring) {
@@ -1453,14 +1455,14 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             }
             {
                 char name[96];
-                if (use_ring && v6) std::snprintf(name, sizeof(name), "pair_ring6_kernel<ring %d, %d threads, %d A/thread, groups of %d%s>", ring, ring_nt, v6_apt, v6_u, n_dirs > 0 ? ", ellipse" : "");
+                if (use_ring && v6) std::snprintf(name, sizeof(name), "pair_ring6_kernel<ring %d, %d threads, %d A/thread, groups of %d over %d lags%s>", ring, ring_nt, v6_apt, v6_u, v6_nl, n_dirs > 0 ? ", ellipse" : "");
                 else if (use_ring) std::snprintf(name, sizeof(name), "pair_ring_kernel<ring %d, %d threads%s>", ring, ring_nt, n_dirs > 0 ? ", ellipse" : "");
                 else std::snprintf(name, sizeof(name), "pair_kernel<%d threads%s>", nt, n_dirs > 0 ? ", ellipse" : "");
                 set_kernel_name(PIB_T_PAIR, name);
             }
             timing_begin(PIB_T_PAIR, stream);
             if (use_ring && v6) {
-                rc = launch_pair_ring6(p, ring, ring_nt, v6_apt, v6_u, fix2 > 1, n_dirs > 0, grid, stream);
+                rc = launch_pair_ring6(p, ring, ring_nt, v6_apt, v6_u, v6_nl, fix2 > 1, n_dirs > 0, grid, stream);
             } else if (use_ring) {
                 const size_t smem = (size_t)(ring + 2) * ring_nt * (sizeof(double2) + sizeof(uint32_t));
 #define PIB_LAUNCH_RING(R, T, F, E)                                                                                     \

@@ -17,6 +17,9 @@ VARIANTS = {
     "default": {},
     "ring16": {"PIB_FORCE_RING": "1", "PIB_RING": "16"},
     "ring32": {"PIB_FORCE_RING": "1", "PIB_RING": "32"},
+    "ring32_four_lags": {"PIB_FORCE_RING": "1", "PIB_RING": "32", "PIB_LAGS_PER_GROUP": "4"},
+    "ring16_four_lags": {"PIB_FORCE_RING": "1", "PIB_RING": "16", "PIB_LAGS_PER_GROUP": "4"},
+    "ring16_v5": {"PIB_FORCE_RING": "1", "PIB_RING": "16", "PIB_PAIR_V": "5"},
     "full": {"PIB_FORCE_FULL": "1"},
     "ring16_pairwise": {"PIB_FORCE_RING": "1", "PIB_RING": "16", "PIB_GROUP_PATH": "0", "PIB_BALANCE": "0"},
 }

@@ -161,19 +161,29 @@ def test_generic_kernel_matches_tiled_kernel(pib, monkeypatch):
         np.testing.assert_allclose(a["sum_sq"], b["sum_sq"], rtol=1e-12)
 
 
+@pytest.mark.parametrize("version", ["6", "5"])
+@pytest.mark.parametrize("lags_per_group", ["2", "4"])
 @pytest.mark.parametrize("ring", ["32", "16"])
 @pytest.mark.parametrize("n,step,maxr", [(30000, 2000.0, 40500.0), (5000, 250.0, 30000.0), (1000, 500.0, 40500.0)])
-def test_ring_kernel_vs_oracle(pib, oracle, monkeypatch, n, step, maxr, ring):
-    """The ring-window kernel (the 1M-point fast path) forced onto sizes the oracle can check:
-    coarse lags (ring slots only), fine lags (tile pairs wider than the ring -> overflow path)."""
+def test_ring_kernel_vs_oracle(pib, oracle, monkeypatch, n, step, maxr, ring, lags_per_group, version):
+    """The ring-window kernels (the 1M-point fast path) forced onto sizes the oracle can check:
+    coarse lags (ring slots only), fine lags (tile pairs wider than the ring -> overflow path); the two-lag and the
+    four-lag group scheme of pair_ring6_kernel and the round-1 kernel (PIB_PAIR_V=5, the dz-form)."""
     from pyinterpolate_b200 import _lib
+    if version == "5" and lags_per_group == "4":
+        pytest.skip("the round-1 kernel has no four-lag scheme")
     pts = dem_like_field(n, seed=31)
     lags = np.arange(step, maxr, step)
     monkeypatch.setenv("PIB_FORCE_RING", "1")
     monkeypatch.setenv("PIB_RING", ring)                    # 32-slot ring x 256 threads or 16-slot ring x 512 threads
+    monkeypatch.setenv("PIB_LAGS_PER_GROUP", lags_per_group)
+    monkeypatch.setenv("PIB_PAIR_V", version)
     got = _lib.variogram_host(pts, lags)
+    assert ("ring6" in _lib.last_kernel_name(_lib.KERNEL_PAIR)) == (version == "6")
     monkeypatch.delenv("PIB_FORCE_RING")
     monkeypatch.delenv("PIB_RING")
+    monkeypatch.delenv("PIB_LAGS_PER_GROUP")
+    monkeypatch.delenv("PIB_PAIR_V")
     want = oracle.variogram_sums(pts, lags)
     np.testing.assert_array_equal(got["count"], want["count"])
     np.testing.assert_allclose(got["sum_sq"], want["sum_sq"], rtol=RTOL)
@@ -182,19 +192,23 @@ def test_ring_kernel_vs_oracle(pib, oracle, monkeypatch, n, step, maxr, ring):
     assert got["pairs_evaluated"] <= n * (n - 1) // 2
 
 
+@pytest.mark.parametrize("lags_per_group", ["2", "4"])
 @pytest.mark.parametrize("ring", ["32", "16"])
-def test_ring_kernel_ellipse_vs_oracle(pib, oracle, monkeypatch, ring):
-    """Ellipse directions through the ring kernel (whitened bounding boxes for culling and lag windows)."""
+def test_ring_kernel_ellipse_vs_oracle(pib, oracle, monkeypatch, ring, lags_per_group):
+    """Ellipse directions through the ring kernel (whitened bounding boxes for culling and lag windows), two-lag and
+    four-lag groups."""
     from pyinterpolate_b200 import _lib, core
     pts = dem_like_field(12000, seed=35)
-    lags = np.arange(3000.0, 40500.0, 3000.0)
+    lags = np.arange(3000.0, 40500.0, 3000.0) if lags_per_group == "2" else np.arange(700.0, 40500.0, 700.0)
     angles = [90, 0, 45, 135, 15]
     W = np.stack([core.define_whitening_matrix(a, 0.2) for a in angles]).reshape(-1, 4)
     monkeypatch.setenv("PIB_FORCE_RING", "1")
     monkeypatch.setenv("PIB_RING", ring)
+    monkeypatch.setenv("PIB_LAGS_PER_GROUP", lags_per_group)
     got = _lib.variogram_host(pts, lags, lower=core.ellipse_lower_limits(lags), W=W)
     monkeypatch.delenv("PIB_FORCE_RING")
     monkeypatch.delenv("PIB_RING")
+    monkeypatch.delenv("PIB_LAGS_PER_GROUP")
     want = oracle.variogram_sums(pts, lags, angles, 0.2)
     np.testing.assert_array_equal(got["count"], want["count"])
     np.testing.assert_allclose(got["sum_sq"], want["sum_sq"], rtol=RTOL)
