@@ -270,11 +270,11 @@ def run_b200(args):
     fp64_peak = _lib.fp64_peak_tflops()
 
     # ---- device-resident timing: K steps between barriers, CUDA events, max over ranks -------------
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local_rank)                 # started ahead of the warm-up: nvidia-smi needs ~0.3 s to deliver its
+    sampler.start()                                    # first sample and an 8-GPU timed region is shorter than that
+    for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms, evaluated = [], 0
     ev0.record()

@@ -965,8 +965,11 @@ struct GjSmem {
     int dup;
 };
 
+#ifndef PIB_GJ64_THREADS
+#define PIB_GJ64_THREADS 384
+#endif
 template <int K>
-__host__ __device__ constexpr int gj_threads() { return K == 64 ? 384 : 256; }
+__host__ __device__ constexpr int gj_threads() { return K == 64 ? PIB_GJ64_THREADS : 256; }
 
 template <int K, int MODE>      // MODE: PIB_KRIGE_ORDINARY, PIB_KRIGE_SIMPLE or PIB_KRIGE_BOTH
 __global__ void __launch_bounds__(gj_threads<K>(), K == 32 ? 2 : 1) solve_gj_kernel(const SolveParams p)

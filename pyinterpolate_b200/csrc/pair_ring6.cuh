@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
 
     const int n_tiles = p.n_tiles;
     const int n_atiles = (n_tiles + A_TILES - 1) / A_TILES;
-    const int n_chunks = (n_tiles + CHUNK - 1) / CHUNK;
+    const int chunk = p.chunk;                     // B tiles per work item (<= CHUNK; smaller for many ranks: finer load balance)
+    const int n_chunks = (n_tiles + chunk - 1) / chunk;
     const int64_t n_items = (int64_t)n_atiles * n_chunks;
     uint32_t seq = 0;
     unsigned long long evaluated = 0;              // lane 0 of every warp counts its warp's pairs
@@ -142,8 +143,8 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
         const int64_t a0 = (item / n_chunks) * NA;            // first point of the CTA's A sub-tile
         const int ta = (int)(a0 / TILE);
         const int ta_last = min(ta + A_TILES, n_tiles) - 1;
-        const int tb0 = (int)(item % n_chunks) * CHUNK;
-        const int tb1 = min(tb0 + CHUNK, n_tiles);
+        const int tb0 = (int)(item % n_chunks) * chunk;
+        const int tb1 = min(tb0 + chunk, n_tiles);
         if (tb1 <= ta || a0 >= p.n) continue;
         const int tb_first = max(tb0, ta);
 
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                 abox.z = fmax(abox.z, o.z); abox.w = fmax(abox.w, o.w);
             }
             uint64_t m = 0;
-            for (int h = 0; h < CHUNK / 32; ++h) {
+            for (int h = 0; h < (chunk + 31) / 32; ++h) {
                 const int tb = tb0 + h * 32 + lane;
                 bool live = false;
                 if (tb >= tb_first && tb < tb1) {
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
             if (lane == 0) s_live = m;
         }
         // ---- my warp: the lag slots each B tile can touch for MY A points (empty = skip the tile) ----------
-        for (int h = 0; h < CHUNK / 32; ++h) {
+        for (int h = 0; h < (chunk + 31) / 32; ++h) {
             const int tb = tb0 + h * 32 + lane;
             short2 r = make_short2(1, 0);                     // empty
             if (tb >= tb_first && tb < tb1) {

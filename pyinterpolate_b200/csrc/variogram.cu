@@ -61,6 +61,7 @@ struct PairParams {
     const double2 *gsum;         // [n_pad / 8] (sum z, sum z^2) over each group of 8 consecutive (sorted) points; z centred
     const int32_t *item_list;    // ring kernel: work items ordered by descending cost (NULL: natural order)
     const unsigned *n_live_items;  // number of items with at least one live tile pair (device scalar)
+    int chunk;                     // pair_ring6_kernel / item_cost_kernel: B tiles per work item (<= CHUNK)
     const int *run_flag;           // NULL, or device flag: the kernel returns at once when it is 0 (conditional re-run)
 };
 
@@ -846,11 +847,12 @@ __global__ void item_cost_kernel(const PairParams p, int a_tiles, int64_t n_item
     const int lane = threadIdx.x & 31;
     if (item >= n_items) return;
     const int n_tiles = p.n_tiles;
-    const int n_chunks = (n_tiles + CHUNK - 1) / CHUNK;
+    const int chunk = p.chunk;
+    const int n_chunks = (n_tiles + chunk - 1) / chunk;
     const int ta = (int)(item / n_chunks) * a_tiles;
     const int ta_last = min(ta + a_tiles, n_tiles) - 1;
-    const int tb0 = (int)(item % n_chunks) * CHUNK;
-    const int tb1 = min(tb0 + CHUNK, n_tiles);
+    const int tb0 = (int)(item % n_chunks) * chunk;
+    const int tb1 = min(tb0 + chunk, n_tiles);
     int cost = 0;
     if (tb1 > ta && (int64_t)ta * TILE < p.n) {
         double4 abox = p.tile_box[ta];
@@ -860,7 +862,7 @@ __global__ void item_cost_kernel(const PairParams p, int a_tiles, int64_t n_item
             abox.z = fmax(abox.z, o.z); abox.w = fmax(abox.w, o.w);
         }
         const int tb_first = max(tb0, ta);
-        for (int h = 0; h < CHUNK / 32; ++h) {
+        for (int h = 0; h < (chunk + 31) / 32; ++h) {
             const int tb = tb0 + h * 32 + lane;
             bool live = false;
             if (tb >= tb_first && tb < tb1) {
@@ -877,7 +879,7 @@ __global__ void item_cost_kernel(const PairParams p, int a_tiles, int64_t n_item
         }
     }
     if (lane == 0) {
-        keys[item] = (uint32_t)(CHUNK - cost);
+        keys[item] = (uint32_t)(chunk - cost);
         vals[item] = (int32_t)item;
         if (cost) atomicAdd(n_live, 1u);
     }
@@ -1260,7 +1262,8 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         const int fix2 = fix_steps;
 
         const int n_tiles = (int)(sp.n_pad / TILE);
-        const int n_chunks = (n_tiles + CHUNK - 1) / CHUNK;
+        int chunk = CHUNK;                         // B tiles per work item; pair_ring6_kernel takes fewer for many ranks (below)
+        int n_chunks = (n_tiles + CHUNK - 1) / CHUNK;
 
         // ring-window kernel or full-histogram kernel?  The ring needs a tile pair to span < 32 lags:
         // estimate the span from the tile bounding boxes (A sub-tile = 2 tiles, B tile = 1 tile).
@@ -1359,6 +1362,14 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             }
         } else v6 = false;
         if (!use_ring) v6 = false;
+        if (v6) {
+            // PIB_PAIR_CHUNK: finer work items.  Measured at 8 ranks (148 CTAs x 8 leave ~19 items of 64 tiles per CTA):
+            // 16-tile items 22.80 ms against 22.30 ms for 64-tile items — the per-item set-up outweighs the finer
+            // balance, so the default stays CHUNK
+            const char *chunk_env = std::getenv("PIB_PAIR_CHUNK");
+            if (chunk_env && std::atoi(chunk_env) >= 1 && std::atoi(chunk_env) <= CHUNK) chunk = std::atoi(chunk_env);
+            n_chunks = (n_tiles + chunk - 1) / chunk;
+        }
         const int a_per_cta = use_ring ? ring_nt * (v6 ? v6_apt : 1) : nt;
         if (use_ring) nt = ring_nt;
         const int64_t a_tiles = use_ring ? (n_tiles + a_per_cta / TILE - 1) / (a_per_cta / TILE) : (int64_t)n_tiles * (TILE / nt);
@@ -1379,7 +1390,7 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         p.gsum = nullptr;
         double *d_mean = nullptr;                  // ring kernel: mean of z (its sums come out centred)
         int64_t guard_groups = 0;                  // ring kernel: number of group sums (cancellation guard)
-        p.item_list = nullptr; p.n_live_items = nullptr; p.run_flag = nullptr;
+        p.item_list = nullptr; p.n_live_items = nullptr; p.run_flag = nullptr; p.chunk = chunk;
         const int64_t n_items_all = a_tiles * n_chunks;            // over all ranks
         const char *bal_env = std::getenv("PIB_BALANCE");
         const bool balance = use_ring && n_items_all < ((int64_t)1 << 31) && !(bal_env && bal_env[0] == '0');
