@@ -41,7 +41,7 @@ template <int RING, int NT, int APT>
 static size_t ring6_smem_bytes(int n_slots, int lut_n)
 {
     const size_t na = (size_t)NT * APT;
-    size_t b = (size_t)(RING + 1) * na * 20;                    // ring: per slot NA x (double2 sums) then NA x u32 counts
+    size_t b = (size_t)(RING + 1) * (na * 16 + (size_t)NT * 4);  // ring: per slot NA x (double2 sums) then NT x 4 bytes of u16 counts
     b += (size_t)(n_slots + 4) * sizeof(SlotInfo);
     b += (size_t)(NT / 32) * CHUNK * sizeof(short2);
     b += ((size_t)lut_n * 2 + 15) / 16 * 16;
@@ -62,7 +62,9 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
     constexpr int A_TILES = NA / TILE;
     constexpr int NW = NT / 32;
     constexpr int WA = 32 * APT;                   // A points per warp (consecutive on the Hilbert curve)
-    constexpr int SLOT_BYTES = NA * 20;
+    // 16-bit counts (an A point meets at most CHUNK * TILE = 8192 pairs between folds), the counts of a thread's A points
+    // in ONE 32-bit word: a thread stays in its own bank whatever ring block each lane addresses
+    constexpr int SLOT_BYTES = NA * 16 + NT * 4;
     constexpr int SB16 = SLOT_BYTES / 16;
     constexpr int CNT_OFF = NA * 16;               // counts follow the sums inside a slot block
     constexpr uint32_t TRASH16 = RING * SB16;
@@ -73,12 +75,14 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
     static_assert(U == 8 || U == 16, "groups of 8 or 16 pairs");
     static_assert(NL == 2 || NL == 4, "a group may span two or four consecutive lags");
     static_assert(NL == 2 || APT == 1, "the four-lag scheme is built for one A point per thread");
-    static_assert((RING + 1) * SB16 < 65536, "ring offsets are 16-bit");
-    __shared__ __align__(16) double2 s_txy[2][TILE];
-    __shared__ __align__(16) double s_tz[2][TILE];
-    __shared__ __align__(16) double2 s_gs[2][TILE / 8];
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ uint64_t s_live;
+    static_assert(APT <= 2, "the counts of a thread's A points share one 32-bit word");
+    static_assert((RING + 1) * SB16 < 65536 && SLOT_BYTES % 16 == 0, "ring offsets are 16-bit, in 16-byte units");
+    constexpr int STAGES = 4;                      // B tiles in flight: the warps of a CTA may drift apart by STAGES - 1 tiles
+    __shared__ __align__(16) double2 s_txy[STAGES][TILE];
+    __shared__ __align__(16) double s_tz[STAGES][TILE];
+    __shared__ __align__(16) double2 s_gs[STAGES][TILE / 8];
+    __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES];     // TMA landed / every warp is done with the buffer
+    __shared__ uint64_t s_live[2];                 // live B tiles of the item (double-buffered over consecutive items)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_slots = p.n_slots, n_lags = n_slots - 2;
@@ -94,13 +98,13 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
 #pragma unroll
     for (int k = 0; k < APT; ++k) {
         my_acc[k] = (k * NT + tid) * 16;
-        my_cnt[k] = CNT_OFF + (k * NT + tid) * 4;
+        my_cnt[k] = CNT_OFF + tid * 4 + k * 2;
     }
     for (int s = 0; s <= RING; ++s) {
 #pragma unroll
         for (int k = 0; k < APT; ++k) {
             *reinterpret_cast<double2 *>(ring + s * SLOT_BYTES + my_acc[k]) = make_double2(0.0, 0.0);
-            *reinterpret_cast<uint32_t *>(ring + s * SLOT_BYTES + my_cnt[k]) = 0u;
+            *reinterpret_cast<uint16_t *>(ring + s * SLOT_BYTES + my_cnt[k]) = 0;
         }
     }
     for (int s = tid; s < n_slots + 4; s += NT) {          // (entries behind the last slot: +inf thresholds, trash block)
@@ -117,8 +121,10 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
         for (int s = tid; s < p.lut2_n; s += NT) lut_w[s] = p.lut2[s];
     }
     if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        for (int b = 0; b < STAGES; ++b) {
+            mbar_init(&s_full[b], 1);
+            mbar_init(&s_empty[b], NW);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -128,7 +134,8 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
     const int chunk = p.chunk;                     // B tiles per work item (<= CHUNK; smaller for many ranks: finer load balance)
     const int n_chunks = (n_tiles + chunk - 1) / chunk;
     const int64_t n_items = (int64_t)n_atiles * n_chunks;
-    uint32_t seq = 0;
+    uint32_t seq = 0, pseq = 0;                    // B tiles consumed by my warp / B tile loads issued (thread 0), over the whole kernel
+    uint32_t item_no = 0;
     unsigned long long evaluated = 0;              // lane 0 of every warp counts its warp's pairs
     double *my_partial = p.partial + ((size_t)blockIdx.x * NW + warp) * n_slots * 4;
     const int base_hi = p.lut2_base, lut_last = p.lut2_n - 1;
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                 }
                 m |= (uint64_t)__ballot_sync(0xffffffffu, live) << (32 * h);
             }
-            if (lane == 0) s_live = m;
+            if (lane == 0) s_live[item_no & 1] = m;
         }
         // ---- my warp: the lag slots each B tile can touch for MY A points (empty = skip the tile) ----------
         for (int h = 0; h < (chunk + 31) / 32; ++h) {
@@ -222,83 +229,105 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
             }
             s_range[h * 32 + lane] = r;
         }
-        __syncthreads();
-        uint64_t live = s_live;
-        if (live == 0) { __syncthreads(); continue; }
+        __syncthreads();                                      // the one CTA-wide barrier of an item (s_live is double-buffered)
+        uint64_t live = s_live[item_no & 1];
+        ++item_no;
+        if (live == 0) continue;
 
-        int win_lo = 0x7fff, win_hi = 0;                      // lag slots my warp touched since its last fold (empty)
+        // My warp's ring window: lag slots [w_lo, w_lo + RING), slot s in ring block s % RING; w_lo < 0 = every block is empty.
+        // The window SLIDES: when a tile needs slots beyond it, only the blocks that leave the window are folded into the
+        // warp's global partials (about half a block per tile on BASELINE config 2 with RING = 10, against 1.7 for
+        // folding the whole ring each time the union of the tiles' ranges outgrew it).
+        int w_lo = -1;
 
-        // fold the rings of my warp into its global partials (lane l owns ring block l)
-        auto fold = [&]() {
+        // fold the ring blocks of slots [s_from, s_to) (inside the window).  Every thread turns ITS A points' entries of a block
+        // into the block's four sums (sum dz^2 = c z^2 - 2 z S1 + S2;  sum z_i z_j = z S1;  sum (z_i + z_j) = c z + S1), a
+        // butterfly adds them over the warp in a fixed order, and lane `block` adds the totals to the warp's partials.  (The
+        // first version let lane r walk block r over the warp's points: a dependent shared-memory chain per point that cost
+        // about as much as a whole B tile.)
+        auto evict = [&](int s_from, int s_to) {
             __syncwarp();
-            if (win_hi >= win_lo) {
-                // the window's slot that lives in ring block `lane`
-                const int abs_slot = win_lo + ((lane - win_lo % RING) + RING) % RING;
+#pragma unroll 1
+            for (int sl = s_from; sl < s_to; ++sl) {
+                const int r = sl % RING;
                 double v_sq = 0.0, v_prod = 0.0, v_val = 0.0;
-                unsigned long long v_cnt = 0;
+                unsigned v_cnt = 0;
 #pragma unroll
                 for (int k = 0; k < APT; ++k) {
-                    unsigned char *blk = ring + min(lane, RING - 1) * SLOT_BYTES + (k * NT + warp * 32) * 16;
-                    unsigned char *cblk = ring + min(lane, RING - 1) * SLOT_BYTES + CNT_OFF + (k * NT + warp * 32) * 4;
-                    for (int t = 0; t < 32; ++t) {
-                        const int tt = (t + lane) & 31;       // rotate so the lanes of a quarter-warp hit different banks
-                        const double z = __shfl_sync(0xffffffffu, zi[k], tt);
-                        if (lane < RING) {
-                            const uint32_t c = *reinterpret_cast<const uint32_t *>(cblk + tt * 4);
-                            if (c) {
-                                const double2 a = *reinterpret_cast<const double2 *>(blk + tt * 16);
-                                const double cd = (double)c;
-                                // sum dz^2 = c z^2 - 2 z S1 + S2;  sum z_i z_j = z S1;  sum (z_i + z_j) = c z + S1
-                                v_sq += __fma_rn(z, __fma_rn(cd, z, -2.0 * a.x), a.y);
-                                v_prod = __fma_rn(z, a.x, v_prod);
-                                v_val += __fma_rn(cd, z, a.x);
-                                v_cnt += c;
-                                *reinterpret_cast<double2 *>(blk + tt * 16) = make_double2(0.0, 0.0);
-                                *reinterpret_cast<uint32_t *>(cblk + tt * 4) = 0u;
-                            }
-                        }
-                    }
+                    double2 *ap = reinterpret_cast<double2 *>(ring + r * SLOT_BYTES + my_acc[k]);
+                    uint16_t *cp = reinterpret_cast<uint16_t *>(ring + r * SLOT_BYTES + my_cnt[k]);
+                    const double2 a = *ap;
+                    const unsigned c = *cp;
+                    *ap = make_double2(0.0, 0.0);
+                    *cp = 0;
+                    const double cd = (double)c, z = zi[k];
+                    v_sq += __fma_rn(z, __fma_rn(cd, z, -2.0 * a.x), a.y);
+                    v_prod = __fma_rn(z, a.x, v_prod);
+                    v_val += __fma_rn(cd, z, a.x);
+                    v_cnt += c;
                 }
-                if (lane < RING && v_cnt && abs_slot <= win_hi) {
-                    double *dst = my_partial + (size_t)abs_slot * 4;
-                    dst[0] += v_sq; dst[1] += v_prod; dst[2] += v_val;
-                    reinterpret_cast<unsigned long long *>(dst)[3] += v_cnt;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    v_sq += __shfl_xor_sync(0xffffffffu, v_sq, o);
+                    v_prod += __shfl_xor_sync(0xffffffffu, v_prod, o);
+                    v_val += __shfl_xor_sync(0xffffffffu, v_val, o);
+                    v_cnt += __shfl_xor_sync(0xffffffffu, v_cnt, o);
+                }
+                if (lane == r && v_cnt) {
+                    // fire-and-forget adds: a slot always lives in the same ring block, so the same lane issues all adds to an
+                    // address, in program order — the sums stay reproducible run to run
+                    double *dst = my_partial + (size_t)sl * 4;
+                    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst), "d"(v_sq) : "memory");
+                    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst + 1), "d"(v_prod) : "memory");
+                    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst + 2), "d"(v_val) : "memory");
+                    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(dst + 3), "l"((unsigned long long)v_cnt) : "memory");
                 }
             }
             __syncwarp();
-            win_lo = 0x7fff; win_hi = 0;
+        };
+        auto fold = [&]() {
+            if (w_lo >= 0) evict(w_lo, w_lo + RING);
+            w_lo = -1;
         };
 
-        int tb = tb0 + __ffsll((long long)live) - 1;
-        live &= live - 1;
+        // B tiles stream through STAGES buffers: thread 0 issues the loads STAGES - 1 tiles ahead (waiting for every warp to
+        // have released the buffer's previous tile), each warp waits for a tile to land, sweeps it and releases the buffer.
+        // No CTA-wide barrier per tile: warps that cull a tile, or finish it early, run ahead.
+        auto issue_tile = [&](int t) {
+            const uint32_t b = pseq % STAGES;
+            if (pseq >= STAGES) mbar_wait(&s_empty[b], ((pseq / STAGES) - 1) & 1);
+            mbar_expect_tx(&s_full[b], TILE_TX);
+            tma_load_1d(s_txy[b], p.xy + (size_t)t * TILE, TILE * sizeof(double2), &s_full[b]);
+            tma_load_1d(s_tz[b], p.z + (size_t)t * TILE, TILE * sizeof(double), &s_full[b]);
+            tma_load_1d(s_gs[b], p.gsum + (size_t)t * (TILE / U), (TILE / U) * sizeof(double2), &s_full[b]);
+            ++pseq;
+        };
+        uint64_t ahead = live;                                // thread 0: tiles not yet requested
         if (tid == 0) {
-            const uint32_t b = seq & 1;
-            mbar_expect_tx(&s_bar[b], TILE_TX);
-            tma_load_1d(s_txy[b], p.xy + (size_t)tb * TILE, TILE * sizeof(double2), &s_bar[b]);
-            tma_load_1d(s_tz[b], p.z + (size_t)tb * TILE, TILE * sizeof(double), &s_bar[b]);
-            tma_load_1d(s_gs[b], p.gsum + (size_t)tb * (TILE / U), (TILE / U) * sizeof(double2), &s_bar[b]);
-        }
-        while (true) {
-            const uint32_t b = seq & 1, phase = (seq >> 1) & 1;
-            const int tb_next = live ? tb0 + __ffsll((long long)live) - 1 : -1;
-            live &= live - 1;
-            if (tid == 0 && tb_next >= 0) {
-                const uint32_t nb = b ^ 1;
-                mbar_expect_tx(&s_bar[nb], TILE_TX);
-                tma_load_1d(s_txy[nb], p.xy + (size_t)tb_next * TILE, TILE * sizeof(double2), &s_bar[nb]);
-                tma_load_1d(s_tz[nb], p.z + (size_t)tb_next * TILE, TILE * sizeof(double), &s_bar[nb]);
-                tma_load_1d(s_gs[nb], p.gsum + (size_t)tb_next * (TILE / U), (TILE / U) * sizeof(double2), &s_bar[nb]);
+            for (int i = 0; i < STAGES - 1 && ahead; ++i) {
+                issue_tile(tb0 + __ffsll((long long)ahead) - 1);
+                ahead &= ahead - 1;
             }
+        }
+        while (live) {
+            const int tb = tb0 + __ffsll((long long)live) - 1;
+            live &= live - 1;
+            if (tid == 0 && ahead) {
+                issue_tile(tb0 + __ffsll((long long)ahead) - 1);
+                ahead &= ahead - 1;
+            }
+            const uint32_t b = seq % STAGES, phase = (seq / STAGES) & 1;
             // ---- my warp's ring window (warp-uniform) ---------------------------------------------------
             const short2 rng = s_range[tb - tb0];
             const bool mine = rng.y >= rng.x;                 // can any of my warp's points reach this tile?
             const bool wide = mine && (rng.y - rng.x >= RING);
             if (mine && !wide) {
-                const int nlo = min(win_lo, (int)rng.x), nhi = max(win_hi, (int)rng.y);
-                if (nhi - nlo >= RING) { fold(); win_lo = rng.x; win_hi = rng.y; }
-                else { win_lo = nlo; win_hi = nhi; }
+                const int l = rng.x, h = rng.y;
+                if (w_lo < 0) w_lo = max(1, l - (RING - (h - l + 1)) / 2);       // empty ring: the tile's range in the middle
+                else if (l < w_lo) { evict(max(l + RING, w_lo), w_lo + RING); w_lo = l; }
+                else if (h >= w_lo + RING) { evict(w_lo, min(h - RING + 1, w_lo + RING)); w_lo = h - RING + 1; }
             }
-            mbar_wait(&s_bar[b], phase);
+            mbar_wait(&s_full[b], phase);
             ++seq;
 
             if (mine) {
@@ -340,11 +369,11 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                     uint32_t off = s_slot[q].offs & 0xffffu;
                     if (wide_mode && !((unsigned)(q - wlo) < wlen)) off = TRASH16;
                     double2 *ap = reinterpret_cast<double2 *>(ring + off * 16 + my_acc[k]);
-                    uint32_t *cp = reinterpret_cast<uint32_t *>(ring + off * 16 + my_cnt[k]);
+                    uint16_t *cp = reinterpret_cast<uint16_t *>(ring + off * 16 + my_cnt[k]);
                     double2 a = *ap;
                     a.x += z; a.y = __fma_rn(z, z, a.y);
                     *ap = a;
-                    *cp += 1u;
+                    *cp = (uint16_t)(*cp + 1u);
                 };
 
                 // ---- one group of U B points, in two stages so that two groups are in flight ----------------------
@@ -421,7 +450,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                         if (!((unsigned)(q - wlo) < wlen)) o_lo = TRASH16;
                         if (!((unsigned)(q + 1 - wlo) < wlen)) o_hi = TRASH16;
                     }
-                    double h1a = 0.0, h1b = 0.0, h2a = 0.0, h2b = 0.0;
+                    double h1a, h1b, h2a, h2b;                // (started from the first pair: x + 0.0 is not free in fp64)
                     int ch = 0;
 #pragma unroll
                     for (int u = 0; u < U; u += 2) {
@@ -451,21 +480,26 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                         }
                         const double za = __hiloint2double(za_hi, __double2loint(zz.x));
                         const double zb = __hiloint2double(zb_hi, __double2loint(zz.y));
-                        h1a += za; h2a = __fma_rn(za, za, h2a);
-                        h1b += zb; h2b = __fma_rn(zb, zb, h2b);
+                        if (u == 0) {
+                            h1a = za; h2a = __dmul_rn(za, za);
+                            h1b = zb; h2b = __dmul_rn(zb, zb);
+                        } else {
+                            h1a += za; h2a = __fma_rn(za, za, h2a);
+                            h1b += zb; h2b = __fma_rn(zb, zb, h2b);
+                        }
                     }
                     const double h1 = h1a + h1b, h2 = h2a + h2b;
                     double2 *alo = reinterpret_cast<double2 *>(ring + o_lo * 16 + my_acc[k]);
                     double2 *ahi = reinterpret_cast<double2 *>(ring + o_hi * 16 + my_acc[k]);
-                    uint32_t *clo = reinterpret_cast<uint32_t *>(ring + o_lo * 16 + my_cnt[k]);
-                    uint32_t *chi = reinterpret_cast<uint32_t *>(ring + o_hi * 16 + my_cnt[k]);
+                    uint16_t *clo = reinterpret_cast<uint16_t *>(ring + o_lo * 16 + my_cnt[k]);
+                    uint16_t *chi = reinterpret_cast<uint16_t *>(ring + o_hi * 16 + my_cnt[k]);
                     double2 v_lo = *alo, v_hi = *ahi;
                     const uint32_t c_lo = *clo, c_hi = *chi;
                     v_lo.x += g1 - h1; v_lo.y += g2 - h2;
                     v_hi.x += h1;      v_hi.y += h2;
                     *alo = v_lo; *ahi = v_hi;               // both blocks are the trash block when they coincide: never read
-                    *clo = c_lo + (uint32_t)(n_in - ch);
-                    *chi = c_hi + (uint32_t)ch;
+                    *clo = (uint16_t)(c_lo + (uint32_t)(n_in - ch));
+                    *chi = (uint16_t)(c_hi + (uint32_t)ch);
                 };
                 // NL == 4: cumulative sums over the pairs above each of the three thresholds; slot q + i gets the difference of
                 // two consecutive ones (q: all - H0, q + 1: H0 - H1, q + 2: H1 - H2, q + 3: H2)
@@ -506,11 +540,11 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                     for (int i = 0; i < 4; ++i) {
                         // one slot after the other: two of the four may be the trash block
                         double2 *ap = reinterpret_cast<double2 *>(ring + o[i] * 16 + my_acc[0]);
-                        uint32_t *cp = reinterpret_cast<uint32_t *>(ring + o[i] * 16 + my_cnt[0]);
+                        uint16_t *cp = reinterpret_cast<uint16_t *>(ring + o[i] * 16 + my_cnt[0]);
                         double2 v = *ap;
                         v.x += a1[i]; v.y += a2[i];
                         *ap = v;
-                        *cp += (uint32_t)n[i];
+                        *cp = (uint16_t)(*cp + (uint32_t)n[i]);
                     }
                 };
                 // stage B: sums and ring updates
@@ -596,11 +630,11 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                                     if (!(jbase + j0 + u > ig[k])) off = TRASH16;                   // keep i < j only
                                     if (wide_mode && !((unsigned)((int)((ea[k][u] - slot_sa) >> 4) - wlo) < wlen)) off = TRASH16;
                                     double2 *ap = reinterpret_cast<double2 *>(ring + off * 16 + my_acc[k]);
-                                    uint32_t *cp = reinterpret_cast<uint32_t *>(ring + off * 16 + my_cnt[k]);
+                                    uint16_t *cp = reinterpret_cast<uint16_t *>(ring + off * 16 + my_cnt[k]);
                                     double2 a = *ap;
                                     a.x += zj[u]; a.y = __fma_rn(zj[u], zj[u], a.y);
                                     *ap = a;
-                                    *cp += 1u;
+                                    *cp = (uint16_t)(*cp + 1u);
                                 }
                             }
                         }
@@ -637,14 +671,13 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                     for (int w0 = rng.x; w0 <= rng.y; w0 += RING) {
                         wlo = w0; wlen = (unsigned)(min(w0 + RING - 1, (int)rng.y) - w0 + 1);
                         sweep(true);
-                        win_lo = w0; win_hi = w0 + (int)wlen - 1;
+                        w_lo = w0;
                         fold();
                     }
                 }
             }
-            __syncthreads();                                  // everyone is done with buffer b
-            if (tb_next < 0) break;
-            tb = tb_next;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[b]);          // my warp is done with buffer b
         }
         fold();                                               // my z_i changes with the next item
     }

@@ -76,6 +76,10 @@ static __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t by
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+static __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 static __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(
@@ -1113,7 +1117,7 @@ template <int RING, int NT, int APT, int U, int NL, bool ALL>
 static int launch_pair_ring6_t(const PairParams &p, bool multi_fix, bool ellipse, int grid, cudaStream_t stream)
 {
     const size_t smem = ring6_smem_bytes<RING, NT, APT>(p.n_slots, p.lut2_n);
-    PIB_CHECK(smem + 8192 <= (size_t)MAX_SMEM, PIB_ERR_UNSUPPORTED, "pair_ring6_kernel: tables do not fit in shared memory");
+    PIB_CHECK(smem + 14336 <= (size_t)MAX_SMEM, PIB_ERR_UNSUPPORTED, "pair_ring6_kernel: tables do not fit in shared memory");   // + static: 4 B-tile buffers
 #define PIB_L6(M, E)                                                                                                              \
     do {                                                                                                                          \
         PIB_CUDA(cudaFuncSetAttribute(pair_ring6_kernel<RING, NT, APT, U, NL, M, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -1144,8 +1148,12 @@ static int launch_pair_ring6(const PairParams &p, int ring, int nt, int apt, int
     PIB_V6_TRY(12, 384, 2, 8);
     PIB_V6_TRY(12, 640, 1, 8);
     PIB_V6_TRY(10, 768, 1, 8);
+    PIB_V6_TRY(9, 512, 2, 8);
+    PIB_V6_TRY(10, 512, 2, 8);
+    PIB_V6_TRY(11, 512, 2, 8);
 #undef PIB_V6_TRY
 #else
+    if (ring == 10 && nt == 512 && apt == 2 && u == 8 && nl == 2) return launch_pair_ring6_t<10, 512, 2, 8, 2, true>(p, multi_fix, ellipse, grid, stream);
     if (ring == 16 && nt == 512 && apt == 1 && u == 8 && nl == 2) return launch_pair_ring6_t<16, 512, 1, 8, 2, true>(p, multi_fix, ellipse, grid, stream);
     if (ring == 32 && nt == 256 && apt == 1 && u == 8 && nl == 2) return launch_pair_ring6_t<32, 256, 1, 8, 2, true>(p, multi_fix, ellipse, grid, stream);
     if (ring == 32 && nt == 256 && apt == 1 && u == 8 && nl == 4) return launch_pair_ring6_t<32, 256, 1, 8, 4, true>(p, multi_fix, ellipse, grid, stream);
@@ -1352,6 +1360,14 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             v6_nl = (0.25 * d90_scaled <= 1.3 * min_width) ? 2 : 4;
             const char *nl_env = std::getenv("PIB_LAGS_PER_GROUP");
             if (nl_env && (nl_env[0] == '2' || nl_env[0] == '4')) v6_nl = nl_env[0] - '0';
+            // two A points per thread (every B point read from shared memory serves two pairs): 64 A points per warp, so the
+            // ring shrinks to 10 slots to keep 1024 A points per CTA — taken when a warp's box against a B tile stays inside
+            // 10 lags (BASELINE config 2: 9 at the 99th percentile); the two-lag scheme only
+            const double span2 = 1.75 * d90_scaled / min_width + 2.0;    // 64 consecutive points: ~0.75 of a tile's diagonal
+            const char *apt_env = std::getenv("PIB_APT");
+            if (use_ring && v6_nl == 2 && !ring_env && !force_ring && span2 <= 10.0 && !(apt_env && apt_env[0] == '1')) {
+                v6_apt = 2; ring = 10; ring_nt = 512;
+            }
             // PIB_V6 = "apt,u,threads,ring" picks another build of the kernel for A/B measurements, e.g. "2,8,384,12"
             const char *v6_env = std::getenv("PIB_V6");
             if (v6_env && use_ring) {
