@@ -54,6 +54,9 @@ static size_t ring6_smem_bytes(int n_slots, int lut_n)
 #ifndef PIB_V6_PIPE
 #define PIB_V6_PIPE 0
 #endif
+#ifndef PIB_V6_HIW
+#define PIB_V6_HIW 1
+#endif
 
 template <int RING, int NT, int APT, int U, int NL, bool MULTI_FIX, bool ELLIPSE>
 __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
@@ -71,6 +74,8 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
     constexpr int CMP = PIB_V6_CMP;
     constexpr bool PIPE = PIB_V6_PIPE != 0;      // two groups in flight per thread (needs the registers)
     constexpr int NG = TILE / U;
+    // high-word fast path (two-lag scheme, plain distances): see sweep_hiw below
+    constexpr bool HIW = PIB_V6_HIW != 0 && NL == 2 && !ELLIPSE && U == 8;
     static_assert(NA % TILE == 0 && RING <= 32 && RING >= 4, "A sub-tile is whole tiles; one lane folds one ring slot");
     static_assert(U == 8 || U == 16, "groups of 8 or 16 pairs");
     static_assert(NL == 2 || NL == 4, "a group may span two or four consecutive lags");
@@ -587,6 +592,152 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                     }
                 };
 
+                // ---- high-word fast path ------------------------------------------------------------------------------------
+                // The squared distance is formed with ONE fused step, d2' = fma(dx, dx, dy * dy) (4 fp64 instructions instead of
+                // the 5 of the un-fused reference order), and only its HIGH word is kept: the lag of a pair is decided by
+                // hi(d2') > hi(T).  d2' is at most one ulp away from the reference's d2, so whenever hi(d2') != hi(T) both sit
+                // on the same side of T and the decision is exactly the reference's (the host clears p.hiw_ok for a threshold
+                // whose low word is all ones, the one pattern where one ulp could cross T between two high words).  A group
+                // with a pair ON the threshold's high word (relative band 2^-20: ~1 % of the warp-wide groups) is redone by the
+                // exact stages above, like a group with a pair beyond its second lag.
+                // The stages of consecutive groups are interleaved in ONE basic block — distances + table lookup of group
+                // g + 1 (fp64 pipe) beside the compares, selects and ring updates of group g (integer pipe, shared memory) —
+                // which the 16 registers freed by dropping the low words pay for.
+                struct GrpH {
+                    int x[APT][U];             // high words of the squared distances
+                    int t_hi[APT];             // high word of the threshold between the group's first and second lag
+                    uint32_t offs[APT];
+                    bool redo;
+                };
+                auto stage_a_h = [&](int g, GrpH &s) __attribute__((always_inline)) {
+                    const int j0 = g * U;
+                    int mn[APT], mx[APT];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const double2 pj = bxy[j0 + u];
+#pragma unroll
+                        for (int k = 0; k < APT; ++k) {
+                            const double dx = __dsub_rn(xi[k], pj.x), dy = __dsub_rn(yi[k], pj.y);
+                            const int h = __double2hiint(__fma_rn(dx, dx, __dmul_rn(dy, dy)));
+                            s.x[k][u] = h;
+                            mn[k] = u ? min(mn[k], h) : h;
+                            mx[k] = u ? max(mx[k], h) : h;
+                        }
+                    }
+                    s.redo = false;
+#pragma unroll
+                    for (int k = 0; k < APT; ++k) {
+                        int idx = (mn[k] - base_hi) >> LUT2_SHIFT;
+                        idx = min(max(idx, 0), lut_last);
+                        unsigned short q0;
+                        asm("ld.shared.u16 %0, [%1];" : "=h"(q0) : "r"(lut_sa + 2u * (uint32_t)idx));
+                        uint32_t ea = slot_sa + 16u * (uint32_t)q0;
+                        int thi;
+                        if (MULTI_FIX) {
+                            while (true) {
+                                asm volatile("ld.shared.s32 %0, [%1+4];" : "=r"(thi) : "r"(ea));
+                                if (!(mn[k] > thi)) break;
+                                ea += 16u;
+                            }
+                        } else {
+                            asm("ld.shared.s32 %0, [%1+4];" : "=r"(thi) : "r"(ea));
+                            ea += (mn[k] > thi) ? 16u : 0u;
+                        }
+                        int e_tlo, e_next;
+                        asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(e_tlo), "=r"(s.t_hi[k]), "=r"(e_next), "=r"(s.offs[k]) : "r"(ea));
+                        bool on_edge = false;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) on_edge |= (s.x[k][u] == s.t_hi[k]);
+                        s.redo |= on_edge | (mx[k] >= e_next);
+                    }
+                };
+                auto stage_b_h = [&](int g, const GrpH &s) __attribute__((always_inline)) {
+                    const int j0 = g * U;
+                    const double2 gs = bgs[g];
+#pragma unroll
+                    for (int k = 0; k < APT; ++k) {
+                        const uint32_t o_lo = s.offs[k] & 0xffffu, o_hi = s.offs[k] >> 16;
+                        double h1a, h1b, h2a, h2b;
+                        int ch = 0;
+#pragma unroll
+                        for (int u = 0; u < U; u += 2) {
+                            const double2 zz = *reinterpret_cast<const double2 *>(bz + j0 + u);
+                            int za_hi, zb_hi;
+                            asm("{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %3, %4;\n\tselp.b32 %0, %2, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
+                                : "=r"(za_hi), "+r"(ch) : "r"(__double2hiint(zz.x)), "r"(s.x[k][u]), "r"(s.t_hi[k]));
+                            asm("{\n\t.reg .pred p;\n\tsetp.gt.s32 p, %3, %4;\n\tselp.b32 %0, %2, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
+                                : "=r"(zb_hi), "+r"(ch) : "r"(__double2hiint(zz.y)), "r"(s.x[k][u + 1]), "r"(s.t_hi[k]));
+                            const double za = __hiloint2double(za_hi, __double2loint(zz.x));
+                            const double zb = __hiloint2double(zb_hi, __double2loint(zz.y));
+                            if (u == 0) {
+                                h1a = za; h2a = __dmul_rn(za, za);
+                                h1b = zb; h2b = __dmul_rn(zb, zb);
+                            } else {
+                                h1a += za; h2a = __fma_rn(za, za, h2a);
+                                h1b += zb; h2b = __fma_rn(zb, zb, h2b);
+                            }
+                        }
+                        const double h1 = h1a + h1b, h2 = h2a + h2b;
+                        double2 *alo = reinterpret_cast<double2 *>(ring + o_lo * 16 + my_acc[k]);
+                        double2 *ahi = reinterpret_cast<double2 *>(ring + o_hi * 16 + my_acc[k]);
+                        uint16_t *clo = reinterpret_cast<uint16_t *>(ring + o_lo * 16 + my_cnt[k]);
+                        uint16_t *chi = reinterpret_cast<uint16_t *>(ring + o_hi * 16 + my_cnt[k]);
+                        double2 v_lo = *alo, v_hi = *ahi;
+                        const uint32_t c_lo = *clo, c_hi = *chi;
+                        v_lo.x += gs.x - h1; v_lo.y += gs.y - h2;
+                        v_hi.x += h1;        v_hi.y += h2;
+                        *alo = v_lo; *ahi = v_hi;
+                        *clo = (uint16_t)(c_lo + (uint32_t)(U - ch));
+                        *chi = (uint16_t)(c_hi + (uint32_t)ch);
+                    }
+                };
+                // group g's second stage beside group g + 1's first, in one basic block; a group that must be redone exactly only
+                // leaves its bit in `redo` — the exact stages run after the sweep, outside the hot loop's code
+                unsigned redo = 0;
+                auto step_h = [&](int g, const GrpH &cur, GrpH &nxt) __attribute__((always_inline)) {
+                    if (!__any_sync(0xffffffffu, cur.redo)) {
+                        // (first stage first: its shared-memory loads must not queue behind the ring stores of the second stage)
+                        stage_a_h(g + 1, nxt);
+                        stage_b_h(g, cur);
+                    } else {
+                        redo |= 1u << g;
+                        stage_a_h(g + 1, nxt);
+                    }
+                };
+                auto sweep_hiw = [&]() __attribute__((always_inline)) {
+                    if (PIB_V6_HIW == 2 || (PIB_V6_HIW == 1 && APT == 2)) {
+                        // one group after the other: the smallest loop body.  With two A points per thread the two chains already
+                        // overlap and the interleaved form below only costs instruction-cache misses (its body plus prologue and
+                        // epilogue is 19 KB against a 6 KB L0: 157.7 ms; this form: 147.7 ms)
+#pragma unroll 1
+                        for (int g = 0; g < NG; ++g) {
+                            GrpH s0;
+                            stage_a_h(g, s0);
+                            if (!__any_sync(0xffffffffu, s0.redo)) stage_b_h(g, s0);
+                            else redo |= 1u << g;
+                        }
+                    } else {
+                    GrpH s0, s1;
+                    stage_a_h(0, s0);
+#pragma unroll 1
+                    for (int g = 0; g < NG - 2; g += 2) {
+                        step_h(g, s0, s1);
+                        step_h(g + 1, s1, s0);
+                    }
+                    step_h(NG - 2, s0, s1);
+                    if (!__any_sync(0xffffffffu, s1.redo)) stage_b_h(NG - 1, s1);
+                    else redo |= 1u << (NG - 1);
+                    }
+#pragma unroll 1
+                    while (redo) {
+                        const int g = __ffs((int)redo) - 1;
+                        redo &= redo - 1;
+                        Grp e;
+                        stage_a(g, e);
+                        stage_b(g, e, false);
+                    }
+                };
+
                 auto sweep = [&](const bool wide_mode) __attribute__((always_inline)) {
                     if (diagonal || !p.group_path) {
                         // Per-pair path: tiles that overlap my CTA's own points (keep i < j only) and data whose groups of
@@ -638,6 +789,10 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                                 }
                             }
                         }
+                        return;
+                    }
+                    if (HIW && !wide_mode && p.hiw_ok) {
+                        sweep_hiw();
                         return;
                     }
                     if (PIPE) {

@@ -62,6 +62,7 @@ struct PairParams {
     const int32_t *item_list;    // ring kernel: work items ordered by descending cost (NULL: natural order)
     const unsigned *n_live_items;  // number of items with at least one live tile pair (device scalar)
     int chunk;                     // pair_ring6_kernel / item_cost_kernel: B tiles per work item (<= CHUNK)
+    int hiw_ok;                    // pair_ring6_kernel: no threshold has an all-ones low word (high-word fast path is exact)
     const int *run_flag;           // NULL, or device flag: the kernel returns at once when it is 0 (conditional re-run)
 };
 
@@ -86,7 +87,7 @@ static __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"     // suspend-time hint: fewer polls from waiting warps
         "@p bra DONE;\n"
         "bra WAIT_LOOP;\n"
         "DONE:\n"
@@ -1399,6 +1400,13 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         PairParams p;
         p.xy = sp.xy; p.z = sp.z; p.tile_box = sp.tile_box; p.n = n; p.n_tiles = n_tiles; p.n_slots = n_slots;
         p.upper = d_upper; p.max_d2 = up_lag[n_lags - 1];
+        p.hiw_ok = 1;
+        for (int sl = 0; sl < n_slots; ++sl) {
+            uint64_t bits;
+            std::memcpy(&bits, &up[sl], sizeof(bits));
+            if ((uint32_t)bits == 0xffffffffu) p.hiw_ok = 0;
+        }
+        { const char *hiw_env = std::getenv("PIB_HIW"); if (hiw_env && hiw_env[0] == '0') p.hiw_ok = 0; }
         p.shard_index = shard_index; p.shard_count = shard_count; p.partial = d_partial;
         p.pairs_evaluated = d_evaluated;
         p.lut2 = d_lut2; p.lut2_base = lut2_base; p.lut2_n = (int)lut2.size();
