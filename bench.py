@@ -449,12 +449,16 @@ def run_b200(args):
         m1 = min(m4, 4_000_000)
         b1, e1 = (rank * m1) // world, ((rank + 1) * m1) // world
         pib.ordinary_kriging(mdl1, pts, unk4[b1:min(e1, b1 + 2_200_000)], no_neighbors=32)
-        barrier()
-        t0 = time.perf_counter()
-        res1 = pib.ordinary_kriging(mdl1, pts, unk4[b1:e1], no_neighbors=32)
-        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t1s = []
+        for _ in range(2):                                   # best of two, like config 4 above
+            barrier()
+            t0 = time.perf_counter()
+            res1 = pib.ordinary_kriging(mdl1, pts, unk4[b1:e1], no_neighbors=32)
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t1s.append(float(tt))
+        tt = min(t1s)
         kriging["ok_k32_public_call"] = {"value": m1 / float(tt), "unit": "points/s", "unknown": m1, "known": n, "seconds": float(tt),
                                          "h2d_bytes": int(pts.nbytes * world + unk4[:m1].nbytes), "d2h_bytes": int(m1 * 4 * 8 + m1)}
         del res1

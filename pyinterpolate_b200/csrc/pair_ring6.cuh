@@ -45,6 +45,7 @@ static size_t ring6_smem_bytes(int n_slots, int lut_n)
     b += (size_t)(n_slots + 4) * sizeof(SlotInfo);
     b += (size_t)(NT / 32) * CHUNK * sizeof(short2);
     b += ((size_t)lut_n * 2 + 15) / 16 * 16;
+    b += (size_t)(n_slots + 4) * 16;                             // high-word slot table
     return b;
 }
 
@@ -96,7 +97,9 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
     SlotInfo *const s_slot = reinterpret_cast<SlotInfo *>(smem_raw + (size_t)(RING + 1) * SLOT_BYTES);
     short2 *const s_range = reinterpret_cast<short2 *>(s_slot + n_slots + 4) + warp * CHUNK;    // my warp's row
     const uint16_t *const s_lut = reinterpret_cast<const uint16_t *>(reinterpret_cast<short2 *>(s_slot + n_slots + 4) + NW * CHUNK);
-    const uint32_t slot_sa = smem_u32(s_slot), lut_sa = smem_u32(s_lut);
+    // high-word fast path: {high word of the slot's threshold, high word of the next one, ring byte offsets of this and the next slot}
+    int4 *const s_sloth = reinterpret_cast<int4 *>(const_cast<unsigned char *>(reinterpret_cast<const unsigned char *>(s_lut)) + ((size_t)p.lut2_n * 2 + 15) / 16 * 16);
+    const uint32_t slot_sa = smem_u32(s_slot), lut_sa = smem_u32(s_lut), sloth_sa = smem_u32(s_sloth);
 
     // my ring entries: sums at ring + 16 * off + my_acc[k], counts at ring + 16 * off + my_cnt[k]
     int my_acc[APT], my_cnt[APT];
@@ -104,6 +107,12 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
     for (int k = 0; k < APT; ++k) {
         my_acc[k] = (k * NT + tid) * 16;
         my_cnt[k] = CNT_OFF + tid * 4 + k * 2;
+    }
+    uint32_t acc_sa[APT], cnt_sa[APT];             // the same as 32-bit shared addresses of ring block 0
+#pragma unroll
+    for (int k = 0; k < APT; ++k) {
+        acc_sa[k] = smem_u32(ring) + (uint32_t)my_acc[k];
+        cnt_sa[k] = smem_u32(ring) + (uint32_t)my_cnt[k];
     }
     for (int s = 0; s <= RING; ++s) {
 #pragma unroll
@@ -120,6 +129,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
         const uint32_t o_hi = (s + 1 >= 1 && s + 1 <= n_lags) ? (uint32_t)((s + 1) % RING) * SB16 : TRASH16;
         e.offs = o_lo | (o_hi << 16);
         s_slot[s] = e;
+        s_sloth[s] = make_int4((int)(e.T >> 32), e.next_hi, (int)(o_lo * 16u), (int)(o_hi * 16u));
     }
     {
         uint16_t *lut_w = const_cast<uint16_t *>(s_lut);
@@ -606,7 +616,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                 struct GrpH {
                     int x[APT][U];             // high words of the squared distances
                     int t_hi[APT];             // high word of the threshold between the group's first and second lag
-                    uint32_t offs[APT];
+                    uint32_t off_lo[APT], off_hi[APT];   // ring byte offsets of the group's two lags
                     bool redo;
                 };
                 auto stage_a_h = [&](int g, GrpH &s) __attribute__((always_inline)) {
@@ -631,20 +641,20 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                         idx = min(max(idx, 0), lut_last);
                         unsigned short q0;
                         asm("ld.shared.u16 %0, [%1];" : "=h"(q0) : "r"(lut_sa + 2u * (uint32_t)idx));
-                        uint32_t ea = slot_sa + 16u * (uint32_t)q0;
+                        uint32_t ea = sloth_sa + 16u * (uint32_t)q0;
                         int thi;
                         if (MULTI_FIX) {
                             while (true) {
-                                asm volatile("ld.shared.s32 %0, [%1+4];" : "=r"(thi) : "r"(ea));
+                                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(thi) : "r"(ea));
                                 if (!(mn[k] > thi)) break;
                                 ea += 16u;
                             }
                         } else {
-                            asm("ld.shared.s32 %0, [%1+4];" : "=r"(thi) : "r"(ea));
+                            asm("ld.shared.s32 %0, [%1];" : "=r"(thi) : "r"(ea));
                             ea += (mn[k] > thi) ? 16u : 0u;
                         }
-                        int e_tlo, e_next;
-                        asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(e_tlo), "=r"(s.t_hi[k]), "=r"(e_next), "=r"(s.offs[k]) : "r"(ea));
+                        int e_next;
+                        asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(s.t_hi[k]), "=r"(e_next), "=r"(s.off_lo[k]), "=r"(s.off_hi[k]) : "r"(ea));
                         bool on_edge = false;
 #pragma unroll
                         for (int u = 0; u < U; ++u) on_edge |= (s.x[k][u] == s.t_hi[k]);
@@ -656,7 +666,6 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                     const double2 gs = bgs[g];
 #pragma unroll
                     for (int k = 0; k < APT; ++k) {
-                        const uint32_t o_lo = s.offs[k] & 0xffffu, o_hi = s.offs[k] >> 16;
                         double h1a, h1b, h2a, h2b;
                         int ch = 0;
 #pragma unroll
@@ -678,17 +687,24 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                             }
                         }
                         const double h1 = h1a + h1b, h2 = h2a + h2b;
-                        double2 *alo = reinterpret_cast<double2 *>(ring + o_lo * 16 + my_acc[k]);
-                        double2 *ahi = reinterpret_cast<double2 *>(ring + o_hi * 16 + my_acc[k]);
-                        uint16_t *clo = reinterpret_cast<uint16_t *>(ring + o_lo * 16 + my_cnt[k]);
-                        uint16_t *chi = reinterpret_cast<uint16_t *>(ring + o_hi * 16 + my_cnt[k]);
-                        double2 v_lo = *alo, v_hi = *ahi;
-                        const uint32_t c_lo = *clo, c_hi = *chi;
+                        // ring updates on 32-bit shared addresses: one add per address (the table holds byte offsets)
+                        const uint32_t a_lo = acc_sa[k] + s.off_lo[k], a_hi = acc_sa[k] + s.off_hi[k];
+                        const uint32_t n_lo = cnt_sa[k] + s.off_lo[k], n_hi = cnt_sa[k] + s.off_hi[k];
+                        double2 v_lo, v_hi;
+                        uint32_t c_lo, c_hi;
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v_lo.x), "=d"(v_lo.y) : "r"(a_lo) : "memory");
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v_hi.x), "=d"(v_hi.y) : "r"(a_hi) : "memory");
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(c_lo) : "r"(n_lo) : "memory");
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(c_hi) : "r"(n_hi) : "memory");
                         v_lo.x += gs.x - h1; v_lo.y += gs.y - h2;
                         v_hi.x += h1;        v_hi.y += h2;
-                        *alo = v_lo; *ahi = v_hi;
-                        *clo = (uint16_t)(c_lo + (uint32_t)(U - ch));
-                        *chi = (uint16_t)(c_hi + (uint32_t)ch);
+                        c_lo = c_lo + (uint32_t)U - (uint32_t)ch;
+                        c_hi = c_hi + (uint32_t)ch;
+                        // (both blocks are the trash block when they coincide: never read)
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a_lo), "d"(v_lo.x), "d"(v_lo.y) : "memory");
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a_hi), "d"(v_hi.x), "d"(v_hi.y) : "memory");
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(n_lo), "r"(c_lo) : "memory");
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(n_hi), "r"(c_hi) : "memory");
                     }
                 };
                 // group g's second stage beside group g + 1's first, in one basic block; a group that must be redone exactly only

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """BASELINE config 3 timing (200k points, 4 ellipse directions, tolerance 0.2, 80 lags) for the kernel variants, with the
-counts checked against each other.  usage: python scripts/exp_config3.py [settings...]  (KEY=VALUE,... per setting)"""
+counts checked against each other.  usage: python scripts/exp_config3.py [settings...]  (KEY=VALUE;KEY=VALUE... per setting)"""
 import os
 import sys
 
@@ -12,7 +12,7 @@ import torch  # noqa: E402
 from pyinterpolate_b200 import _lib, core  # noqa: E402
 from pyinterpolate_b200.synthetic import dem_like_field  # noqa: E402
 
-settings = sys.argv[1:] or ["PIB_PAIR_V=5", "", "PIB_FORCE_RING=1,PIB_RING=32", "PIB_FORCE_RING=1,PIB_RING=32,PIB_GROUP_PATH=1", "PIB_FORCE_FULL=1"]
+settings = sys.argv[1:] or ["PIB_PAIR_V=5", "", "PIB_FORCE_RING=1;PIB_RING=32", "PIB_FORCE_RING=1;PIB_RING=32;PIB_GROUP_PATH=1", "PIB_FORCE_FULL=1"]
 lags = np.arange(500.0, 40500.0, 500.0)
 p3 = torch.from_numpy(dem_like_field(200_000, extent=100_000.0, seed=3)).cuda()
 W = np.stack([core.define_whitening_matrix(a, 0.2) for a in (90, 0, 45, 135)]).reshape(-1, 4)
@@ -20,10 +20,10 @@ lower = core.ellipse_lower_limits(lags)
 peak = _lib.fp64_peak_tflops()
 ref = None
 for s in settings:
-    for k in ("PIB_PAIR_V", "PIB_FORCE_RING", "PIB_RING", "PIB_GROUP_PATH", "PIB_FORCE_FULL", "PIB_V6"):
+    for k in ("PIB_PAIR_V", "PIB_FORCE_RING", "PIB_RING", "PIB_GROUP_PATH", "PIB_FORCE_FULL", "PIB_V6", "PIB_LAGS_PER_GROUP"):
         os.environ.pop(k, None)
-    for kv in filter(None, s.split(",")):
-        k, v = kv.split("=")
+    for kv in filter(None, s.split(";")):
+        k, v = kv.split("=", 1)
         os.environ[k] = v
     ms = []
     for _ in range(4):

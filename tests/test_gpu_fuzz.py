@@ -22,6 +22,11 @@ VARIANTS = {
     "ring16_v5": {"PIB_FORCE_RING": "1", "PIB_RING": "16", "PIB_PAIR_V": "5"},
     "full": {"PIB_FORCE_FULL": "1"},
     "ring16_pairwise": {"PIB_FORCE_RING": "1", "PIB_RING": "16", "PIB_GROUP_PATH": "0", "PIB_BALANCE": "0"},
+    # two A points per thread, 10-slot sliding ring (the BASELINE config 2 kernel), forced onto every geometry: spans wider
+    # than the ring take the per-window sweeps; with and without the high-word fast path (PIB_HIW=0: exact stages only)
+    "apt2_ring10": {"PIB_FORCE_RING": "1", "PIB_V6": "2,8,512,10", "PIB_LAGS_PER_GROUP": "2"},
+    "apt2_ring10_exact": {"PIB_FORCE_RING": "1", "PIB_V6": "2,8,512,10", "PIB_LAGS_PER_GROUP": "2", "PIB_HIW": "0"},
+    "ring16_exact": {"PIB_FORCE_RING": "1", "PIB_RING": "16", "PIB_HIW": "0"},
 }
 
 
@@ -104,7 +109,7 @@ def test_omni_fuzz(lib, oracle, monkeypatch, name, variant):
     assert want["count"].sum() > 0
 
 
-@pytest.mark.parametrize("variant", ["default", "ring16", "ring32", "full"])
+@pytest.mark.parametrize("variant", ["default", "ring16", "ring32", "full", "apt2_ring10"])
 @pytest.mark.parametrize("name", ["grid", "clustered", "utm", "strip"])
 def test_ellipse_fuzz(lib, oracle, monkeypatch, name, variant):
     from pyinterpolate_b200 import core
