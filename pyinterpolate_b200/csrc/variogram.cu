@@ -844,6 +844,7 @@ namespace pib {
 // Cost of every ring-kernel work item = number of B tiles of its chunk that can hold a pair within range
 // (the same box test as the kernel's).  One warp per item; key = CHUNK - cost so that an ascending radix sort
 // puts the most expensive items first.
+constexpr int ITEM_COST_BITS = 10, ITEM_COST_MAX = (1 << ITEM_COST_BITS) - 1;
 template <bool ELLIPSE>
 __global__ void item_cost_kernel(const PairParams p, int a_tiles, int64_t n_items, uint32_t *__restrict__ keys,
                                  int32_t *__restrict__ vals, unsigned *__restrict__ n_live)
@@ -858,6 +859,9 @@ __global__ void item_cost_kernel(const PairParams p, int a_tiles, int64_t n_item
     const int ta_last = min(ta + a_tiles, n_tiles) - 1;
     const int tb0 = (int)(item % n_chunks) * chunk;
     const int tb1 = min(tb0 + chunk, n_tiles);
+    // cost of the item ~ sum over its live B tiles of (1 + number of the item's A tiles within range of the B tile): the
+    // kernels cull per warp, so an item at the rim of the range costs a fraction of one in the middle.  Tiles on the
+    // diagonal take the per-pair path: three times the weight.  (<= CHUNK * (1 + 3 * 8) ... clamped to 10 bits.)
     int cost = 0;
     if (tb1 > ta && (int64_t)ta * TILE < p.n) {
         double4 abox = p.tile_box[ta];
@@ -867,24 +871,33 @@ __global__ void item_cost_kernel(const PairParams p, int a_tiles, int64_t n_item
             abox.z = fmax(abox.z, o.z); abox.w = fmax(abox.w, o.w);
         }
         const int tb_first = max(tb0, ta);
+        auto min_d2 = [&](const double4 &A, const double4 &B) {
+            if (ELLIPSE) {
+                const double gx = fmax(0.0, fmax(A.x - B.z, B.x - A.z) - p.box_slack);
+                const double gy = fmax(0.0, fmax(A.y - B.w, B.y - A.w) - p.box_slack);
+                return (gx * gx + gy * gy) * (1.0 - 1e-12);
+            }
+            return box_min_d2(A, B);
+        };
         for (int h = 0; h < (chunk + 31) / 32; ++h) {
             const int tb = tb0 + h * 32 + lane;
-            bool live = false;
+            int c = 0;
             if (tb >= tb_first && tb < tb1) {
                 const double4 bbox = p.tile_box[tb];
-                double dmin;
-                if (ELLIPSE) {
-                    const double gx = fmax(0.0, fmax(abox.x - bbox.z, bbox.x - abox.z) - p.box_slack);
-                    const double gy = fmax(0.0, fmax(abox.y - bbox.w, bbox.y - abox.w) - p.box_slack);
-                    dmin = (gx * gx + gy * gy) * (1.0 - 1e-12);
-                } else dmin = box_min_d2(abox, bbox);
-                live = dmin <= p.max_d2;
+                if (min_d2(abox, bbox) <= p.max_d2) {
+                    c = 1;
+                    for (int t = ta; t <= ta_last && t <= tb; ++t)
+                        if (min_d2(p.tile_box[t], bbox) <= p.max_d2) c += (tb <= ta_last) ? 3 : 1;
+                }
             }
-            cost += __popc(__ballot_sync(0xffffffffu, live));
+#pragma unroll
+            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            cost += c;
         }
+        cost = min(cost, ITEM_COST_MAX);
     }
     if (lane == 0) {
-        keys[item] = (uint32_t)(chunk - cost);
+        keys[item] = (uint32_t)(ITEM_COST_MAX - cost);      // ascending sort = most expensive first, dead items last
         vals[item] = (int32_t)item;
         if (cost) atomicAdd(n_live, 1u);
     }
@@ -1380,9 +1393,10 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         } else v6 = false;
         if (!use_ring) v6 = false;
         if (v6) {
-            // PIB_PAIR_CHUNK: finer work items.  Measured at 8 ranks (148 CTAs x 8 leave ~19 items of 64 tiles per CTA):
-            // 16-tile items 22.80 ms against 22.30 ms for 64-tile items — the per-item set-up outweighs the finer
-            // balance, so the default stays CHUNK
+            // B tiles per work item.  Measured per-rank kernel times of config 2 (scripts/exp_shard_balance.py, ideal 18.13 ms at
+            // 8 ranks): 64-tile items 18.81 ms, 32-tile items 18.51 ms, 16-tile items 18.73 ms (the per-item set-up outweighs
+            // the finer balance); at 1 and 2 ranks 64-tile items are the fastest (143.9 vs 144.6 ms).  PIB_PAIR_CHUNK overrides.
+            if (shard_count >= 4) chunk = 32;
             const char *chunk_env = std::getenv("PIB_PAIR_CHUNK");
             if (chunk_env && std::atoi(chunk_env) >= 1 && std::atoi(chunk_env) <= CHUNK) chunk = std::atoi(chunk_env);
             n_chunks = (n_tiles + chunk - 1) / chunk;
@@ -1485,7 +1499,7 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
                 else
                     item_cost_kernel<false><<<cgrid, 256, 0, stream>>>(p, a_per_cta / TILE, n_items_all, d_keys, d_items, d_nlive);
                 PIB_CUDA(cudaGetLastError());
-                PIB_TRY(sort_pairs_u32(d_keys, d_keys2, d_items, d_items2, n_items_all, 7, ws, stream));
+                PIB_TRY(sort_pairs_u32(d_keys, d_keys2, d_items, d_items2, n_items_all, ITEM_COST_BITS, ws, stream));
                 p.item_list = d_items2; p.n_live_items = d_nlive;
             }
             {
