@@ -113,4 +113,20 @@ int sort_queries_by_cell(const double *d_unknown, int64_t m, const GridIndex &g,
 
 static __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// Bounds checks of the hot kernels' computed indices, compiled in with -DPIB_BOUNDS_CHECK (scripts/build_dbg.sh builds
+// build/libpib_dbg.so; run the GPU tests against it with PIB_LIB_PATH).  compute-sanitizer is closed on the GPU pool, so this
+// is the memory-safety evidence: a violated check prints the site and traps, which fails the call with a CUDA error.
+#ifdef PIB_BOUNDS_CHECK
+#define PIB_DBG_ASSERT(cond)                                                                          \
+    do {                                                                                              \
+        if (!(cond)) {                                                                                \
+            printf("PIB_BOUNDS_CHECK failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+                   (int)threadIdx.x);                                                                 \
+            __trap();                                                                                 \
+        }                                                                                             \
+    } while (0)
+#else
+#define PIB_DBG_ASSERT(cond) do { } while (0)
+#endif
+
 }  // namespace pib

@@ -539,6 +539,7 @@ __global__ void solve_kernel(const SolveParams p)
     }
     for (int t = lane; t < kk; t += 32) {
         const int pos = p.nbr_pos[slot * kmax + t];
+        PIB_DBG_ASSERT(pos >= 0 && pos < g.n);
         npos[t] = pos; nx[t] = g.x[pos]; ny[t] = g.y[pos]; nd[t] = p.nbr_d[slot * kmax + t];
     }
     __syncwarp();
@@ -724,6 +725,7 @@ __global__ void __launch_bounds__(solve_reg_threads<K>(), solve_reg_min_ctas<K>(
     double my_d = 0.0;
     if (t < kk) {
         my_pos = p.nbr_pos[slot * p.kk + t];
+        PIB_DBG_ASSERT(my_pos >= 0 && my_pos < g.n);
         my_d = p.nbr_d[slot * p.kk + t];
         S.nxy[t] = make_double2(g.x[my_pos], g.y[my_pos]);
     } else if (t < K) {
@@ -1005,6 +1007,7 @@ __global__ void __launch_bounds__(gj_threads<K>(), K == 32 ? 2 : 1) solve_gj_ker
     double my_d = 0.0;
     if (t < kk) {
         my_pos = p.nbr_pos[slot * p.kk + t];
+        PIB_DBG_ASSERT(my_pos >= 0 && my_pos < g.n);
         my_d = p.nbr_d[slot * p.kk + t];
         S.nxy[t] = make_double2(g.x[my_pos], g.y[my_pos]);
     } else if (t < K) {
@@ -1318,6 +1321,7 @@ __global__ void __launch_bounds__(32) singular_kernel(const SingularParams sp)
             __syncwarp();
             for (int t = lane; t < kk; t += 32) {
                 const int pos = p.nbr_pos[slot * kmax + t];
+                PIB_DBG_ASSERT(pos >= 0 && pos < g.n);
                 npos[t] = pos; nx[t] = g.x[pos]; ny[t] = g.y[pos]; nd[t] = p.nbr_d[slot * kmax + t];
             }
             __syncwarp();

@@ -159,8 +159,14 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
     constexpr uint32_t TILE_TX = TILE * (sizeof(double2) + sizeof(double)) + (TILE / U) * sizeof(double2);
 
     const int64_t n_work = p.item_list ? (int64_t)*p.n_live_items : n_items;
-    for (int64_t kk = ((int64_t)blockIdx.x) * p.shard_count + p.shard_index; kk < n_work;
-         kk += (int64_t)gridDim.x * p.shard_count) {
+    // The cost-ordered list is dealt to the (rank, CTA) slots in rounds, in SNAKE order: dealt in the same direction every round,
+    // slot 0 gets the most expensive item of each round and ends up one whole item above the last slot (3.6 % of a rank's
+    // kernel time at 8 ranks); alternating the direction cancels that round by round.  Static, so a warp's partial sums are
+    // the same in every run.
+    const int64_t deal = (int64_t)gridDim.x * p.shard_count, my_slot = (int64_t)blockIdx.x * p.shard_count + p.shard_index;
+    for (int64_t round = 0; round * deal < n_work; ++round) {
+        const int64_t kk = round * deal + ((round & 1) ? deal - 1 - my_slot : my_slot);
+        if (kk >= n_work) continue;
         const int64_t item = p.item_list ? (int64_t)p.item_list[kk] : kk;
         const int64_t a0 = (item / n_chunks) * NA;            // first point of the CTA's A sub-tile
         const int ta = (int)(a0 / TILE);
@@ -177,8 +183,12 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
 #pragma unroll
         for (int k = 0; k < APT; ++k) {
             ig[k] = (int)a0 + warp * WA + k * 32 + lane;
-            const double2 pa = p.xy[ig[k]];
-            xi[k] = pa.x; yi[k] = pa.y; zi[k] = p.z[ig[k]];
+            // the last A sub-tile may reach past the padded arrays (n_pad is a multiple of TILE, not of NA): rows >= n never
+            // count (every B tile they meet is a diagonal tile and keeps j > i only), but their loads must stay inside
+            const int il = min(ig[k], n_tiles * TILE - 1);
+            PIB_DBG_ASSERT(il >= 0 && il < n_tiles * TILE);
+            const double2 pa = p.xy[il];
+            xi[k] = pa.x; yi[k] = pa.y; zi[k] = p.z[il];
             if (ig[k] < p.n) {
                 const double u = ELLIPSE ? w00 * pa.x + w01 * pa.y : pa.x, v = ELLIPSE ? w10 * pa.x + w11 * pa.y : pa.y;
                 bx0 = fmin(bx0, u); bx1 = fmax(bx1, u); by0 = fmin(by0, v); by1 = fmax(by1, v);
@@ -265,6 +275,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
 #pragma unroll 1
             for (int sl = s_from; sl < s_to; ++sl) {
                 const int r = sl % RING;
+                PIB_DBG_ASSERT(sl >= 0 && sl < n_slots + RING && r >= 0);
                 double v_sq = 0.0, v_prod = 0.0, v_val = 0.0;
                 unsigned v_cnt = 0;
 #pragma unroll
@@ -291,6 +302,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                 if (lane == r && v_cnt) {
                     // fire-and-forget adds: a slot always lives in the same ring block, so the same lane issues all adds to an
                     // address, in program order — the sums stay reproducible run to run
+                    PIB_DBG_ASSERT(sl >= 1 && sl <= n_lags);
                     double *dst = my_partial + (size_t)sl * 4;
                     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst), "d"(v_sq) : "memory");
                     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst + 1), "d"(v_prod) : "memory");
@@ -309,6 +321,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
         // have released the buffer's previous tile), each warp waits for a tile to land, sweeps it and releases the buffer.
         // No CTA-wide barrier per tile: warps that cull a tile, or finish it early, run ahead.
         auto issue_tile = [&](int t) {
+            PIB_DBG_ASSERT(t >= 0 && t < n_tiles);
             const uint32_t b = pseq % STAGES;
             if (pseq >= STAGES) mbar_wait(&s_empty[b], ((pseq / STAGES) - 1) & 1);
             mbar_expect_tx(&s_full[b], TILE_TX);
@@ -381,6 +394,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                 };
                 // one pair into the ring (slow paths)
                 auto add_pair = [&](int q, int k, double z, bool wide_mode) __attribute__((always_inline)) {
+                    PIB_DBG_ASSERT(q >= 0 && q < n_slots + 4);
                     uint32_t off = s_slot[q].offs & 0xffffu;
                     if (wide_mode && !((unsigned)(q - wlo) < wlen)) off = TRASH16;
                     double2 *ap = reinterpret_cast<double2 *>(ring + off * 16 + my_acc[k]);
@@ -426,6 +440,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                         idx = min(max(idx, 0), lut_last);
                         unsigned short q0;
                         asm("ld.shared.u16 %0, [%1];" : "=h"(q0) : "r"(lut_sa + 2u * (uint32_t)idx));
+                        PIB_DBG_ASSERT((int)q0 < n_slots);
                         uint32_t ea = slot_sa + 16u * (uint32_t)q0;
                         int thi;
                         if (MULTI_FIX) {
@@ -461,6 +476,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                                         double g2, int n_in, const bool wide_mode, const bool bounded, long long t1)
                                         __attribute__((always_inline)) {
                     uint32_t o_lo = offs & 0xffffu, o_hi = offs >> 16;
+                    PIB_DBG_ASSERT(o_lo <= TRASH16 && o_hi <= TRASH16 && o_lo % SB16 == 0 && o_hi % SB16 == 0);
                     if (wide_mode) {
                         if (!((unsigned)(q - wlo) < wlen)) o_lo = TRASH16;
                         if (!((unsigned)(q + 1 - wlo) < wlen)) o_hi = TRASH16;
@@ -641,6 +657,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                         idx = min(max(idx, 0), lut_last);
                         unsigned short q0;
                         asm("ld.shared.u16 %0, [%1];" : "=h"(q0) : "r"(lut_sa + 2u * (uint32_t)idx));
+                        PIB_DBG_ASSERT((int)q0 < n_slots);
                         uint32_t ea = sloth_sa + 16u * (uint32_t)q0;
                         int thi;
                         if (MULTI_FIX) {
@@ -690,6 +707,8 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                         // ring updates on 32-bit shared addresses: one add per address (the table holds byte offsets)
                         const uint32_t a_lo = acc_sa[k] + s.off_lo[k], a_hi = acc_sa[k] + s.off_hi[k];
                         const uint32_t n_lo = cnt_sa[k] + s.off_lo[k], n_hi = cnt_sa[k] + s.off_hi[k];
+                        PIB_DBG_ASSERT(s.off_lo[k] <= (uint32_t)RING * SLOT_BYTES && s.off_hi[k] <= (uint32_t)RING * SLOT_BYTES &&
+                                       s.off_lo[k] % SLOT_BYTES == 0 && s.off_hi[k] % SLOT_BYTES == 0);
                         double2 v_lo, v_hi;
                         uint32_t c_lo, c_hi;
                         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v_lo.x), "=d"(v_lo.y) : "r"(a_lo) : "memory");

@@ -495,8 +495,10 @@ __global__ void __launch_bounds__(NT, 1) pair_ring_kernel(const PairParams p)
         if (live == 0) { __syncthreads(); continue; }
 
         const int ig = (int)a0 + tid;
-        const double2 pa = p.xy[ig];
-        const double xi = pa.x, yi = pa.y, zi = p.z[ig];
+        const int il = min(ig, p.n_tiles * TILE - 1);         // the last A sub-tile may reach past the padded arrays (rows >= n never count)
+        PIB_DBG_ASSERT(il >= 0);
+        const double2 pa = p.xy[il];
+        const double xi = pa.x, yi = pa.y, zi = p.z[il];
         s_zi[tid] = zi;
         const double z8 = zi * 8.0, zm2 = zi * -2.0, zq8 = (zi * zi) * 8.0;
         int win_lo = 0x7fff, win_hi = 0;                      // lag slots touched since the last fold (empty)
@@ -1393,10 +1395,9 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         } else v6 = false;
         if (!use_ring) v6 = false;
         if (v6) {
-            // B tiles per work item.  Measured per-rank kernel times of config 2 (scripts/exp_shard_balance.py, ideal 18.13 ms at
-            // 8 ranks): 64-tile items 18.81 ms, 32-tile items 18.51 ms, 16-tile items 18.73 ms (the per-item set-up outweighs
-            // the finer balance); at 1 and 2 ranks 64-tile items are the fastest (143.9 vs 144.6 ms).  PIB_PAIR_CHUNK overrides.
-            if (shard_count >= 4) chunk = 32;
+            // B tiles per work item: CHUNK.  Per-rank kernel times of config 2 at 8 ranks (scripts/exp_shard_balance.py, ideal
+            // 17.91 ms) with the snake-order deal of pair_ring6_kernel: 64-tile items 18.20 ms, 32-tile items 18.41 ms (the
+            // per-item set-up outweighs the finer balance).  PIB_PAIR_CHUNK overrides.
             const char *chunk_env = std::getenv("PIB_PAIR_CHUNK");
             if (chunk_env && std::atoi(chunk_env) >= 1 && std::atoi(chunk_env) <= CHUNK) chunk = std::atoi(chunk_env);
             n_chunks = (n_tiles + chunk - 1) / chunk;
