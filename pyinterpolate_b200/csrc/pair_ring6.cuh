@@ -59,6 +59,42 @@ static size_t ring6_smem_bytes(int n_slots, int lut_n)
 #define PIB_V6_HIW 1
 #endif
 
+// packed single precision (two lanes per 64-bit register): FADD2 / FMUL2 / FFMA2 of sm_100
+static __device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+static __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+static __device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+static __device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+static __device__ __forceinline__ unsigned long long f2_pack(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+static __device__ __forceinline__ void f2_unpack(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
 template <int RING, int NT, int APT, int U, int NL, bool MULTI_FIX, bool ELLIPSE>
 __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
 {
@@ -77,6 +113,8 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
     constexpr int NG = TILE / U;
     // high-word fast path (two-lag scheme, plain distances): see sweep_hiw below
     constexpr bool HIW = PIB_V6_HIW != 0 && NL == 2 && !ELLIPSE && U == 8;
+    // fp32 screening path (sweep_f32 below): the default two-A-point build only (its tiles take 4 KB of shared memory)
+    constexpr bool F32S = HIW && APT == 2 && RING == 10;
     static_assert(NA % TILE == 0 && RING <= 32 && RING >= 4, "A sub-tile is whole tiles; one lane folds one ring slot");
     static_assert(U == 8 || U == 16, "groups of 8 or 16 pairs");
     static_assert(NL == 2 || NL == 4, "a group may span two or four consecutive lags");
@@ -87,6 +125,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
     __shared__ __align__(16) double2 s_txy[STAGES][TILE];
     __shared__ __align__(16) double s_tz[STAGES][TILE];
     __shared__ __align__(16) double2 s_gs[STAGES][TILE / 8];
+    __shared__ __align__(16) unsigned char s_tf[F32S ? STAGES : 1][F32S ? TF32_TILE_BYTES : 16];
     __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES];     // TMA landed / every warp is done with the buffer
     __shared__ uint64_t s_live[2];                 // live B tiles of the item (double-buffered over consecutive items)
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -129,8 +168,15 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
         const uint32_t o_hi = (s + 1 >= 1 && s + 1 <= n_lags) ? (uint32_t)((s + 1) % RING) * SB16 : TRASH16;
         e.offs = o_lo | (o_hi << 16);
         s_slot[s] = e;
+        if (F32S && p.tf32) {
+            const float2 tf = p.slotf[s];
+            s_sloth[s] = make_int4(__float_as_int(tf.x), __float_as_int(tf.y), (int)(o_lo * 16u), (int)(o_hi * 16u));
+        } else
         s_sloth[s] = make_int4((int)(e.T >> 32), e.next_hi, (int)(o_lo * 16u), (int)(o_hi * 16u));
     }
+    const bool f32_on = F32S && p.tf32 != nullptr;
+    // (same cells as the fp64 high-word table: a normal float's bits are ((high word - 896 * 2^20) << 3) | 3 more mantissa bits)
+    const int base_f = (p.lut2_base - 0x38000000) << 3;
     {
         uint16_t *lut_w = const_cast<uint16_t *>(s_lut);
         for (int s = tid; s < p.lut2_n; s += NT) lut_w[s] = p.lut2[s];
@@ -156,7 +202,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
     const int base_hi = p.lut2_base, lut_last = p.lut2_n - 1;
     const double w00 = p.w00, w01 = p.w01, w10 = p.w10, w11 = p.w11;
     const double slack = p.box_slack;
-    constexpr uint32_t TILE_TX = TILE * (sizeof(double2) + sizeof(double)) + (TILE / U) * sizeof(double2);
+    const uint32_t TILE_TX = TILE * (sizeof(double2) + sizeof(double)) + (TILE / U) * sizeof(double2) + (f32_on ? TF32_TILE_BYTES : 0);
 
     const int64_t n_work = p.item_list ? (int64_t)*p.n_live_items : n_items;
     // The cost-ordered list is dealt to the (rank, CTA) slots in rounds, in SNAKE order: dealt in the same direction every round,
@@ -227,11 +273,16 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
             if (lane == 0) s_live[item_no & 1] = m;
         }
         // ---- my warp: the lag slots each B tile can touch for MY A points (empty = skip the tile) ----------
+        uint64_t f32_tiles = 0;                               // B tiles of the chunk the fp32 screening path may take
         for (int h = 0; h < (chunk + 31) / 32; ++h) {
             const int tb = tb0 + h * 32 + lane;
             short2 r = make_short2(1, 0);                     // empty
+            bool narrow = false;
             if (tb >= tb_first && tb < tb1) {
                 const double4 bbox = p.tile_box[tb];
+                // full tiles whose points lie within f32_rcap of the tile's origin (the error bound of the screening)
+                narrow = f32_on && (int64_t)(tb + 1) * TILE <= p.n &&
+                         0.5 * fmax(bbox.z - bbox.x, bbox.w - bbox.y) <= p.f32_rcap;
                 const double sl = ELLIPSE ? slack : 0.0;
                 const double gx = fmax(0.0, fmax(bx0 - bbox.z, bbox.x - bx1) - sl);
                 const double gy = fmax(0.0, fmax(by0 - bbox.w, bbox.y - by1) - sl);
@@ -253,6 +304,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                 }
             }
             s_range[h * 32 + lane] = r;
+            if (F32S) f32_tiles |= (uint64_t)__ballot_sync(0xffffffffu, narrow) << (32 * h);
         }
         __syncthreads();                                      // the one CTA-wide barrier of an item (s_live is double-buffered)
         uint64_t live = s_live[item_no & 1];
@@ -328,6 +380,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
             tma_load_1d(s_txy[b], p.xy + (size_t)t * TILE, TILE * sizeof(double2), &s_full[b]);
             tma_load_1d(s_tz[b], p.z + (size_t)t * TILE, TILE * sizeof(double), &s_full[b]);
             tma_load_1d(s_gs[b], p.gsum + (size_t)t * (TILE / U), (TILE / U) * sizeof(double2), &s_full[b]);
+            if (F32S && f32_on) tma_load_1d(s_tf[b], p.tf32 + (size_t)t * TF32_TILE_BYTES, TF32_TILE_BYTES, &s_full[b]);
             ++pseq;
         };
         uint64_t ahead = live;                                // thread 0: tiles not yet requested
@@ -373,6 +426,20 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                         if (ig[k] < p.n) np += (unsigned)max(0, jend - max(ig[k] + 1, jbase));
                     np = __reduce_add_sync(0xffffffffu, np);
                     evaluated += np;
+                }
+                // fp32 screening: my A points relative to the tile's origin, each duplicated into both lanes of a pair
+                const bool tile_f32 = F32S && !diagonal && ((f32_tiles >> (tb - tb0)) & 1);
+                unsigned long long xa2[APT], ya2[APT];
+#pragma unroll
+                for (int k = 0; k < APT; ++k) xa2[k] = ya2[k] = 0;
+                if (F32S && tile_f32) {
+                    const double2 org = *reinterpret_cast<const double2 *>(s_tf[F32S ? b : 0] + TILE * 8);
+#pragma unroll
+                    for (int k = 0; k < APT; ++k) {
+                        const float xf = __double2float_rn(__dsub_rn(xi[k], org.x)), yf = __double2float_rn(__dsub_rn(yi[k], org.y));
+                        xa2[k] = f2_pack(xf, xf);
+                        ya2[k] = f2_pack(yf, yf);
+                    }
                 }
                 int wlo = 1;                                  // wide sweeps: lag slots the ring accepts, [wlo, wlo + wlen)
                 unsigned wlen = (unsigned)n_lags;
@@ -773,6 +840,141 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                     }
                 };
 
+                // ---- fp32 screening path ---------------------------------------------------------------------------------
+                // The lag of nearly every pair is decided in SINGLE precision, two pairs per instruction (FADD2 / FMUL2 /
+                // FFMA2): B coordinates relative to their tile's origin, rounded to fp32 by the pre-pass (tile_f32_kernel), A
+                // coordinates relative to the same origin, d2f = fma(dxf, dxf, dyf * dyf).  With R = the tile's half-extent
+                // (<= f32_rcap) and u = 2^-24:  |d2f - d2| <= u (6 d2 + 5.66 R d)  (conversion of both points, the fp32
+                // subtraction, product and fused sum; d2 = the reference's fp64 value, whose own rounding is 2^-29 of that).
+                // The host turns that bound (x 1.05) into a band per threshold T: the table holds tmid = fl32(T) and hw with
+                // [tmid - hw, tmid + hw] covering T +- bound(T).  A pair with d2f - tmid > hw is above T in the reference's
+                // arithmetic, one with d2f - tmid < -hw is not; a group with a pair INSIDE a band (about 1 % of the warp-wide
+                // groups on BASELINE config 2), like a group with a pair that may lie beyond its second lag, is redone by the
+                // exact fp64 stages after the sweep — so the counts stay bit-exact.  Per pair: 2 packed fp32 instructions for
+                // the distance instead of 4 fp64, 1 instead of 2 for the group's min / max, half a shared-memory wavefront less.
+                struct GrpF {
+                    float e[APT][U];           // d2f - tmid of the group's first lag
+                    float hw[APT];
+                    uint32_t off_lo[APT], off_hi[APT];
+                    bool redo;
+                };
+                auto stage_a_f = [&](int g, GrpF &s) __attribute__((always_inline)) {
+                    const ulonglong2 *btf = reinterpret_cast<const ulonglong2 *>(s_tf[F32S ? b : 0]) + g * (U / 2);
+                    unsigned long long d[APT][U / 2];
+                    float mn[APT], mx[APT];
+#pragma unroll
+                    for (int m = 0; m < U / 2; ++m) {
+                        const ulonglong2 pb = btf[m];          // {x0, x1}, {y0, y1} of B points 2m, 2m + 1 of the group
+#pragma unroll
+                        for (int k = 0; k < APT; ++k) {
+                            const unsigned long long dx = f2_sub(xa2[k], pb.x), dy = f2_sub(ya2[k], pb.y);
+                            d[k][m] = f2_fma(dx, dx, f2_mul(dy, dy));
+                            float lo, hi;
+                            f2_unpack(d[k][m], lo, hi);
+                            mn[k] = m ? fminf(fminf(mn[k], lo), hi) : fminf(lo, hi);
+                            mx[k] = m ? fmaxf(fmaxf(mx[k], lo), hi) : fmaxf(lo, hi);
+                        }
+                    }
+                    s.redo = false;
+#pragma unroll
+                    for (int k = 0; k < APT; ++k) {
+                        int idx = (__float_as_int(mn[k]) - base_f) >> (LUT2_SHIFT + 3);
+                        idx = min(max(idx, 0), lut_last);
+                        unsigned short q0;
+                        asm("ld.shared.u16 %0, [%1];" : "=h"(q0) : "r"(lut_sa + 2u * (uint32_t)idx));
+                        PIB_DBG_ASSERT((int)q0 < n_slots);
+                        uint32_t ea = sloth_sa + 16u * (uint32_t)q0;
+                        float tm, hw0;
+                        if (MULTI_FIX) {
+                            while (true) {
+                                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(tm), "=f"(hw0) : "r"(ea));
+                                if (!(__fsub_rn(mn[k], tm) > hw0)) break;
+                                ea += 16u;
+                            }
+                        } else {
+                            asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(tm), "=f"(hw0) : "r"(ea));
+                            ea += (__fsub_rn(mn[k], tm) > hw0) ? 16u : 0u;
+                        }
+                        float tmid, hwq, tnext, hwnext;
+                        asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(tmid), "=f"(hwq), "=r"(s.off_lo[k]), "=r"(s.off_hi[k]) : "r"(ea));
+                        asm("ld.shared.v2.f32 {%0, %1}, [%2+16];" : "=f"(tnext), "=f"(hwnext) : "r"(ea));
+                        s.hw[k] = hwq;
+                        const unsigned long long nt2 = f2_pack(-tmid, -tmid);
+                        float em = INFINITY;
+#pragma unroll
+                        for (int m = 0; m < U / 2; ++m) {
+                            f2_unpack(f2_add(d[k][m], nt2), s.e[k][2 * m], s.e[k][2 * m + 1]);
+                            em = fminf(fminf(em, fabsf(s.e[k][2 * m])), fabsf(s.e[k][2 * m + 1]));
+                        }
+                        // undecided pair, or a pair that may lie beyond the group's second lag
+                        s.redo |= (em <= hwq) | (__fsub_rn(mx[k], tnext) >= -hwnext);
+                    }
+                };
+                auto stage_b_f = [&](int g, const GrpF &s) __attribute__((always_inline)) {
+                    const int j0 = g * U;
+                    const double2 gs = bgs[g];
+#pragma unroll
+                    for (int k = 0; k < APT; ++k) {
+                        double h1a, h1b, h2a, h2b;
+                        int ch = 0;
+#pragma unroll
+                        for (int u = 0; u < U; u += 2) {
+                            const double2 zz = *reinterpret_cast<const double2 *>(bz + j0 + u);
+                            int za_hi, zb_hi;
+                            asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %3, %4;\n\tselp.b32 %0, %2, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
+                                : "=r"(za_hi), "+r"(ch) : "r"(__double2hiint(zz.x)), "f"(s.e[k][u]), "f"(s.hw[k]));
+                            asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %3, %4;\n\tselp.b32 %0, %2, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
+                                : "=r"(zb_hi), "+r"(ch) : "r"(__double2hiint(zz.y)), "f"(s.e[k][u + 1]), "f"(s.hw[k]));
+                            const double za = __hiloint2double(za_hi, __double2loint(zz.x));
+                            const double zb = __hiloint2double(zb_hi, __double2loint(zz.y));
+                            if (u == 0) {
+                                h1a = za; h2a = __dmul_rn(za, za);
+                                h1b = zb; h2b = __dmul_rn(zb, zb);
+                            } else {
+                                h1a += za; h2a = __fma_rn(za, za, h2a);
+                                h1b += zb; h2b = __fma_rn(zb, zb, h2b);
+                            }
+                        }
+                        const double h1 = h1a + h1b, h2 = h2a + h2b;
+                        const uint32_t a_lo = acc_sa[k] + s.off_lo[k], a_hi = acc_sa[k] + s.off_hi[k];
+                        const uint32_t n_lo = cnt_sa[k] + s.off_lo[k], n_hi = cnt_sa[k] + s.off_hi[k];
+                        PIB_DBG_ASSERT(s.off_lo[k] <= (uint32_t)RING * SLOT_BYTES && s.off_hi[k] <= (uint32_t)RING * SLOT_BYTES &&
+                                       s.off_lo[k] % SLOT_BYTES == 0 && s.off_hi[k] % SLOT_BYTES == 0);
+                        double2 v_lo, v_hi;
+                        uint32_t c_lo, c_hi;
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v_lo.x), "=d"(v_lo.y) : "r"(a_lo) : "memory");
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v_hi.x), "=d"(v_hi.y) : "r"(a_hi) : "memory");
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(c_lo) : "r"(n_lo) : "memory");
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(c_hi) : "r"(n_hi) : "memory");
+                        v_lo.x += gs.x - h1; v_lo.y += gs.y - h2;
+                        v_hi.x += h1;        v_hi.y += h2;
+                        c_lo = c_lo + (uint32_t)U - (uint32_t)ch;
+                        c_hi = c_hi + (uint32_t)ch;
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a_lo), "d"(v_lo.x), "d"(v_lo.y) : "memory");
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a_hi), "d"(v_hi.x), "d"(v_hi.y) : "memory");
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(n_lo), "r"(c_lo) : "memory");
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(n_hi), "r"(c_hi) : "memory");
+                    }
+                };
+                auto sweep_f32 = [&]() __attribute__((always_inline)) {
+                    unsigned redo_f = 0;
+#pragma unroll 1
+                    for (int g = 0; g < NG; ++g) {
+                        GrpF s0;
+                        stage_a_f(g, s0);
+                        if (!__any_sync(0xffffffffu, s0.redo)) stage_b_f(g, s0);
+                        else redo_f |= 1u << g;
+                    }
+#pragma unroll 1
+                    while (redo_f) {
+                        const int g = __ffs((int)redo_f) - 1;
+                        redo_f &= redo_f - 1;
+                        Grp e;
+                        stage_a(g, e);
+                        stage_b(g, e, false);
+                    }
+                };
+
                 auto sweep = [&](const bool wide_mode) __attribute__((always_inline)) {
                     if (diagonal || !p.group_path) {
                         // Per-pair path: tiles that overlap my CTA's own points (keep i < j only) and data whose groups of
@@ -826,7 +1028,11 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                         }
                         return;
                     }
-                    if (HIW && !wide_mode && p.hiw_ok) {
+                    if (F32S && !wide_mode && tile_f32) {
+                        sweep_f32();
+                        return;
+                    }
+                    if (HIW && !wide_mode && p.hiw_ok && !f32_on) {
                         sweep_hiw();
                         return;
                     }

@@ -24,6 +24,7 @@
 //   * private histograms are folded warp-wise into per-warp global partials after every work item
 //     and a last kernel adds the partials in a fixed order: results are deterministic
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -64,7 +65,13 @@ struct PairParams {
     int chunk;                     // pair_ring6_kernel / item_cost_kernel: B tiles per work item (<= CHUNK)
     int hiw_ok;                    // pair_ring6_kernel: no threshold has an all-ones low word (high-word fast path is exact)
     const int *run_flag;           // NULL, or device flag: the kernel returns at once when it is 0 (conditional re-run)
+    // pair_ring6_kernel, fp32 screening path (see sweep_f32): per tile TILE / 2 x {x0, x1, y0, y1} single-precision coordinates
+    // relative to the tile's origin, then the origin itself (double2) — TF32_TILE_BYTES per tile; NULL = path off
+    const unsigned char *tf32;
+    const float2 *slotf;           // [n_slots + 4] (fp32 threshold, half-width of its undecided band) per slot
+    double f32_rcap;               // tiles wider than 2 * f32_rcap (either axis) take the exact path
 };
+constexpr int TF32_TILE_BYTES = TILE * 8 + 16;
 
 // ---- PTX helpers: mbarrier + 1D TMA bulk copy -------------------------------------------------
 static __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -960,6 +967,25 @@ __global__ void group_sum_kernel(const double *__restrict__ z, const double *__r
     gsum[gidx] = make_double2(s1, qe + qo);
 }
 
+// fp32 screening tiles of pair_ring6_kernel: coordinates relative to the centre of the tile's box, rounded to single
+// precision, two points per 16-byte entry {x0, x1, y0, y1}; the origin follows the TILE / 2 entries (one thread per entry)
+__global__ void tile_f32_kernel(const double2 *__restrict__ xy, const double4 *__restrict__ tile_box, int64_t n_tiles,
+                                unsigned char *__restrict__ out)
+{
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= n_tiles * (TILE / 2)) return;
+    const int64_t t = e / (TILE / 2);
+    const int m = (int)(e % (TILE / 2));
+    const double4 box = tile_box[t];
+    // (an empty tile has an infinite box: its entries are never used, the kernel only screens full tiles)
+    const double ox = __dmul_rn(0.5, __dadd_rn(box.x, box.z)), oy = __dmul_rn(0.5, __dadd_rn(box.y, box.w));
+    const double2 a = xy[t * TILE + 2 * m], b = xy[t * TILE + 2 * m + 1];
+    unsigned char *rec = out + (size_t)t * TF32_TILE_BYTES;
+    reinterpret_cast<float4 *>(rec)[m] = make_float4(__double2float_rn(__dsub_rn(a.x, ox)), __double2float_rn(__dsub_rn(b.x, ox)),
+                                                     __double2float_rn(__dsub_rn(a.y, oy)), __double2float_rn(__dsub_rn(b.y, oy)));
+    if (m == 0) *reinterpret_cast<double2 *>(rec + TILE * 8) = make_double2(ox, oy);
+}
+
 // bounding boxes of the whitened coordinates (u, v) = W p of every tile (one warp per tile)
 __global__ void tile_box_whitened_kernel(const double2 *__restrict__ xy, int64_t n, int64_t n_tiles,
                                          double w00, double w01, double w10, double w11, double4 *__restrict__ box)
@@ -1133,7 +1159,9 @@ template <int RING, int NT, int APT, int U, int NL, bool ALL>
 static int launch_pair_ring6_t(const PairParams &p, bool multi_fix, bool ellipse, int grid, cudaStream_t stream)
 {
     const size_t smem = ring6_smem_bytes<RING, NT, APT>(p.n_slots, p.lut2_n);
-    PIB_CHECK(smem + 14336 <= (size_t)MAX_SMEM, PIB_ERR_UNSUPPORTED, "pair_ring6_kernel: tables do not fit in shared memory");   // + static: 4 B-tile buffers
+    // + static: 4 B-tile buffers (and the fp32 screening tiles of the two-A-point build)
+    PIB_CHECK(smem + 14336 + (RING == 10 && APT == 2 ? 4 * TF32_TILE_BYTES : 0) <= (size_t)MAX_SMEM, PIB_ERR_UNSUPPORTED,
+              "pair_ring6_kernel: tables do not fit in shared memory");
 #define PIB_L6(M, E)                                                                                                              \
     do {                                                                                                                          \
         PIB_CUDA(cudaFuncSetAttribute(pair_ring6_kernel<RING, NT, APT, U, NL, M, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -1280,10 +1308,8 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
                 lut2[e] = (uint16_t)q_lo;
                 fix_steps = std::max(fix_steps, q_hi - q_lo);
             }
-            PIB_TRY(ws.alloc(&d_lut2, lut2.size()));
-            PIB_CUDA(cudaMemcpyAsync(d_lut2, lut2.data(), lut2.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
         }
-        const int fix2 = fix_steps;
+        int fix2 = fix_steps;                      // (the table is uploaded further down: the fp32 screening path lowers some cells)
 
         const int n_tiles = (int)(sp.n_pad / TILE);
         int chunk = CHUNK;                         // B tiles per work item; pair_ring6_kernel takes fewer for many ranks (below)
@@ -1381,7 +1407,8 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             // 10 lags (BASELINE config 2: 9 at the 99th percentile); the two-lag scheme only
             const double span2 = 1.75 * d90_scaled / min_width + 2.0;    // 64 consecutive points: ~0.75 of a tile's diagonal
             const char *apt_env = std::getenv("PIB_APT");
-            if (use_ring && v6_nl == 2 && !ring_env && !force_ring && span2 <= 10.0 && !(apt_env && apt_env[0] == '1')) {
+            const bool apt2_fits = ring6_smem_bytes<10, 512, 2>(n_slots, (int)lut2.size()) + 14336 + 4 * TF32_TILE_BYTES <= (size_t)MAX_SMEM;
+            if (use_ring && v6_nl == 2 && !ring_env && !force_ring && span2 <= 10.0 && !(apt_env && apt_env[0] == '1') && apt2_fits) {
                 v6_apt = 2; ring = 10; ring_nt = 512;
             }
             // PIB_V6 = "apt,u,threads,ring" picks another build of the kernel for A/B measurements, e.g. "2,8,384,12"
@@ -1402,6 +1429,50 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
             if (chunk_env && std::atoi(chunk_env) >= 1 && std::atoi(chunk_env) <= CHUNK) chunk = std::atoi(chunk_env);
             n_chunks = (n_tiles + chunk - 1) / chunk;
         }
+        // fp32 screening path of the two-A-point kernel (pair_ring6.cuh, sweep_f32): per-slot bands from the error bound
+        // u (6 T + 5.66 R sqrt(T)) x 1.05, u = 2^-24, R = the widest tile half-extent the path accepts; the slot table is lowered
+        // to the first slot a cell's smallest value may still belong to (a valid lower bound for the exact stages as well)
+        std::vector<float2> slotf;
+        double f32_rcap = 0.0;
+        {
+            const char *f32_env = std::getenv("PIB_F32");
+            const bool want = v6 && v6_apt == 2 && ring == 10 && ring_nt == 512 && v6_u == 8 && v6_nl == 2 && n_dirs == 0 &&
+                              std::isfinite(d90_scaled) && d90_scaled > 0.0 && !(f32_env && f32_env[0] == '0') &&
+                              up[1] >= 1e-30 && up[n_slots - 2] <= 1e30;
+            if (want) {
+                f32_rcap = d90_scaled;
+                const double u24 = std::ldexp(1.0, -24);
+                slotf.resize(n_slots + 4);
+                for (int sl = 0; sl < n_slots + 4; ++sl) {
+                    if (sl == 0) { slotf[sl] = make_float2(0.0f, 0.0f); continue; }
+                    if (sl >= n_slots - 1) { slotf[sl] = make_float2(FLT_MAX, 0.0f); continue; }
+                    const double T = up[sl];
+                    const double band = 1.05 * u24 * (6.0 * T + 5.66 * f32_rcap * std::sqrt(T)) + 1e-37;
+                    const float tmid = (float)T;
+                    float hw = (float)(band + std::fabs(T - (double)tmid));
+                    while ((double)hw < band + std::fabs(T - (double)tmid)) hw = std::nextafterf(hw, INFINITY);
+                    hw = std::nextafterf(hw, INFINITY);
+                    slotf[sl] = make_float2(tmid, hw);
+                }
+                auto slot_f = [&](double v) { int q = 0; while (q < n_slots - 1 && v - (double)slotf[q].x > (double)slotf[q].y) ++q; return q; };
+                auto slot_x = [&](double v) { int q = 0; while (q < n_slots - 1 && v > up[q]) ++q; return q; };
+                auto from_hi = [](int hi) { long long b = (long long)hi << 32; double v; std::memcpy(&v, &b, 8); return v; };
+                const int cell = 1 << LUT2_SHIFT, n_cells = (int)lut2.size();
+                int steps = 0;
+                for (int e = 0; e < n_cells; ++e) {
+                    const double v_lo = e == 0 ? 0.0 : from_hi(lut2_base + e * cell);
+                    const int q_lo = std::min((int)lut2[e], slot_f(v_lo));
+                    lut2[e] = (uint16_t)q_lo;
+                    if (e < n_cells - 1) {
+                        const double v_hi = from_hi(lut2_base + (e + 1) * cell);
+                        steps = std::max(steps, std::max(slot_x(std::nextafter(v_hi, 0.0)), slot_f((double)std::nextafterf((float)v_hi, 0.0f))) - q_lo);
+                    } else steps = std::max(steps, n_slots - 1 - q_lo);
+                }
+                fix2 = std::max(fix2, steps);
+            }
+        }
+        PIB_TRY(ws.alloc(&d_lut2, lut2.size()));
+        PIB_CUDA(cudaMemcpyAsync(d_lut2, lut2.data(), lut2.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
         const int a_per_cta = use_ring ? ring_nt * (v6 ? v6_apt : 1) : nt;
         if (use_ring) nt = ring_nt;
         const int64_t a_tiles = use_ring ? (n_tiles + a_per_cta / TILE - 1) / (a_per_cta / TILE) : (int64_t)n_tiles * (TILE / nt);
@@ -1430,6 +1501,17 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         double *d_mean = nullptr;                  // ring kernel: mean of z (its sums come out centred)
         int64_t guard_groups = 0;                  // ring kernel: number of group sums (cancellation guard)
         p.item_list = nullptr; p.n_live_items = nullptr; p.run_flag = nullptr; p.chunk = chunk;
+        p.tf32 = nullptr; p.slotf = nullptr; p.f32_rcap = f32_rcap;
+        if (!slotf.empty()) {
+            unsigned char *d_tf32;
+            float2 *d_slotf;
+            PIB_TRY(ws.alloc(&d_tf32, (size_t)n_tiles * TF32_TILE_BYTES));
+            PIB_TRY(ws.alloc(&d_slotf, slotf.size()));
+            PIB_CUDA(cudaMemcpyAsync(d_slotf, slotf.data(), slotf.size() * sizeof(float2), cudaMemcpyHostToDevice, stream));
+            tile_f32_kernel<<<(int)(((int64_t)n_tiles * (TILE / 2) + 255) / 256), 256, 0, stream>>>(sp.xy, sp.tile_box, n_tiles, d_tf32);
+            PIB_CUDA(cudaGetLastError());
+            p.tf32 = d_tf32; p.slotf = d_slotf;
+        }
         const int64_t n_items_all = a_tiles * n_chunks;            // over all ranks
         const char *bal_env = std::getenv("PIB_BALANCE");
         const bool balance = use_ring && n_items_all < ((int64_t)1 << 31) && !(bal_env && bal_env[0] == '0');
@@ -1504,8 +1586,8 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
                 p.item_list = d_items2; p.n_live_items = d_nlive;
             }
             {
-                char name[96];
-                if (use_ring && v6) std::snprintf(name, sizeof(name), "pair_ring6_kernel<ring %d, %d threads, %d A/thread, groups of %d over %d lags%s>", ring, ring_nt, v6_apt, v6_u, v6_nl, n_dirs > 0 ? ", ellipse" : "");
+                char name[128];
+                if (use_ring && v6) std::snprintf(name, sizeof(name), "pair_ring6_kernel<ring %d, %d threads, %d A/thread, groups of %d over %d lags%s%s>", ring, ring_nt, v6_apt, v6_u, v6_nl, n_dirs > 0 ? ", ellipse" : "", p.tf32 ? ", fp32 screening" : "");
                 else if (use_ring) std::snprintf(name, sizeof(name), "pair_ring_kernel<ring %d, %d threads%s>", ring, ring_nt, n_dirs > 0 ? ", ellipse" : "");
                 else std::snprintf(name, sizeof(name), "pair_kernel<%d threads%s>", nt, n_dirs > 0 ? ", ellipse" : "");
                 set_kernel_name(PIB_T_PAIR, name);

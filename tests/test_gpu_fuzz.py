@@ -25,7 +25,9 @@ VARIANTS = {
     # two A points per thread, 10-slot sliding ring (the BASELINE config 2 kernel), forced onto every geometry: spans wider
     # than the ring take the per-window sweeps; with and without the high-word fast path (PIB_HIW=0: exact stages only)
     "apt2_ring10": {"PIB_FORCE_RING": "1", "PIB_V6": "2,8,512,10", "PIB_LAGS_PER_GROUP": "2"},
-    "apt2_ring10_exact": {"PIB_FORCE_RING": "1", "PIB_V6": "2,8,512,10", "PIB_LAGS_PER_GROUP": "2", "PIB_HIW": "0"},
+    # the same with the fp32 screening path switched off (high-word fast path instead)
+    "apt2_ring10_hiw": {"PIB_FORCE_RING": "1", "PIB_V6": "2,8,512,10", "PIB_LAGS_PER_GROUP": "2", "PIB_F32": "0"},
+    "apt2_ring10_exact": {"PIB_FORCE_RING": "1", "PIB_V6": "2,8,512,10", "PIB_LAGS_PER_GROUP": "2", "PIB_HIW": "0", "PIB_F32": "0"},
     "ring16_exact": {"PIB_FORCE_RING": "1", "PIB_RING": "16", "PIB_HIW": "0"},
 }
 
