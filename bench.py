@@ -322,6 +322,11 @@ def run_b200(args):
                                "has no FP64 figure (its HBM %.0f GB/s / bf16 figures do not bound this kernel)"
                                % measured_peaks().get("hbm_gbs", float("nan")),
                 "flop_per_pair": FLOP_PER_PAIR, "pairs_evaluated_per_launch": evaluated_per_rank,
+                "flop_note": "algorithmic fp64 operations per pair of the reference formulation (SURVEY section 8d: 5 for the "
+                             "distance, 8 for the three sums), not instructions executed: with 'fp32 screening' in the kernel name "
+                             "the lag of a pair is decided in packed single precision (FADD2 / FMUL2 / FFMA2) and confirmed in fp64 "
+                             "only for the undecided groups, so the FP64 pipe itself is busy well below this fraction "
+                             "(profiles/r2_pair_ring6_f32_ncu_full.md)",
                 "kernel_ms_per_launch": pair_kernel_ms, "kernel_share_of_step": pair_kernel_ms / ms_per_step,
                 "traffic": profile_traffic("pair_ring_kernel")}
 
@@ -482,9 +487,9 @@ def run_b200(args):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(n, world),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 24), "d2h_bytes_per_step": out_bytes},
-                "gpu_launches": 14 * args.steps,
+                "gpu_launches": 15 * args.steps,
                 "gpu_launches_note": "per step: bbox_partial, bbox_final, curve_key, gather_soa, tile_box, mean_partial, mean_final, "
-                                     "group_sum, item_cost, pair_ring6, reduce_partials, cancellation_guard, pair_kernel + "
+                                     "group_sum, tile_f32, item_cost, pair_ring6, reduce_partials, cancellation_guard, pair_kernel + "
                                      "reduce_partials (conditional re-run: both return at once unless the guard fired) "
                                      "(+ CUB radix-sort passes and memsets, not counted)",
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "kriging": kriging, "extra": extra}

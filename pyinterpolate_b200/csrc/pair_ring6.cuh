@@ -46,6 +46,7 @@ static size_t ring6_smem_bytes(int n_slots, int lut_n)
     b += (size_t)(NT / 32) * CHUNK * sizeof(short2);
     b += ((size_t)lut_n * 2 + 15) / 16 * 16;
     b += (size_t)(n_slots + 4) * 16;                             // high-word slot table
+    b += (size_t)(n_slots + 4) * 4;                              // fp32 screening: lower band edge of the next slot
     return b;
 }
 
@@ -57,6 +58,21 @@ static size_t ring6_smem_bytes(int n_slots, int lut_n)
 #endif
 #ifndef PIB_V6_HIW
 #define PIB_V6_HIW 1
+#endif
+#ifndef PIB_V6_ANYISSUE
+#define PIB_V6_ANYISSUE 0
+#endif
+#ifndef PIB_F32_LOOKUP2
+#define PIB_F32_LOOKUP2 0
+#endif
+#ifndef PIB_F32_CHAIN
+#define PIB_F32_CHAIN 1
+#endif
+#ifndef PIB_F32_CLAMP
+#define PIB_F32_CLAMP 1
+#endif
+#ifndef PIB_F32_ZRELOAD
+#define PIB_F32_ZRELOAD 0
 #endif
 
 // packed single precision (two lanes per 64-bit register): FADD2 / FMUL2 / FFMA2 of sm_100
@@ -128,6 +144,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
     __shared__ __align__(16) unsigned char s_tf[F32S ? STAGES : 1][F32S ? TF32_TILE_BYTES : 16];
     __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES];     // TMA landed / every warp is done with the buffer
     __shared__ uint64_t s_live[2];                 // live B tiles of the item (double-buffered over consecutive items)
+    __shared__ unsigned s_issued[2];               // B tile loads of the item requested so far (any warp may request the next one)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_slots = p.n_slots, n_lags = n_slots - 2;
@@ -138,7 +155,8 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
     const uint16_t *const s_lut = reinterpret_cast<const uint16_t *>(reinterpret_cast<short2 *>(s_slot + n_slots + 4) + NW * CHUNK);
     // high-word fast path: {high word of the slot's threshold, high word of the next one, ring byte offsets of this and the next slot}
     int4 *const s_sloth = reinterpret_cast<int4 *>(const_cast<unsigned char *>(reinterpret_cast<const unsigned char *>(s_lut)) + ((size_t)p.lut2_n * 2 + 15) / 16 * 16);
-    const uint32_t slot_sa = smem_u32(s_slot), lut_sa = smem_u32(s_lut), sloth_sa = smem_u32(s_sloth);
+    float *const s_cnext = reinterpret_cast<float *>(s_sloth + n_slots + 4);
+    const uint32_t slot_sa = smem_u32(s_slot), lut_sa = smem_u32(s_lut), sloth_sa = smem_u32(s_sloth), cnext_sa = smem_u32(s_cnext);
 
     // my ring entries: sums at ring + 16 * off + my_acc[k], counts at ring + 16 * off + my_cnt[k]
     int my_acc[APT], my_cnt[APT];
@@ -169,14 +187,18 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
         e.offs = o_lo | (o_hi << 16);
         s_slot[s] = e;
         if (F32S && p.tf32) {
-            const float2 tf = p.slotf[s];
+            const float2 tf = p.slotf[s], tn = p.slotf[min(s + 1, n_slots + 3)];
             s_sloth[s] = make_int4(__float_as_int(tf.x), __float_as_int(tf.y), (int)(o_lo * 16u), (int)(o_hi * 16u));
+            // largest float <= (next threshold - its half-width): a squared distance below it is surely inside the next slot's
+            // lower band edge
+            float c = __fsub_rd(tn.x, tn.y);
+            s_cnext[s] = c;
         } else
         s_sloth[s] = make_int4((int)(e.T >> 32), e.next_hi, (int)(o_lo * 16u), (int)(o_hi * 16u));
     }
     const bool f32_on = F32S && p.tf32 != nullptr;
     // (same cells as the fp64 high-word table: a normal float's bits are ((high word - 896 * 2^20) << 3) | 3 more mantissa bits)
-    const int base_f = (p.lut2_base - 0x38000000) << 3;
+    const int base_f = p.lut2_base_f;
     {
         uint16_t *lut_w = const_cast<uint16_t *>(s_lut);
         for (int s = tid; s < p.lut2_n; s += NT) lut_w[s] = p.lut2[s];
@@ -270,7 +292,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                 }
                 m |= (uint64_t)__ballot_sync(0xffffffffu, live) << (32 * h);
             }
-            if (lane == 0) s_live[item_no & 1] = m;
+            if (lane == 0) { s_live[item_no & 1] = m; s_issued[item_no & 1] = 0; }
         }
         // ---- my warp: the lag slots each B tile can touch for MY A points (empty = skip the tile) ----------
         uint64_t f32_tiles = 0;                               // B tiles of the chunk the fp32 screening path may take
@@ -308,6 +330,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
         }
         __syncthreads();                                      // the one CTA-wide barrier of an item (s_live is double-buffered)
         uint64_t live = s_live[item_no & 1];
+        const uint32_t item_slot = item_no & 1;
         ++item_no;
         if (live == 0) continue;
 
@@ -383,6 +406,41 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
             if (F32S && f32_on) tma_load_1d(s_tf[b], p.tf32 + (size_t)t * TF32_TILE_BYTES, TF32_TILE_BYTES, &s_full[b]);
             ++pseq;
         };
+#if PIB_V6_ANYISSUE
+        // Any warp requests the next loads: a buffer is refilled as soon as its last reader has released it (by that reader, on
+        // its way into the next tile) instead of when one fixed producer thread comes by — with thread 0 as the only producer
+        // warp 0 waited at every tile for the slowest warp to release the previous one, and everybody else for warp 0.
+        const uint64_t live_all = live;
+        const int n_live = __popcll(live_all);
+        const uint32_t seq0 = seq;                            // (every warp consumes every live tile: CTA-uniform at the item's start)
+        auto request_tiles = [&]() {                          // lane 0 of any warp
+            volatile unsigned *issued = &s_issued[item_slot];
+            while (true) {
+                const unsigned t = *issued;
+                if ((int)t >= n_live) break;
+                const uint32_t g = seq0 + t, b = g % STAGES;
+                if (g >= STAGES && !mbar_test(&s_empty[b], ((g / STAGES) - 1) & 1)) break;     // a reader still holds the buffer
+                if (atomicCAS(&s_issued[item_slot], t, t + 1) != t) continue;                  // another warp took this one
+                // the t-th live tile of the item
+                const uint32_t m_lo = (uint32_t)live_all, m_hi = (uint32_t)(live_all >> 32);
+                const unsigned c_lo = __popc(m_lo);
+                const int bit = t < c_lo ? (int)__fns(m_lo, 0, (int)t + 1) : 32 + (int)__fns(m_hi, 0, (int)(t - c_lo) + 1);
+                const int tile = tb0 + bit;
+                PIB_DBG_ASSERT(bit >= 0 && bit < 64 && tile >= 0 && tile < n_tiles);
+                mbar_expect_tx(&s_full[b], TILE_TX);
+                tma_load_1d(s_txy[b], p.xy + (size_t)tile * TILE, TILE * sizeof(double2), &s_full[b]);
+                tma_load_1d(s_tz[b], p.z + (size_t)tile * TILE, TILE * sizeof(double), &s_full[b]);
+                tma_load_1d(s_gs[b], p.gsum + (size_t)tile * (TILE / U), (TILE / U) * sizeof(double2), &s_full[b]);
+                if (F32S && f32_on) tma_load_1d(s_tf[b], p.tf32 + (size_t)tile * TF32_TILE_BYTES, TF32_TILE_BYTES, &s_full[b]);
+            }
+        };
+        (void)pseq; (void)issue_tile;
+        while (live) {
+            const int tb = tb0 + __ffsll((long long)live) - 1;
+            live &= live - 1;
+            if (lane == 0) request_tiles();
+            __syncwarp();
+#else
         uint64_t ahead = live;                                // thread 0: tiles not yet requested
         if (tid == 0) {
             for (int i = 0; i < STAGES - 1 && ahead; ++i) {
@@ -397,6 +455,7 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                 issue_tile(tb0 + __ffsll((long long)ahead) - 1);
                 ahead &= ahead - 1;
             }
+#endif
             const uint32_t b = seq % STAGES, phase = (seq / STAGES) & 1;
             // ---- my warp's ring window (warp-uniform) ---------------------------------------------------
             const short2 rng = s_range[tb - tb0];
@@ -878,26 +937,41 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                     s.redo = false;
 #pragma unroll
                     for (int k = 0; k < APT; ++k) {
+#if PIB_F32_CLAMP
+                        // clamp ahead of the shift: add + max fuse into one instruction
+                        const int idx = min(max(__float_as_int(mn[k]) - base_f, 0), (lut_last << (LUT2_SHIFT + 3)) | 0xffff) >> (LUT2_SHIFT + 3);
+#else
                         int idx = (__float_as_int(mn[k]) - base_f) >> (LUT2_SHIFT + 3);
                         idx = min(max(idx, 0), lut_last);
+#endif
                         unsigned short q0;
                         asm("ld.shared.u16 %0, [%1];" : "=h"(q0) : "r"(lut_sa + 2u * (uint32_t)idx));
                         PIB_DBG_ASSERT((int)q0 < n_slots);
                         uint32_t ea = sloth_sa + 16u * (uint32_t)q0;
-                        float tm, hw0;
-                        if (MULTI_FIX) {
-                            while (true) {
-                                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(tm), "=f"(hw0) : "r"(ea));
-                                if (!(__fsub_rn(mn[k], tm) > hw0)) break;
-                                ea += 16u;
-                            }
-                        } else {
+                        float tmid, hwq;
+#if PIB_F32_LOOKUP2
+                        if (!MULTI_FIX) {
+                            // threshold and half-width of the table's slot first, the whole entry of the slot it decides on after
+                            float tm, hw0;
                             asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(tm), "=f"(hw0) : "r"(ea));
                             ea += (__fsub_rn(mn[k], tm) > hw0) ? 16u : 0u;
                         }
-                        float tmid, hwq, tnext, hwnext;
+#endif
                         asm("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(tmid), "=f"(hwq), "=r"(s.off_lo[k]), "=r"(s.off_hi[k]) : "r"(ea));
-                        asm("ld.shared.v2.f32 {%0, %1}, [%2+16];" : "=f"(tnext), "=f"(hwnext) : "r"(ea));
+                        if (PIB_F32_LOOKUP2 && !MULTI_FIX) {
+                        } else if (MULTI_FIX) {
+                            while (__fsub_rn(mn[k], tmid) > hwq) {
+                                ea += 16u;
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(tmid), "=f"(hwq), "=r"(s.off_lo[k]), "=r"(s.off_hi[k]) : "r"(ea));
+                            }
+                        } else {
+                            // the table cell is at most one slot low: the next entry is loaded by the few lanes that need it
+                            asm("{\n\t.reg .pred p;\n\t.reg .f32 t;\n\tsub.rn.f32 t, %5, %0;\n\tsetp.gt.f32 p, t, %1;\n\t"
+                                "@p ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+16];\n\t@p add.u32 %4, %4, 16;\n\t}"
+                                : "+f"(tmid), "+f"(hwq), "+r"(s.off_lo[k]), "+r"(s.off_hi[k]), "+r"(ea) : "f"(mn[k]));
+                        }
+                        float cnext;
+                        asm("ld.shared.f32 %0, [%1];" : "=f"(cnext) : "r"(cnext_sa + ((ea - sloth_sa) >> 2)));
                         s.hw[k] = hwq;
                         const unsigned long long nt2 = f2_pack(-tmid, -tmid);
                         float em = INFINITY;
@@ -907,35 +981,60 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                             em = fminf(fminf(em, fabsf(s.e[k][2 * m])), fabsf(s.e[k][2 * m + 1]));
                         }
                         // undecided pair, or a pair that may lie beyond the group's second lag
-                        s.redo |= (em <= hwq) | (__fsub_rn(mx[k], tnext) >= -hwnext);
+                        s.redo |= (em <= hwq) | (mx[k] >= cnext);
                     }
                 };
                 auto stage_b_f = [&](int g, const GrpF &s) __attribute__((always_inline)) {
                     const int j0 = g * U;
+                    // second-lag sums of both A points from ONE pass over the group's values
+                    double h1a[APT], h1b[APT], h2a[APT], h2b[APT];
+                    int ch[APT];
+#pragma unroll
+                    for (int k = 0; k < APT; ++k) ch[k] = 0;
+#pragma unroll
+                    for (int u = 0; u < U; u += 2) {
+                        double2 zz = *reinterpret_cast<const double2 *>(bz + j0 + u);
+#pragma unroll
+                        for (int k = 0; k < APT; ++k) {
+#if PIB_F32_ZRELOAD
+                            // a second load of the two values instead of register copies of their low words
+                            if (k > 0) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(zz.x), "=d"(zz.y) : "r"(smem_u32(bz + j0 + u)));
+#endif
+                            int za_hi, zb_hi;
+                            asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %3, %4;\n\tselp.b32 %0, %2, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
+                                : "=r"(za_hi), "+r"(ch[k]) : "r"(__double2hiint(zz.x)), "f"(s.e[k][u]), "f"(s.hw[k]));
+                            asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %3, %4;\n\tselp.b32 %0, %2, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
+                                : "=r"(zb_hi), "+r"(ch[k]) : "r"(__double2hiint(zz.y)), "f"(s.e[k][u + 1]), "f"(s.hw[k]));
+                            const double za = __hiloint2double(za_hi, __double2loint(zz.x));
+                            const double zb = __hiloint2double(zb_hi, __double2loint(zz.y));
+#if PIB_F32_CHAIN
+                            // one chain per sum (the two A points give four independent chains): two fp64 additions fewer per
+                            // A point and group than with even / odd partial sums
+                            if (u == 0) {
+                                h1a[k] = za + zb; h2a[k] = __fma_rn(zb, zb, __dmul_rn(za, za));
+                            } else {
+                                h1a[k] = (h1a[k] + za) + zb; h2a[k] = __fma_rn(zb, zb, __fma_rn(za, za, h2a[k]));
+                            }
+#else
+                            if (u == 0) {
+                                h1a[k] = za; h2a[k] = __dmul_rn(za, za);
+                                h1b[k] = zb; h2b[k] = __dmul_rn(zb, zb);
+                            } else {
+                                h1a[k] += za; h2a[k] = __fma_rn(za, za, h2a[k]);
+                                h1b[k] += zb; h2b[k] = __fma_rn(zb, zb, h2b[k]);
+                            }
+#endif
+                        }
+                    }
                     const double2 gs = bgs[g];
 #pragma unroll
                     for (int k = 0; k < APT; ++k) {
-                        double h1a, h1b, h2a, h2b;
-                        int ch = 0;
-#pragma unroll
-                        for (int u = 0; u < U; u += 2) {
-                            const double2 zz = *reinterpret_cast<const double2 *>(bz + j0 + u);
-                            int za_hi, zb_hi;
-                            asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %3, %4;\n\tselp.b32 %0, %2, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
-                                : "=r"(za_hi), "+r"(ch) : "r"(__double2hiint(zz.x)), "f"(s.e[k][u]), "f"(s.hw[k]));
-                            asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %3, %4;\n\tselp.b32 %0, %2, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
-                                : "=r"(zb_hi), "+r"(ch) : "r"(__double2hiint(zz.y)), "f"(s.e[k][u + 1]), "f"(s.hw[k]));
-                            const double za = __hiloint2double(za_hi, __double2loint(zz.x));
-                            const double zb = __hiloint2double(zb_hi, __double2loint(zz.y));
-                            if (u == 0) {
-                                h1a = za; h2a = __dmul_rn(za, za);
-                                h1b = zb; h2b = __dmul_rn(zb, zb);
-                            } else {
-                                h1a += za; h2a = __fma_rn(za, za, h2a);
-                                h1b += zb; h2b = __fma_rn(zb, zb, h2b);
-                            }
-                        }
-                        const double h1 = h1a + h1b, h2 = h2a + h2b;
+#if PIB_F32_CHAIN
+                        const double h1 = h1a[k], h2 = h2a[k];
+                        (void)h1b; (void)h2b;
+#else
+                        const double h1 = h1a[k] + h1b[k], h2 = h2a[k] + h2b[k];
+#endif
                         const uint32_t a_lo = acc_sa[k] + s.off_lo[k], a_hi = acc_sa[k] + s.off_hi[k];
                         const uint32_t n_lo = cnt_sa[k] + s.off_lo[k], n_hi = cnt_sa[k] + s.off_hi[k];
                         PIB_DBG_ASSERT(s.off_lo[k] <= (uint32_t)RING * SLOT_BYTES && s.off_hi[k] <= (uint32_t)RING * SLOT_BYTES &&
@@ -948,8 +1047,8 @@ __global__ void __launch_bounds__(NT, 1) pair_ring6_kernel(const PairParams p)
                         asm volatile("ld.shared.u16 %0, [%1];" : "=r"(c_hi) : "r"(n_hi) : "memory");
                         v_lo.x += gs.x - h1; v_lo.y += gs.y - h2;
                         v_hi.x += h1;        v_hi.y += h2;
-                        c_lo = c_lo + (uint32_t)U - (uint32_t)ch;
-                        c_hi = c_hi + (uint32_t)ch;
+                        c_lo = c_lo + (uint32_t)U - (uint32_t)ch[k];
+                        c_hi = c_hi + (uint32_t)ch[k];
                         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a_lo), "d"(v_lo.x), "d"(v_lo.y) : "memory");
                         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a_hi), "d"(v_hi.x), "d"(v_hi.y) : "memory");
                         asm volatile("st.shared.u16 [%0], %1;" ::"r"(n_lo), "r"(c_lo) : "memory");

@@ -52,6 +52,7 @@ struct PairParams {
     const double *upper;         // [n_slots] slot upper thresholds on d2: U[0] = 0, U[s] = T(edge[s-1]), U[last] = +inf
     const uint16_t *lut2;        // [lut2_n] (hi word of d2 - lut2_base) >> 13 -> first candidate slot
     int lut2_base, lut2_n;
+    int lut2_base_f;             // the same base as fp32 bits (a normal float's bits are (high word - 896 * 2^20) << 3 | 3 more mantissa bits)
     double box_slack;            // ellipse ring kernel: slack on the whitened bounding boxes
     double max_d2;               // T(edges[n_lags-1])
     double w00, w01, w10, w11;   // whitening matrix (ellipse)
@@ -100,6 +101,20 @@ static __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
+}
+static __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 static __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
 {
@@ -1496,6 +1511,7 @@ int variogram_device(const double *d_xyz, int64_t n, const double *edges, const 
         p.shard_index = shard_index; p.shard_count = shard_count; p.partial = d_partial;
         p.pairs_evaluated = d_evaluated;
         p.lut2 = d_lut2; p.lut2_base = lut2_base; p.lut2_n = (int)lut2.size();
+        p.lut2_base_f = (int)((uint32_t)(lut2_base - 0x38000000) << 3);
         p.box_slack = 0.0;
         p.gsum = nullptr;
         double *d_mean = nullptr;                  // ring kernel: mean of z (its sums come out centred)
