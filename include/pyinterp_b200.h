@@ -167,6 +167,22 @@ PIB_API int pib_variogram_cloud_host(const double *xyz, int64_t n,
                              const int64_t *lag_offsets, double *values);
 
 /* ------------------------------------------------------------------------------------------
+ * Triangle-method point cloud — what the reference's point_cloud_semivariance returns for a direction with its DEFAULT
+ * dir_neighbors_selection_method='t'.  Replaces
+ *   semivariogram/experimental/functions/directional.py:213-273   from_triangle_cloud
+ *   semivariogram/experimental/functions/directional.py:583-620   _get_values_triangle_cloud
+ * tri_lags, cos_t, sin_t, tolerance: as for pib_variogram_triangle_host.
+ * lag_offsets [n_lags + 1] (HOST): start of each lag's block in `values`; lag b holds count[b] values, count from
+ * pib_variogram_triangle_host (ORDERED pairs, q == p of the first lag included).  The call returns PIB_ERR_INVALID
+ * without writing if its own membership pass disagrees with the offsets.
+ * values [lag_offsets[n_lags]] (HOST, out): (z_p - z_q)^2, centre p ascending, neighbour q ascending within a centre.
+ * ---------------------------------------------------------------------------------------- */
+PIB_API int pib_variogram_triangle_cloud_host(const double *xyz, int64_t n,
+                                      const double *tri_lags, int n_lags,
+                                      double cos_t, double sin_t, double tolerance,
+                                      const int64_t *lag_offsets, double *values);
+
+/* ------------------------------------------------------------------------------------------
  * Point kriging — batched neighbour search + system assembly + solve.
  *
  * Replaces the per-location Python loop of

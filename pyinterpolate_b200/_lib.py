@@ -23,7 +23,7 @@ STATUS_LSA, STATUS_ZERO_MATRIX = 4, 5
 EXPORTS = ("pib_trim", "pib_last_kernel_name", "pib_krige_loo_host", "pib_krige_ex_device", "pib_krige_ex_host", "pib_last_error", "pib_version", "pib_device_sm_count", "pib_variogram_device",
            "pib_variogram_host", "pib_krige_device", "pib_krige_host", "pib_gamma_host",
            "pib_fp64_peak_tflops", "pib_last_kernel_ms", "pib_variogram_cloud_host",
-           "pib_variogram_weighted_host", "pib_variogram_triangle_host")
+           "pib_variogram_weighted_host", "pib_variogram_triangle_host", "pib_variogram_triangle_cloud_host")
 
 _lib = None
 
@@ -63,6 +63,7 @@ def load():
     L.pib_variogram_cloud_host.argtypes = [dp, i64, dp, dp, i32, dp, i32, dp, dp]
     L.pib_variogram_weighted_host.argtypes = [dp, dp, i64, dp, dp, i32, dp, i32, dp, dp]
     L.pib_variogram_triangle_host.argtypes = [dp, i64, dp, i32, f64, f64, f64, dp, dp]
+    L.pib_variogram_triangle_cloud_host.argtypes = [dp, i64, dp, i32, f64, f64, f64, dp, dp]
     for name in EXPORTS:
         getattr(L, name).restype = getattr(L, name).restype or i32
     L.pib_last_error.restype = ctypes.c_char_p
@@ -130,6 +131,22 @@ def variogram_triangle_host(xyz, tri_lags, cos_t, sin_t, tolerance):
                                        float(tolerance), _host_ptr(sums), _host_ptr(cnt))
     check(rc, "pib_variogram_triangle_host")
     return sums, cnt
+
+
+def variogram_triangle_cloud_host(xyz, tri_lags, cos_t, sin_t, tolerance):
+    """Triangle-method point cloud: per lag the (z_p - z_q)^2 of the ordered pairs, in the reference's order
+    (functions/directional.py:213-273).  Returns a list of float64 arrays, one per lag."""
+    L = load()
+    xyz, tri_lags = _f64(xyz), _f64(tri_lags).reshape(-1, 9)
+    n, n_lags = xyz.shape[0], tri_lags.shape[0]
+    _, counts = variogram_triangle_host(xyz, tri_lags, cos_t, sin_t, tolerance)
+    offsets = np.zeros(n_lags + 1, dtype=np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    values = np.empty(int(offsets[-1]), dtype=np.float64)
+    rc = L.pib_variogram_triangle_cloud_host(_host_ptr(xyz), n, _host_ptr(tri_lags), n_lags, float(cos_t), float(sin_t),
+                                             float(tolerance), _host_ptr(offsets), _host_ptr(values))
+    check(rc, "pib_variogram_triangle_cloud_host")
+    return [values[offsets[b]:offsets[b + 1]] for b in range(n_lags)]
 
 
 def variogram_cloud_host(xyz, edges, lower=None, W=None):

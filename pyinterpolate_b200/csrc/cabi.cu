@@ -93,6 +93,9 @@ int variogram_weighted_device(const double *d_xyz, const double *d_weights, int6
                               int64_t *d_count, cudaStream_t stream);
 int variogram_triangle_device(const double *d_xyz, int64_t n, const double *tri_lags, int n_lags, double cos_t,
                               double sin_t, double tolerance, double *d_sums, int64_t *d_count, cudaStream_t stream);
+int variogram_triangle_cloud_device(const double *d_xyz, int64_t n, const double *tri_lags, int n_lags, double cos_t,
+                                    double sin_t, double tolerance, const int64_t *lag_offsets, double *d_values,
+                                    cudaStream_t stream);
 int krige_device(const double *d_known, int64_t n, const double *d_values, int n_sets, const double *params,
                  const double *d_unknown, int64_t m, int model, int mode, double process_mean, int k,
                  double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
@@ -272,6 +275,35 @@ int pib_variogram_cloud_host(const double *xyz, int64_t n, const double *edges, 
         if (rc == PIB_OK && e == cudaSuccess) e = cudaMemcpyAsync(values, d_values, sizeof(double) * total, cudaMemcpyDeviceToHost, stream);
         if (rc == PIB_OK && e == cudaSuccess) e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) { set_error(std::string("cloud: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; }
+    }
+    cudaStreamSynchronize(stream);
+    cudaStreamDestroy(stream);
+    return rc;
+}
+
+int pib_variogram_triangle_cloud_host(const double *xyz, int64_t n, const double *tri_lags, int n_lags, double cos_t,
+                                      double sin_t, double tolerance, const int64_t *lag_offsets, double *values)
+{
+    PIB_CHECK((xyz || n == 0) && tri_lags && lag_offsets, PIB_ERR_INVALID, "triangle cloud: NULL pointer");
+    PIB_CHECK(n >= 0 && n_lags >= 1, PIB_ERR_INVALID, "triangle cloud: need n >= 0 and at least one lag");
+    const int64_t total = lag_offsets[n_lags];
+    PIB_CHECK(total >= 0 && (values || total == 0), PIB_ERR_INVALID, "triangle cloud: values is NULL");
+    if (n < 1 || total == 0) return PIB_OK;
+    cudaStream_t stream;
+    PIB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    int rc;
+    {
+        Scratch ws(stream);
+        double *d_xyz, *d_values;
+        rc = ws.alloc(&d_xyz, (size_t)n * 3);
+        if (rc == PIB_OK) rc = ws.alloc(&d_values, (size_t)total);
+        cudaError_t e = cudaSuccess;
+        if (rc == PIB_OK) e = cudaMemcpyAsync(d_xyz, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, stream);
+        if (rc == PIB_OK && e == cudaSuccess)
+            rc = variogram_triangle_cloud_device(d_xyz, n, tri_lags, n_lags, cos_t, sin_t, tolerance, lag_offsets, d_values, stream);
+        if (rc == PIB_OK && e == cudaSuccess) e = cudaMemcpyAsync(values, d_values, sizeof(double) * total, cudaMemcpyDeviceToHost, stream);
+        if (rc == PIB_OK && e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { set_error(std::string("triangle cloud: ") + cudaGetErrorString(e)); rc = PIB_ERR_CUDA; }
     }
     cudaStreamSynchronize(stream);
     cudaStreamDestroy(stream);

@@ -1747,7 +1747,8 @@ __global__ void cloud_kernel(const double *__restrict__ xyz, int64_t n, const do
 }
 
 // exclusive scan of each lag's row counts, shifted by the lag's global offset (one CTA per lag)
-__global__ void cloud_scan_kernel(unsigned long long *cursor, int64_t n, const int64_t *__restrict__ lag_offsets)
+__global__ void cloud_scan_kernel(unsigned long long *cursor, int64_t n, const int64_t *__restrict__ lag_offsets,
+                                  unsigned long long *__restrict__ lag_end /* NULL, or [n_lags]: offset + total of each lag */)
 {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_carry;
@@ -1780,6 +1781,7 @@ __global__ void cloud_scan_kernel(unsigned long long *cursor, int64_t n, const i
         if (threadIdx.x == blockDim.x - 1) s_carry = carry + s_warp[warp] + incl;
         __syncthreads();
     }
+    if (lag_end && threadIdx.x == 0) lag_end[blockIdx.x] = s_carry;
 }
 
 int variogram_cloud_device(const double *d_xyz, int64_t n, const double *edges, const double *lower, int n_lags,
@@ -1808,7 +1810,7 @@ int variogram_cloud_device(const double *d_xyz, int64_t n, const double *edges, 
     const int grid = (int)((n + 127) / 128);
     cloud_kernel<false><<<grid, 128, 0, stream>>>(d_xyz, n, d_up, d_low, n_lags, n_dirs > 0, w00, w01, w10, w11, d_cursor, nullptr);
     PIB_CUDA(cudaGetLastError());
-    cloud_scan_kernel<<<n_lags, 1024, 0, stream>>>(d_cursor, n, d_off);
+    cloud_scan_kernel<<<n_lags, 1024, 0, stream>>>(d_cursor, n, d_off, nullptr);
     PIB_CUDA(cudaGetLastError());
     cloud_kernel<true><<<grid, 128, 0, stream>>>(d_xyz, n, d_up, d_low, n_lags, n_dirs > 0, w00, w01, w10, w11, d_cursor, d_values);
     PIB_CUDA(cudaGetLastError());
@@ -2052,6 +2054,53 @@ static __device__ __forceinline__ bool raw_mask_ref(const TriLag &L, double px, 
     return in_triangle_ref(ax, ay, bx, by, cx, cy, qx, qy) || in_triangle_ref(ax, ay, ix, iy, cx, cy, qx, qy);
 }
 
+// The lags of the ORDERED pair (centre p, neighbour q) under the triangle selection, reported through emit(lag, certain).
+// A pair far from every rhombus edge belongs to exactly one lag — the first with rho = |u| + |v| / tol <= h — and is
+// reported as certain; lags whose edge lies within the band of rho (and every lag for q == p, which sits on an edge of
+// every triangle) are decided by the reference's own operation sequence and its XOR with the previous lag's mask
+// (clean_mask_indices, distance/angular.py:188-218).  H(k) = lag distance k.
+template <class LagH, class Emit>
+static __device__ __forceinline__ void triangle_pair_lags(const TriLag *__restrict__ lags, int n_lags, LagH H, double h_max,
+                                                          double cos_t, double sin_t, double inv_tol, double band_rel,
+                                                          double px, double py, double qx, double qy, bool same_point,
+                                                          Emit emit)
+{
+    const double dx = qx - px, dy = qy - py;
+    const double u = dx * cos_t + dy * sin_t, v = dy * cos_t - dx * sin_t;
+    const double rho = fabs(u) + fabs(v) * inv_tol;
+    const double band = band_rel * (fabs(px) + fabs(py) + fabs(qx) + fabs(qy) + h_max) * (1.0 + inv_tol);
+    if (rho > h_max + band) return;                             // outside every rhombus for certain
+    // k* = first lag with rho <= h_k
+    int lo = 0, hi = n_lags;                                    // hi == n_lags: beyond the last lag
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (rho <= H(mid)) hi = mid; else lo = mid + 1; }
+    const int ks = lo;
+    // lags whose edge is within the band of rho need the reference's own test; q == p needs it everywhere
+    int k_first = ks, k_last = ks - 1;                          // empty range = everything certain
+    if (same_point) { k_first = 0; k_last = n_lags - 1; }
+    else {
+        if (ks < n_lags && H(ks) - rho <= band) k_last = ks;
+        if (ks > 0 && rho - H(ks - 1) <= band) { k_first = ks - 1; if (k_last < k_first) k_last = ks - 1; }
+        // (edges farther away than the neighbours of k* are farther than the band too: lags ascend)
+        while (k_first > 0 && rho - H(k_first - 1) <= band) --k_first;
+        while (k_last + 1 < n_lags && H(k_last + 1) - rho <= band) ++k_last;
+    }
+    if (k_last < k_first) {
+        if (ks < n_lags) emit(ks, true);
+        return;
+    }
+    // uncertain range [k_first, k_last]: raw masks from the reference's arithmetic, certain outside it
+    bool prev = (k_first > 0) ? (k_first - 1 >= ks) : false;   // raw_{k_first-1}: certain
+    for (int k = k_first; k <= min(k_last + 1, n_lags - 1); ++k) {
+        const bool raw = (k <= k_last) ? raw_mask_ref(lags[k], px, py, qx, qy) : (k >= ks);
+        const bool in_lag = (k == 0) ? raw : (raw != prev);    // clean_mask_indices: XOR with the previous lag
+        if (in_lag) emit(k, false);
+        prev = raw;
+    }
+    // lags beyond k_last + 1 are certain and equal to their predecessor (both 0 or both 1): nothing to add,
+    // except when k* lies beyond the uncertain range
+    if (ks > k_last + 1 && ks < n_lags) emit(ks, false);
+}
+
 __global__ void __launch_bounds__(128) triangle_kernel(const double2 *__restrict__ xy, const double *__restrict__ z,
                                                        const int32_t *__restrict__ orig, int64_t n,
                                                        const double4 *__restrict__ rbox /* per tile, rotated (u, v) */,
@@ -2118,56 +2167,20 @@ __global__ void __launch_bounds__(128) triangle_kernel(const double2 *__restrict
                 const int64_t j0 = (int64_t)(t0 + tl) * TILE, j1 = min(j0 + (int64_t)TILE, n);
                 if (!valid) continue;
         for (int64_t j = j0; j < j1; ++j) {
-            const double qx = xy[j].x, qy = xy[j].y;
-            const double dx = qx - px, dy = qy - py;
-            const double u = dx * cos_t + dy * sin_t, v = dy * cos_t - dx * sin_t;
-            const double rho = fabs(u) + fabs(v) * inv_tol;
-            const double band = band_rel * (fabs(px) + fabs(py) + fabs(qx) + fabs(qy) + h_max) * (1.0 + inv_tol);
-            if (rho > h_max + band) continue;                       // outside every rhombus for certain
-            // k* = first lag with rho <= h_k
-            int lo = 0, hi = n_lags;                                // hi == n_lags: beyond the last lag
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (rho <= H(mid)) hi = mid; else lo = mid + 1; }
-            const int ks = lo;
-            // lags whose edge is within the band of rho need the reference's own test; q == p needs it everywhere
-            int k_first = ks, k_last = ks - 1;                      // empty range = everything certain
-            if (orig[j] == orig[i]) { k_first = 0; k_last = n_lags - 1; }
-            else {
-                if (ks < n_lags && H(ks) - rho <= band) k_last = ks;
-                if (ks > 0 && rho - H(ks - 1) <= band) { k_first = ks - 1; if (k_last < k_first) k_last = ks - 1; }
-                // (edges farther away than the neighbours of k* are farther than the band too: lags ascend)
-                while (k_first > 0 && rho - H(k_first - 1) <= band) --k_first;
-                while (k_last + 1 < n_lags && H(k_last + 1) - rho <= band) ++k_last;
-            }
-            const double qz = z[j];
+            const double qx = xy[j].x, qy = xy[j].y, qz = z[j];
             const double dz = pz - qz;
-            if (k_last < k_first) {
-                if (ks < n_lags) {                                  // certain: counted once, in lag k*
-                    if (ks != run) { flush(); run = ks; }
+            triangle_pair_lags(lags, n_lags, H, h_max, cos_t, sin_t, inv_tol, band_rel, px, py, qx, qy, orig[j] == orig[i],
+                               [&](int k, bool certain) {
+                if (certain) {                                      // counted once, in lag k: runs accumulate in registers
+                    if (k != run) { flush(); run = k; }
                     r1 += dz * dz; r2 += pz * qz; r3 += qz; ++rc;
-                }
-                continue;
-            }
-            // uncertain range [k_first, k_last]: raw masks from the reference's arithmetic, certain outside it
-            bool prev = (k_first > 0) ? (k_first - 1 >= ks) : false;           // raw_{k_first-1}: certain
-            for (int k = k_first; k <= min(k_last + 1, n_lags - 1); ++k) {
-                const bool raw = (k <= k_last) ? raw_mask_ref(lags[k], px, py, qx, qy) : (k >= ks);
-                const bool in_lag = (k == 0) ? raw : (raw != prev);            // clean_mask_indices: XOR with the previous lag
-                if (in_lag) {
+                } else {
                     atomicAdd(&sums[k], dz * dz);
                     atomicAdd(&sums[n_lags + k], pz * qz);
                     atomicAdd(&sums[2 * n_lags + k], qz);
                     atomicAdd(&count[k], 1ull);
                 }
-                prev = raw;
-            }
-            // lags beyond k_last + 1 are certain and equal to their predecessor (both 0 or both 1): nothing to add,
-            // except when k* lies beyond the uncertain range
-            if (ks > k_last + 1 && ks < n_lags) {
-                atomicAdd(&sums[ks], dz * dz);
-                atomicAdd(&sums[n_lags + ks], pz * qz);
-                atomicAdd(&sums[2 * n_lags + ks], qz);
-                atomicAdd(&count[ks], 1ull);
-            }
+            });
         }
             }
         }
@@ -2222,6 +2235,67 @@ int variogram_triangle_device(const double *d_xyz, int64_t n, const double *tri_
     triangle_kernel<<<grid, 128, tri_smem, stream>>>(sp.xy, sp.z, sp.orig, n, d_rbox, n_tiles, cull_rho, d_lags, n_lags, cos_t,
                                                      sin_t, 1.0 / tolerance, 1e-9, d_sums,
                                                      reinterpret_cast<unsigned long long *>(d_count), use_smem);
+    PIB_CUDA(cudaGetLastError());
+    return PIB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Triangle-method point cloud (SURVEY section 8f-2 with the reference's DEFAULT directional method):
+//   semivariogram/experimental/functions/directional.py:213-273 (from_triangle_cloud), :583-620
+// Per lag the values (z_i - z_j)^2 of the cleaned masks, row i ascending and j ascending within a row (points[mask]),
+// the pair q == p of the first lag included.  Same two passes as cloud_kernel (count, scan, write) on the points in
+// the caller's order; membership comes from triangle_pair_lags, i.e. exactly what triangle_kernel counts.
+// ---------------------------------------------------------------------------------------------
+template <bool WRITE>
+__global__ void triangle_cloud_kernel(const double *__restrict__ xyz, int64_t n, const TriLag *__restrict__ lags, int n_lags,
+                                      double cos_t, double sin_t, double inv_tol, double band_rel,
+                                      unsigned long long *__restrict__ cursor /* [n_lags][n] */, double *__restrict__ values)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+    const double h_max = lags[n_lags - 1].h;
+    auto H = [&](int k) -> double { return lags[k].h; };
+    for (int64_t j = 0; j < n; ++j) {
+        const double qx = xyz[3 * j], qy = xyz[3 * j + 1];
+        triangle_pair_lags(lags, n_lags, H, h_max, cos_t, sin_t, inv_tol, band_rel, px, py, qx, qy, j == i, [&](int k, bool) {
+            unsigned long long *c = cursor + (size_t)k * n + i;
+            if (WRITE) {
+                const double dz = pz - xyz[3 * j + 2];
+                values[(*c)++] = dz * dz;
+            } else ++(*c);
+        });
+    }
+}
+
+int variogram_triangle_cloud_device(const double *d_xyz, int64_t n, const double *tri_lags /* host [n_lags][9] */, int n_lags,
+                                    double cos_t, double sin_t, double tolerance, const int64_t *lag_offsets /* host [n_lags + 1] */,
+                                    double *d_values, cudaStream_t stream)
+{
+    PIB_CHECK(n >= 0 && n_lags >= 1 && tri_lags && lag_offsets, PIB_ERR_INVALID, "triangle cloud: bad arguments");
+    PIB_CHECK(tolerance > 0, PIB_ERR_INVALID, "triangle cloud: tolerance must be positive");
+    if (n < 1) return PIB_OK;
+    Scratch ws(stream);
+    TriLag *d_lags;
+    int64_t *d_off;
+    unsigned long long *d_cursor, *d_end;
+    PIB_TRY(ws.alloc(&d_lags, n_lags)); PIB_TRY(ws.alloc(&d_off, n_lags)); PIB_TRY(ws.alloc(&d_end, n_lags));
+    PIB_TRY(ws.alloc(&d_cursor, (size_t)n_lags * n));
+    PIB_CUDA(cudaMemcpyAsync(d_lags, tri_lags, sizeof(TriLag) * n_lags, cudaMemcpyHostToDevice, stream));
+    PIB_CUDA(cudaMemcpyAsync(d_off, lag_offsets, n_lags * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+    PIB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long) * n_lags * n, stream));
+    const int grid = (int)((n + 127) / 128);
+    triangle_cloud_kernel<false><<<grid, 128, 0, stream>>>(d_xyz, n, d_lags, n_lags, cos_t, sin_t, 1.0 / tolerance, 1e-9, d_cursor, nullptr);
+    PIB_CUDA(cudaGetLastError());
+    cloud_scan_kernel<<<n_lags, 1024, 0, stream>>>(d_cursor, n, d_off, d_end);
+    PIB_CUDA(cudaGetLastError());
+    // the caller sized `values` from the counts of pib_variogram_triangle_host: refuse to write if this pass disagrees
+    std::vector<unsigned long long> end(n_lags);
+    PIB_CUDA(cudaMemcpyAsync(end.data(), d_end, sizeof(unsigned long long) * n_lags, cudaMemcpyDeviceToHost, stream));
+    PIB_CUDA(cudaStreamSynchronize(stream));
+    for (int b = 0; b < n_lags; ++b)
+        PIB_CHECK((int64_t)end[b] == lag_offsets[b + 1], PIB_ERR_INVALID, "triangle cloud: lag_offsets do not match the pair counts");
+    triangle_cloud_kernel<true><<<grid, 128, 0, stream>>>(d_xyz, n, d_lags, n_lags, cos_t, sin_t, 1.0 / tolerance, 1e-9, d_cursor, d_values);
     PIB_CUDA(cudaGetLastError());
     return PIB_OK;
 }

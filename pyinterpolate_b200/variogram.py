@@ -212,12 +212,12 @@ def point_cloud_semivariance(ds, step_size=None, max_range=None, direction=None,
     if direction is not None and tolerance is not None:
         _check_method(direction, dir_neighbors_selection_method, None)
         if dir_neighbors_selection_method in ("t", "triangle"):
-            # the reference sends 't' (its default) to from_triangle_cloud (experimental_semivariogram.py:282-294); only
-            # the ellipse cloud is built here — substituting it silently would return a different point set
-            raise NotImplementedError("directional point clouds are built for dir_neighbors_selection_method='e' only; "
-                                      "the triangle-method cloud (functions/directional.py:213-273) is not implemented")
-        W = core.define_whitening_matrix(direction, tolerance).reshape(4)
-        clouds = _lib.variogram_cloud_host(xyz, lags64, lower=core.ellipse_lower_limits(lags64), W=W)
+            # the reference's default: from_triangle_cloud (experimental_semivariogram.py:282-294, directional.py:213-273)
+            table, c, s_ = _triangle_lag_table(lags, direction, tolerance)
+            clouds = _lib.variogram_triangle_cloud_host(xyz, table, c, s_, tolerance)
+        else:
+            W = core.define_whitening_matrix(direction, tolerance).reshape(4)
+            clouds = _lib.variogram_cloud_host(xyz, lags64, lower=core.ellipse_lower_limits(lags64), W=W)
     else:
         clouds = _lib.variogram_cloud_host(xyz, lags64)
     out = OrderedDict()

@@ -250,11 +250,3 @@ def test_directional_variogram_passes_custom_weights(monkeypatch):
     w = np.ones(10)
     vg.DirectionalVariogram(np.zeros((10, 3)), 1.0, 4.0, custom_weights=w, dir_neighbors_selection_method="e")
     assert len(seen) == 5 and all(s is w for s in seen)
-
-
-def test_directional_cloud_triangle_method_is_refused():
-    """The triangle-method point cloud is not built; the ellipse must not be substituted silently."""
-    from pyinterpolate_b200 import point_cloud_semivariance
-    pts = np.random.default_rng(0).uniform(0, 10, (30, 3))
-    with pytest.raises(NotImplementedError):
-        point_cloud_semivariance(pts, 1.0, 4.0, direction=45, tolerance=0.2)
