@@ -494,6 +494,10 @@ struct SolveParams {
     const int32_t *nbr_count;   // NULL, or [count] neighbours actually selected (<= kk; directional selection)
     int only_status;            // 0: every system; else only the (set, location) entries whose status byte equals it
     size_t mode_stride;         // PIB_KRIGE_BOTH: offset (in systems) of the simple-kriging block behind the ordinary one
+    int *singular_flag;         // NULL, or a device word set by every solver that marks a system PIB_STATUS_SINGULAR (singular_kernel
+                                // leaves at once while it is 0)
+    int *retry_flag;            // NULL, or a device word the Gauss-Jordan kernels set when they mark a system PIB_STATUS_RETRY:
+                                // the bordered pass behind them (only_status == PIB_STATUS_RETRY) leaves at once while it is 0
 };
 
 // per-warp shared memory: A[dim][stride] | rhs0[dim] | dinv[dim] | nx[kk] ny[kk] nd[kk] | npos[kk] (int)
@@ -509,6 +513,7 @@ __global__ void solve_kernel(const SolveParams p)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t slot = (int64_t)blockIdx.x * p.warps + warp;
     if (slot >= p.count) return;
+    if (p.only_status && p.retry_flag && *p.retry_flag == 0) return;            // nothing was marked for this pass
     const int kmax = p.kk, mode = p.mode;                       // shared-memory layout is sized for kmax neighbours
     const int dmax = (mode == PIB_KRIGE_ORDINARY) ? kmax + 1 : kmax;
     const int st = p.stride;
@@ -637,6 +642,7 @@ __global__ void solve_kernel(const SolveParams p)
             double *o = p.out + ((size_t)set * p.m + q) * 4;
             o[0] = zhat; o[1] = sigma; o[2] = ux; o[3] = uy;
             if (p.status) p.status[(size_t)set * p.m + q] = stat;
+            if (stat == PIB_STATUS_SINGULAR && p.singular_flag) *p.singular_flag = 1;
         }
         __syncwarp();
     }
@@ -703,9 +709,15 @@ __global__ void __launch_bounds__(solve_reg_threads<K>(), solve_reg_min_ctas<K>(
     const int sid = threadIdx.x / TPS, t = threadIdx.x % TPS, lane = threadIdx.x & 31, wis = t >> 5;
     const int64_t slot = (int64_t)blockIdx.x * SPC + sid;
     if (slot >= p.count) return;                   // whole systems leave together (barriers are per system)
+    if (p.only_status && p.retry_flag && *p.retry_flag == 0) return;            // nothing was marked for this pass
     RegSysSmem<K, ORD> &S = smem[sid];
     const GridIndex &g = p.g;
     const int32_t q = p.order[slot];
+    if (p.only_status) {                           // a pass over marked systems: leave before the neighbour gathers (uniform per system)
+        bool wanted = false;
+        for (int set = 0; set < p.n_sets; ++set) wanted |= p.status[(size_t)set * p.m + q] == p.only_status;
+        if (!wanted) return;
+    }
     const double ux = p.unknown[2 * (int64_t)q], uy = p.unknown[2 * (int64_t)q + 1];
     // neighbours of THIS location (<= p.kk <= K); a non-finite location has none (every candidate distance is NaN)
     const int kk = !(isfinite(ux) && isfinite(uy)) ? 0 : p.nbr_count ? p.nbr_count[slot] : p.kk;
@@ -905,6 +917,7 @@ __global__ void __launch_bounds__(solve_reg_threads<K>(), solve_reg_min_ctas<K>(
             double *o = p.out + ((size_t)set * p.m + q) * 4;
             o[0] = zhat; o[1] = sigma; o[2] = ux; o[3] = uy;
             if (p.status) p.status[(size_t)set * p.m + q] = stat;
+            if (stat == PIB_STATUS_SINGULAR && p.singular_flag) *p.singular_flag = 1;
         }
         sys_sync<TPS>(sid);
     }
@@ -1000,6 +1013,7 @@ __global__ void __launch_bounds__(gj_threads<K>(), K == 32 ? 2 : 1) solve_gj_ker
             for (int set = 0; set < p.n_sets; ++set) {
                 if (WANT_OK) p.status[(size_t)set * p.m + q] = PIB_STATUS_RETRY;
                 if (WANT_SK) p.status[sk_off + (size_t)set * p.m + q] = PIB_STATUS_RETRY;
+                if (p.retry_flag) *p.retry_flag = 1;
             }
         return;
     }
@@ -1157,7 +1171,10 @@ __global__ void __launch_bounds__(gj_threads<K>(), K == 32 ? 2 : 1) solve_gj_ker
                 uint8_t stat = PIB_STATUS_SINGULAR;
                 if (!dup) {
                     const double mu = (s[0] - 1.0) / s[1];
-                    if (singular || !(fabs(s[1]) > 0.0) || !isfinite(mu)) stat = PIB_STATUS_RETRY;       // decide on the bordered matrix
+                    if (singular || !(fabs(s[1]) > 0.0) || !isfinite(mu)) {                             // decide on the bordered matrix
+                        stat = PIB_STATUS_RETRY;
+                        if (p.retry_flag) *p.retry_flag = 1;
+                    }
                     else {
                         zhat = s[2] - mu * s[3];
                         sigma = (s[4] - mu * s[5]) + mu;
@@ -1168,6 +1185,7 @@ __global__ void __launch_bounds__(gj_threads<K>(), K == 32 ? 2 : 1) solve_gj_ker
                 double *o = p.out + ((size_t)set * p.m + q) * 4;
                 o[0] = zhat; o[1] = sigma; o[2] = ux; o[3] = uy;
                 p.status[(size_t)set * p.m + q] = stat;
+                if (stat == PIB_STATUS_SINGULAR && p.singular_flag) *p.singular_flag = 1;
             }
             if (WANT_SK) {
                 // w = u:  zhat = (z - mean).w + mean (simple.py:114-116), sigma^2 = w.g0 (:118)
@@ -1182,6 +1200,7 @@ __global__ void __launch_bounds__(gj_threads<K>(), K == 32 ? 2 : 1) solve_gj_ker
                 double *o = p.out + (sk_off + (size_t)set * p.m + q) * 4;
                 o[0] = zhat; o[1] = sigma; o[2] = ux; o[3] = uy;
                 p.status[sk_off + (size_t)set * p.m + q] = stat;
+                if (stat == PIB_STATUS_SINGULAR && p.singular_flag) *p.singular_flag = 1;
             }
         }
         sys_sync<TPS>(sid);
@@ -1199,6 +1218,280 @@ static int launch_solve_gj_m(const SolveParams &sp, cudaStream_t stream)
     solve_gj_kernel<K, MODE><<<grid, NT, bytes, stream>>>(sp);
     PIB_CUDA(cudaGetLastError());
     return PIB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// solve_gj2_kernel (k <= 32, the default there): the same Gauss-Jordan recurrence with TWO ROWS PER THREAD, so a system
+// takes K / 2 lanes and a warp carries 2 (K = 32), 4 (K = 16) or 8 (K = 8) systems in lockstep.  solve_gj_kernel<32> spends
+// ~110 warp instructions per elimination step of ONE system, only ~16 of them DFMAs (ncu: the pivot search, the reciprocal,
+// the single-lane publication of the pivot row and its read-back are per step, not per row); here those instructions serve
+// two rows per lane and several systems per warp, every pivot-row value read from shared memory feeds two DFMAs, and
+// nothing crosses a warp (no named barriers).  Pivot rule, arithmetic per row and the outputs are those of
+// solve_gj_kernel; only the order of the final dot-product reduction differs (fp64 rounding).
+// Lanes never leave early (the pivot search is a warp-wide butterfly): systems beyond the batch, systems with fewer than
+// two neighbours, duplicated neighbours and systems that met a zero pivot ride along masked.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__host__ __device__ constexpr int gj2_threads() { return 64; }
+template <int K>
+__host__ __device__ constexpr int gj2_min_ctas() { return K == 32 ? 5 : 8; }
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(gj2_threads<K>(), gj2_min_ctas<K>()) solve_gj2_kernel(const SolveParams p)
+{
+    constexpr int TPS = K / 2;                    // lanes per system: lane t owns rows t and t + TPS
+    constexpr int SPC = gj2_threads<K>() / TPS;   // systems per CTA
+    constexpr int CS = GjSmem<K>::CS;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr bool WANT_OK = MODE != PIB_KRIGE_SIMPLE, WANT_SK = MODE != PIB_KRIGE_ORDINARY;
+    static_assert(K == 8 || K == 16 || K == 32, "two rows per thread: 4, 8 or 16 lanes per system");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GjSmem<K> *smem = reinterpret_cast<GjSmem<K> *>(smem_raw);
+    const int sid = threadIdx.x / TPS, t = threadIdx.x % TPS, lane = threadIdx.x & 31;
+    const unsigned seg = ((1u << TPS) - 1u) << (lane & ~(TPS - 1));             // the lanes of my system
+    const int64_t slot_raw = (int64_t)blockIdx.x * SPC + sid;
+    const int64_t slot = min(slot_raw, p.count - 1);                            // (systems beyond the batch redo the last one, unstored)
+    GjSmem<K> &S = smem[sid];
+    const GridIndex &g = p.g;
+    const int32_t q = p.order[slot];
+    const double ux = p.unknown[2 * (int64_t)q], uy = p.unknown[2 * (int64_t)q + 1];
+    const int kk = !(isfinite(ux) && isfinite(uy)) ? 0 : p.nbr_count ? p.nbr_count[slot] : p.kk;
+    const size_t sk_off = MODE == PIB_KRIGE_BOTH ? p.mode_stride : 0;
+    const bool store = slot_raw < p.count && kk > 1;
+    if (slot_raw < p.count && kk <= 1 && t == 0) {
+        // 0 / -1: no (too many) neighbours; 1: Gamma = [gamma(0)] may be singular although the bordered matrix is not
+        for (int set = 0; set < p.n_sets; ++set) {
+            if (WANT_OK) p.status[(size_t)set * p.m + q] = PIB_STATUS_RETRY;
+            if (WANT_SK) p.status[sk_off + (size_t)set * p.m + q] = PIB_STATUS_RETRY;
+        }
+        if (p.retry_flag) *p.retry_flag = 1;
+    }
+    int my_pos[2];
+    double my_d[2];
+    double2 me[2];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int r = t + rr * TPS;
+        my_pos[rr] = -1; my_d[rr] = 0.0;
+        me[rr] = make_double2(0.0, 0.0);
+        if (r < kk) {
+            my_pos[rr] = p.nbr_pos[slot * p.kk + r];
+            PIB_DBG_ASSERT(my_pos[rr] >= 0 && my_pos[rr] < g.n);
+            my_d[rr] = p.nbr_d[slot * p.kk + r];
+            me[rr] = make_double2(g.x[my_pos[rr]], g.y[my_pos[rr]]);
+        }
+        S.nxy[r] = me[rr];
+    }
+    if (t == 0) S.dup = 0;
+    __syncwarp();
+
+    for (int set = 0; set < p.n_sets; ++set) {
+        const double nugget = p.params[3 * set], sill = p.params[3 * set + 1], rang = p.params[3 * set + 2];
+        // ---- Gamma, every entry evaluated once: row r takes the columns r + 1 .. r + K / 2 cyclically, both halves written ----
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = t + rr * TPS;
+            constexpr int AU = 4;
+#pragma unroll 1
+            for (int i0 = 0; i0 < K / 2; i0 += AU) {
+                int cc[AU];
+                double hh[AU], vv[AU];
+#pragma unroll
+                for (int u = 0; u < AU; ++u) {
+                    int c = r + 1 + i0 + u;
+                    if (c >= K) c -= K;
+                    cc[u] = c;
+                    const double2 o = S.nxy[c];
+                    const double dx = __dsub_rn(me[rr].x, o.x), dy = __dsub_rn(me[rr].y, o.y);
+                    hh[u] = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                }
+#pragma unroll
+                for (int u = 0; u < AU; ++u) {
+                    const bool real = (r < kk && cc[u] < kk);
+                    if (real && hh[u] == 0.0) S.dup = 1;
+                    vv[u] = real ? gamma_model(p.model, hh[u], nugget, sill, rang) : 0.0;       // identity padding (off diagonal)
+                }
+#pragma unroll
+                for (int u = 0; u < AU; ++u) {
+                    S.G[r * (K + 2) + cc[u]] = vv[u];
+                    S.G[cc[u] * (K + 2) + r] = vv[u];
+                }
+            }
+            S.G[r * (K + 2) + r] = (r < kk) ? nugget : 1.0;                     // gamma(0) / identity padding
+            S.g0[r] = (r < kk) ? gamma_model(p.model, my_d[rr], nugget, sill, rang) : 0.0;
+            double zv = 0.0;
+            if (r < kk) zv = p.values ? p.values[(size_t)set * p.n + g.orig[my_pos[rr]]] : g.z[my_pos[rr]];
+            S.zv[r] = zv;
+        }
+        __syncwarp();
+        double a[2][K], r0[2], r1[2], my_inv[2];
+        int my_step[2];
+        bool active[2];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = t + rr * TPS;
+#pragma unroll
+            for (int c = 0; c < K; c += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(&S.G[r * (K + 2) + c]);
+                a[rr][c] = v.x; a[rr][c + 1] = v.y;
+            }
+            r0[rr] = S.g0[r];                                                   // right-hand side g0
+            r1[rr] = (WANT_OK && r < kk) ? 1.0 : 0.0;                           // right-hand side 1 (ordinary kriging)
+            active[rr] = true; my_step[rr] = -1; my_inv[rr] = 0.0;
+        }
+        const bool dup = S.dup != 0;              // two identical rows: singular in exact arithmetic (see solve_gj_kernel)
+        bool singular = false;
+        __syncwarp();                                                           // G is dead: the candidate slots take its place
+        double *const cand = S.G;
+
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            // ---- pivot of column j: largest |a[j]| among my system's rows not yet used, lowest row on ties ----
+            const bool go = !(dup || singular);
+            const double av0 = fabs(a[0][j]), av1 = fabs(a[1][j]);
+            // |v| >= 0, so the fp64 order is the order of the bit pattern: high words first (inactive rows 0, NaN on top)
+            const unsigned hi0 = (go && active[0]) ? (unsigned)__double2hiint(av0) + 1u : 0u;
+            const unsigned hi1 = (go && active[1]) ? (unsigned)__double2hiint(av1) + 1u : 0u;
+            unsigned hmax = max(hi0, hi1);
+#pragma unroll
+            for (int o = TPS / 2; o; o >>= 1) hmax = max(hmax, __shfl_xor_sync(FULL, hmax, o));
+            unsigned lead0 = __ballot_sync(FULL, hi0 == hmax) & seg, lead1 = __ballot_sync(FULL, hi1 == hmax) & seg;
+            if (__any_sync(FULL, hmax != 0u && __popc(lead0) + __popc(lead1) > 1)) {      // rare: equal high words somewhere in the warp
+                const unsigned lo0 = (hi0 == hmax) ? (unsigned)__double2loint(av0) : 0u;
+                const unsigned lo1 = (hi1 == hmax) ? (unsigned)__double2loint(av1) : 0u;
+                unsigned lmax = max(lo0, lo1);
+#pragma unroll
+                for (int o = TPS / 2; o; o >>= 1) lmax = max(lmax, __shfl_xor_sync(FULL, lmax, o));
+                lead0 = __ballot_sync(FULL, hi0 == hmax && lo0 == lmax) & seg;
+                lead1 = __ballot_sync(FULL, hi1 == hmax && lo1 == lmax) & seg;
+            }
+            // rows t come before rows t + TPS
+            const int src = __ffs(lead0 ? lead0 : lead1) - 1;
+            double *const C = cand + (j & 1) * CS;
+            if (lane == src) {
+                if (lead0) {
+#pragma unroll
+                    for (int c = 0; c < K; ++c)
+                        if (c > j) C[c] = a[0][c];
+                    C[K] = r0[0]; C[K + 1] = r1[0];
+                    C[K + 2] = hmax ? av0 : -1.0;
+                    C[K + 3] = __drcp_rn(a[0][j]);                              // dgetf2 scales by the reciprocal of the pivot
+                    reinterpret_cast<int *>(C + K + 4)[0] = t;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < K; ++c)
+                        if (c > j) C[c] = a[1][c];
+                    C[K] = r0[1]; C[K + 1] = r1[1];
+                    C[K + 2] = hmax ? av1 : -1.0;
+                    C[K + 3] = __drcp_rn(a[1][j]);
+                    reinterpret_cast<int *>(C + K + 4)[0] = t + TPS;
+                }
+            }
+            __syncwarp();
+            const double pv = C[K + 2];
+            if (go && (!(pv > 0.0) || isinf(pv))) singular = true;              // zero / NaN pivot column (uniform over the system)
+            if (go && !singular) {
+                const double inv = C[K + 3];
+                const int prow = reinterpret_cast<const int *>(C + K + 4)[0];
+                const bool is_p0 = (prow == t), is_p1 = (prow == t + TPS);
+                if (is_p0) { active[0] = false; my_step[0] = j; my_inv[0] = inv; }
+                if (is_p1) { active[1] = false; my_step[1] = j; my_inv[1] = inv; }
+                // Gauss-Jordan: EVERY other row eliminates column j, the rows already used included
+                const double l0 = is_p0 ? 0.0 : a[0][j] * inv, l1 = is_p1 ? 0.0 : a[1][j] * inv;
+#pragma unroll
+                for (int c = 0; c < K; ++c)
+                    if (c > j) {
+                        const double pc = C[c];
+                        a[0][c] = __fma_rn(-l0, pc, a[0][c]);
+                        a[1][c] = __fma_rn(-l1, pc, a[1][c]);
+                    }
+                const double p0 = C[K];
+                r0[0] = __fma_rn(-l0, p0, r0[0]);
+                r0[1] = __fma_rn(-l1, p0, r0[1]);
+                if (WANT_OK) {
+                    const double p1 = C[K + 1];
+                    r1[0] = __fma_rn(-l0, p1, r1[0]);
+                    r1[1] = __fma_rn(-l1, p1, r1[1]);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- solution: a row that was the pivot of column s gives u[s] = r0 / pivot, v[s] = r1 / pivot ----
+        double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};       // 1^T u, 1^T v, u.z, v.z, u.g0, v.g0
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const bool real = (my_step[rr] >= 0 && my_step[rr] < kk);
+            const double u = real ? r0[rr] * my_inv[rr] : 0.0, v = real ? r1[rr] * my_inv[rr] : 0.0;
+            const double zn = real ? S.zv[my_step[rr]] : 0.0, gn = real ? S.g0[my_step[rr]] : 0.0;
+            s[0] += u; s[1] += v; s[2] += u * zn; s[3] += v * zn; s[4] += u * gn; s[5] += v * gn;
+        }
+#pragma unroll
+        for (int o = TPS / 2; o; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) s[i] += __shfl_xor_sync(FULL, s[i], o);
+        if (t == 0 && store) {
+            if (WANT_OK) {
+                // mu = (1^T u - 1) / (1^T v), w = u - mu v:  zhat = w.z (ordinary.py:121), sigma^2 = w.g0 + mu (:123)
+                double zhat = nan(""), sigma = nan("");
+                uint8_t stat = PIB_STATUS_SINGULAR;
+                if (!dup) {
+                    const double mu = (s[0] - 1.0) / s[1];
+                    if (singular || !(fabs(s[1]) > 0.0) || !isfinite(mu)) {                             // decide on the bordered matrix
+                        stat = PIB_STATUS_RETRY;
+                        if (p.retry_flag) *p.retry_flag = 1;
+                    }
+                    else {
+                        zhat = s[2] - mu * s[3];
+                        sigma = (s[4] - mu * s[5]) + mu;
+                        stat = PIB_STATUS_OK;
+                        if (sigma < 0.0) { sigma = nan(""); stat = PIB_STATUS_NEGATIVE_VARIANCE; }       // ordinary.py:125-126
+                    }
+                }
+                double *o = p.out + ((size_t)set * p.m + q) * 4;
+                o[0] = zhat; o[1] = sigma; o[2] = ux; o[3] = uy;
+                p.status[(size_t)set * p.m + q] = stat;
+                if (stat == PIB_STATUS_SINGULAR && p.singular_flag) *p.singular_flag = 1;
+            }
+            if (WANT_SK) {
+                // w = u:  zhat = (z - mean).w + mean (simple.py:114-116), sigma^2 = w.g0 (:118)
+                double zhat = nan(""), sigma = nan("");
+                uint8_t stat = PIB_STATUS_SINGULAR;
+                if (!dup && !singular) {
+                    zhat = (s[2] - p.process_mean * s[0]) + p.process_mean;
+                    sigma = s[4];
+                    stat = PIB_STATUS_OK;
+                    if (sigma < 0.0) { sigma = nan(""); stat = PIB_STATUS_NEGATIVE_VARIANCE; }
+                }
+                double *o = p.out + (sk_off + (size_t)set * p.m + q) * 4;
+                o[0] = zhat; o[1] = sigma; o[2] = ux; o[3] = uy;
+                p.status[sk_off + (size_t)set * p.m + q] = stat;
+                if (stat == PIB_STATUS_SINGULAR && p.singular_flag) *p.singular_flag = 1;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int K, int MODE>
+static int launch_solve_gj2_m(const SolveParams &sp, cudaStream_t stream)
+{
+    constexpr int NT = gj2_threads<K>();
+    constexpr int SPC = NT / (K / 2);
+    const int grid = (int)((sp.count + SPC - 1) / SPC);
+    const size_t bytes = sizeof(GjSmem<K>) * SPC;
+    PIB_CUDA(cudaFuncSetAttribute(solve_gj2_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    solve_gj2_kernel<K, MODE><<<grid, NT, bytes, stream>>>(sp);
+    PIB_CUDA(cudaGetLastError());
+    return PIB_OK;
+}
+
+template <int K>
+static int launch_solve_gj2(const SolveParams &sp, int mode, cudaStream_t stream)
+{
+    if (mode == PIB_KRIGE_ORDINARY) return launch_solve_gj2_m<K, PIB_KRIGE_ORDINARY>(sp, stream);
+    if (mode == PIB_KRIGE_SIMPLE) return launch_solve_gj2_m<K, PIB_KRIGE_SIMPLE>(sp, stream);
+    return launch_solve_gj2_m<K, PIB_KRIGE_BOTH>(sp, stream);
 }
 
 template <int K>
@@ -1301,6 +1594,7 @@ __global__ void __launch_bounds__(32) singular_kernel(const SingularParams sp)
     int32_t *npos = reinterpret_cast<int32_t *>(nd + kmax);
     const GridIndex &g = p.g;
 
+    if (p.singular_flag && *p.singular_flag == 0) return;                       // no solver marked a system singular
     for (int64_t base = (int64_t)blockIdx.x * 32; base < p.count; base += (int64_t)gridDim.x * 32) {
         const int64_t mine = base + lane;
         bool hit = false;
@@ -1493,6 +1787,8 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
     if (!v_in_smem) PIB_TRY(ws.alloc(&vglobal, (size_t)sing_grid * dim * stride));
     PIB_CUDA(cudaFuncSetAttribute(singular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sing_smem));
 
+    int *d_retry_flag = nullptr;                    // [0] systems marked PIB_STATUS_RETRY, [1] systems marked PIB_STATUS_SINGULAR
+    PIB_TRY(ws.alloc(&d_retry_flag, 2));
     for (int64_t begin = 0; begin < m; begin += chunk) {
         const int64_t count = std::min(chunk, m - begin);
         KnnParams kp;
@@ -1523,6 +1819,9 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
         sp.model = model; sp.mode = mode; sp.process_mean = process_mean; sp.out = d_out; sp.status = d_status;
         sp.warps = solve_warps; sp.stride = stride; sp.nbr_count = nbr_count;
         sp.only_status = 0; sp.mode_stride = mode_stride;
+        sp.retry_flag = use_gj ? d_retry_flag : nullptr;
+        sp.singular_flag = d_retry_flag + 1;
+        PIB_CUDA(cudaMemsetAsync(d_retry_flag, 0, 2 * sizeof(int), stream));
         timing_begin(PIB_T_SOLVE, stream);
         int rc = PIB_OK;
         // the round-1 solvers on the bordered matrix, one kriging mode at a time (`only` = just the flagged systems)
@@ -1539,12 +1838,20 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
             if (cudaGetLastError() != cudaSuccess) { set_error("solve_kernel launch failed"); return PIB_ERR_CUDA; }
             return PIB_OK;
         };
-        set_kernel_name(PIB_T_SOLVE, use_gj ? "solve_gj_kernel" : use_reg ? "solve_reg_kernel" : "solve_kernel");
-        if (use_gj) {
+        const char *gj2_env = std::getenv("PIB_GJ2");                    // "0": one row per thread for k <= 16 as well; "1": two rows up to k = 32
+        const bool use_gj2 = use_gj && (kk <= 16 || (kk <= 32 && gj2_env && gj2_env[0] == '1')) && !(gj2_env && gj2_env[0] == '0');
+        set_kernel_name(PIB_T_SOLVE, use_gj2 ? "solve_gj2_kernel" : use_gj ? "solve_gj_kernel" : use_reg ? "solve_reg_kernel" : "solve_kernel");
+        if (use_gj2) {
+            if (kk <= 8) rc = launch_solve_gj2<8>(sp, mode, stream);
+            else if (kk <= 16) rc = launch_solve_gj2<16>(sp, mode, stream);
+            else rc = launch_solve_gj2<32>(sp, mode, stream);
+        } else if (use_gj) {
             if (kk <= 8) rc = launch_solve_gj<8>(sp, mode, stream);
             else if (kk <= 16) rc = launch_solve_gj<16>(sp, mode, stream);
             else if (kk <= 32) rc = launch_solve_gj<32>(sp, mode, stream);
             else rc = launch_solve_gj<64>(sp, mode, stream);
+        }
+        if (use_gj) {
             // systems Gauss-Jordan on Gamma could not decide (marked PIB_STATUS_RETRY): bordered LU; returns at once otherwise
             if (rc == PIB_OK && mode != PIB_KRIGE_SIMPLE) rc = bordered(PIB_KRIGE_ORDINARY, PIB_STATUS_RETRY);
             if (rc == PIB_OK && mode != PIB_KRIGE_ORDINARY) rc = bordered(PIB_KRIGE_SIMPLE, PIB_STATUS_RETRY);
