@@ -440,10 +440,28 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_dir_kernel(const KnnParams
 // gamma(h): semivariogram/theoretical/variogram_models/models.py:41-440 (sill = partial sill).
 // h == 0 gives the nugget for every model (what _get_zero_lag_value + the formulas evaluate to).
 // ---------------------------------------------------------------------------------------------
-static __device__ __forceinline__ double gamma_model(int model, double h, double nugget, double sill, double rang)
+// a / b with y = RN(1 / b) at hand: Markstein's correction step, q' = RN(q + (a - b q) y) with q = RN(a y) and the residual
+// exact in an FMA, IS the correctly rounded quotient (3 instructions instead of the ~25 of a full fp64 division; compared
+// with a / b on 2e8 random pairs: no difference).  y == 0 asks for the plain division (parameters near the ends of the
+// exponent range, where y or the residual would over- / underflow).
+static __device__ __forceinline__ double div_by(double a, double b, double y)
+{
+    if (y == 0.0) return a / b;
+    const double q = __dmul_rn(a, y);
+    return __fma_rn(__fma_rn(-q, b, a), y, q);
+}
+// the reciprocal div_by may use for a divisor b, or 0
+static __device__ __forceinline__ double safe_rcp(double b)
+{
+    return (fabs(b) > 1e-100 && fabs(b) < 1e100) ? __drcp_rn(b) : 0.0;
+}
+
+// rinv = safe_rcp(rang), rinv2 = safe_rcp(rang * rang) (or 0, 0): the quotients h / rang and (h h) / (rang rang) are the same bits either way
+static __device__ __forceinline__ double gamma_model(int model, double h, double nugget, double sill, double rang,
+                                                     double rinv = 0.0, double rinv2 = 0.0)
 {
     if (h == 0.0) return nugget;
-    const double ar = h / rang;
+    const double ar = div_by(h, rang, rinv);
     switch (model) {
     case PIB_MODEL_CIRCULAR: {
         if (!(h <= rang)) return nugget + sill;
@@ -456,7 +474,7 @@ static __device__ __forceinline__ double gamma_model(int model, double h, double
         return nugget + sill * (a2 * 7.0 + a3 * -8.75 + a5 * 3.5 + a7 * -0.75);
     }
     case PIB_MODEL_EXPONENTIAL: return nugget + sill * (1.0 - exp(-ar));
-    case PIB_MODEL_GAUSSIAN: return nugget + sill * (1.0 - exp(-((h * h) / (rang * rang))));
+    case PIB_MODEL_GAUSSIAN: return nugget + sill * (1.0 - exp(-div_by(h * h, rang * rang, rinv2)));
     case PIB_MODEL_LINEAR: return (h <= rang) ? nugget + sill * ar : nugget + sill;
     case PIB_MODEL_POWER: return (h <= rang) ? nugget + sill * (ar * ar) : nugget + sill;
     case PIB_MODEL_SPHERICAL: {
@@ -494,6 +512,7 @@ struct SolveParams {
     const int32_t *nbr_count;   // NULL, or [count] neighbours actually selected (<= kk; directional selection)
     int only_status;            // 0: every system; else only the (set, location) entries whose status byte equals it
     size_t mode_stride;         // PIB_KRIGE_BOTH: offset (in systems) of the simple-kriging block behind the ordinary one
+    int fast_div;               // 1: quotients by the model range through div_by (same bits, 3 instructions); 0 (PIB_FAST_DIV=0): plain divisions
     int *singular_flag;         // NULL, or a device word set by every solver that marks a system PIB_STATUS_SINGULAR (singular_kernel
                                 // leaves at once while it is 0)
     int *retry_flag;            // NULL, or a device word the Gauss-Jordan kernels set when they mark a system PIB_STATUS_RETRY:
@@ -1033,6 +1052,7 @@ __global__ void __launch_bounds__(gj_threads<K>(), K == 32 ? 2 : 1) solve_gj_ker
 
     for (int set = 0; set < p.n_sets; ++set) {
         const double nugget = p.params[3 * set], sill = p.params[3 * set + 1], rang = p.params[3 * set + 2];
+        const double rinv = p.fast_div ? safe_rcp(rang) : 0.0, rinv2 = p.fast_div ? safe_rcp(rang * rang) : 0.0;
         // ---- Gamma, every entry evaluated once: thread t takes (t, t+1 .. t+K/2) cyclically and writes both halves.
         // Four entries per iteration: one evaluation is a chain of ~100 dependent instructions (sqrt, division, model) ----
         if (t < K) {
@@ -1054,7 +1074,7 @@ __global__ void __launch_bounds__(gj_threads<K>(), K == 32 ? 2 : 1) solve_gj_ker
                 for (int u = 0; u < AU; ++u) {
                     const bool real = (t < kk && cc[u] < kk);
                     if (real && hh[u] == 0.0) S.dup = 1;
-                    vv[u] = real ? gamma_model(p.model, hh[u], nugget, sill, rang) : 0.0;       // identity padding (off diagonal)
+                    vv[u] = real ? gamma_model(p.model, hh[u], nugget, sill, rang, rinv, rinv2) : 0.0;       // identity padding (off diagonal)
                 }
 #pragma unroll
                 for (int u = 0; u < AU; ++u) {
@@ -1063,7 +1083,7 @@ __global__ void __launch_bounds__(gj_threads<K>(), K == 32 ? 2 : 1) solve_gj_ker
                 }
             }
             S.G[t * (K + 2) + t] = (t < kk) ? nugget : 1.0;                     // gamma(0) / identity padding
-            const double kv = (t < kk) ? gamma_model(p.model, my_d, nugget, sill, rang) : 0.0;
+            const double kv = (t < kk) ? gamma_model(p.model, my_d, nugget, sill, rang, rinv, rinv2) : 0.0;
             S.g0[t] = kv;
             double zv = 0.0;
             if (t < kk) zv = p.values ? p.values[(size_t)set * p.n + g.orig[my_pos]] : g.z[my_pos];
@@ -1231,10 +1251,16 @@ static int launch_solve_gj_m(const SolveParams &sp, cudaStream_t stream)
 // Lanes never leave early (the pivot search is a warp-wide butterfly): systems beyond the batch, systems with fewer than
 // two neighbours, duplicated neighbours and systems that met a zero pivot ride along masked.
 // ---------------------------------------------------------------------------------------------
+#ifndef PIB_GJ2_32_THREADS
+#define PIB_GJ2_32_THREADS 64
+#endif
+#ifndef PIB_GJ2_32_CTAS
+#define PIB_GJ2_32_CTAS 5
+#endif
 template <int K>
-__host__ __device__ constexpr int gj2_threads() { return 64; }
+__host__ __device__ constexpr int gj2_threads() { return K == 32 ? PIB_GJ2_32_THREADS : 64; }
 template <int K>
-__host__ __device__ constexpr int gj2_min_ctas() { return K == 32 ? 5 : 8; }
+__host__ __device__ constexpr int gj2_min_ctas() { return K == 32 ? PIB_GJ2_32_CTAS : 8; }
 
 template <int K, int MODE>
 __global__ void __launch_bounds__(gj2_threads<K>(), gj2_min_ctas<K>()) solve_gj2_kernel(const SolveParams p)
@@ -1287,6 +1313,7 @@ __global__ void __launch_bounds__(gj2_threads<K>(), gj2_min_ctas<K>()) solve_gj2
 
     for (int set = 0; set < p.n_sets; ++set) {
         const double nugget = p.params[3 * set], sill = p.params[3 * set + 1], rang = p.params[3 * set + 2];
+        const double rinv = p.fast_div ? safe_rcp(rang) : 0.0, rinv2 = p.fast_div ? safe_rcp(rang * rang) : 0.0;
         // ---- Gamma, every entry evaluated once: row r takes the columns r + 1 .. r + K / 2 cyclically, both halves written ----
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
@@ -1309,7 +1336,7 @@ __global__ void __launch_bounds__(gj2_threads<K>(), gj2_min_ctas<K>()) solve_gj2
                 for (int u = 0; u < AU; ++u) {
                     const bool real = (r < kk && cc[u] < kk);
                     if (real && hh[u] == 0.0) S.dup = 1;
-                    vv[u] = real ? gamma_model(p.model, hh[u], nugget, sill, rang) : 0.0;       // identity padding (off diagonal)
+                    vv[u] = real ? gamma_model(p.model, hh[u], nugget, sill, rang, rinv, rinv2) : 0.0;       // identity padding (off diagonal)
                 }
 #pragma unroll
                 for (int u = 0; u < AU; ++u) {
@@ -1318,7 +1345,7 @@ __global__ void __launch_bounds__(gj2_threads<K>(), gj2_min_ctas<K>()) solve_gj2
                 }
             }
             S.G[r * (K + 2) + r] = (r < kk) ? nugget : 1.0;                     // gamma(0) / identity padding
-            S.g0[r] = (r < kk) ? gamma_model(p.model, my_d[rr], nugget, sill, rang) : 0.0;
+            S.g0[r] = (r < kk) ? gamma_model(p.model, my_d[rr], nugget, sill, rang, rinv, rinv2) : 0.0;
             double zv = 0.0;
             if (r < kk) zv = p.values ? p.values[(size_t)set * p.n + g.orig[my_pos[rr]]] : g.z[my_pos[rr]];
             S.zv[r] = zv;
@@ -1821,6 +1848,7 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
         sp.only_status = 0; sp.mode_stride = mode_stride;
         sp.retry_flag = use_gj ? d_retry_flag : nullptr;
         sp.singular_flag = d_retry_flag + 1;
+        { const char *fd = std::getenv("PIB_FAST_DIV"); sp.fast_div = !(fd && fd[0] == '0'); }
         PIB_CUDA(cudaMemsetAsync(d_retry_flag, 0, 2 * sizeof(int), stream));
         timing_begin(PIB_T_SOLVE, stream);
         int rc = PIB_OK;
