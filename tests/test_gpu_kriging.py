@@ -137,6 +137,37 @@ def test_vs_oracle_1m_known(pib, oracle, k, model):
     np.testing.assert_allclose(sk[:, :2], ref_sk[:, :2], rtol=RTOL)
 
 
+@pytest.mark.parametrize("k,model,nug,rang", [(5, "circular", 0.0, 15000.0), (8, "cubic", 0.5, 15000.0), (12, "gaussian", 1.0, 1500.0),
+                                              (16, "exponential", 0.0, 15000.0), (16, "spherical", 1.0, 15000.0),
+                                              (24, "linear", 0.0, 15000.0), (32, "spherical", 1.0, 15000.0)])
+def test_two_row_solver_vs_oracle_and_one_row_solver(pib, oracle, monkeypatch, k, model, nug, rang):
+    """solve_gj2_kernel (two rows per thread, 2 - 8 systems per warp; the default up to k = 16, PIB_GJ2=1 up to 32) against the
+    oracle and against solve_gj_kernel (PIB_GJ2=0): same pivot sequence, so the outputs agree to the last reduction.  The
+    known points hold DUPLICATED coordinates, so singular systems (every lane of theirs masked) share warps with regular ones;
+    a location count that is not a multiple of the systems per CTA leaves masked systems at the end of the batch."""
+    from pyinterpolate_b200 import _lib
+    known = dem_like_field(20_000, seed=31)
+    known[5000:5040, :2] = known[100:140, :2]                # 40 duplicated coordinates
+    unk = np.concatenate([uniform_locations(1501, seed=32), known[100:140, :2] + 1.0])
+    var, mean = float(np.var(known[:, 2])), float(known[:, 2].mean())
+    params = np.array([[nug, var, rang]])
+    res = {}
+    for ver in ("1", "0"):
+        monkeypatch.setenv("PIB_GJ2", ver)
+        res[ver] = _lib.krige_host(known, unk, _lib.MODEL_IDS[model], params, _lib.KRIGE_BOTH, k, process_mean=mean)
+        assert _lib.last_kernel_name(_lib.KERNEL_SOLVE) == ("solve_gj2_kernel" if ver == "1" else "solve_gj_kernel")
+    (o1, _, s1), (o0, _, s0) = res["1"], res["0"]
+    np.testing.assert_array_equal(s1, s0)
+    assert (s1 == 1).any() and (s1 == 0).any()                # singular and regular systems side by side
+    np.testing.assert_allclose(o1, o0, rtol=1e-12, equal_nan=True)
+    for mi, mode in enumerate(("ok", "sk")):
+        ref, _, rst = oracle.krige(known, unk, model, nug, var, rang, k, mode, process_mean=mean)
+        fine = (rst == 0) & (s1[mi, 0] == 0)
+        assert fine.sum() > 1400
+        np.testing.assert_array_equal(s1[mi, 0] == 1, rst == 1)
+        np.testing.assert_allclose(o1[mi, 0][fine, :2], ref[fine, :2], rtol=RTOL)
+
+
 def test_clustered_and_outside_locations(pib, oracle):
     """Strongly non-uniform density and locations far outside the data's bounding box."""
     rng = np.random.default_rng(3)
