@@ -199,34 +199,46 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const KnnParams p)
                     if (c[b].orig == ex) c[b] = cand_inf();
                 }
             }
-            // bitonic sort of the 32 * E candidates; element index = lane * E + b
+            // bitonic sort of the 32 * E candidates; element index = lane * E + b.  Branch-free compare-exchanges: the
+            // comparison is three predicates combined without short-circuit evaluation and the exchange is field-wise selects
+            // (written as `if (less(o, c)) c = o` with || and && it compiled to ~26 instructions per exchange, two of them
+            // branches; the direction of a shuffle stage depends on the lane alone, so it is formed once per stage).
+            auto less_nb = [](const Cand &a, const Cand &b) -> bool {
+                const bool lt = a.d < b.d, eq = a.d == b.d, ol = a.orig < b.orig;
+                return lt | (eq & ol);
+            };
 #pragma unroll
             for (int size = 2; size <= 32 * E; size <<= 1) {
 #pragma unroll
                 for (int stride = size >> 1; stride > 0; stride >>= 1) {
                     if (stride >= E) {                        // partner lives in another lane
                         const int lane_stride = stride / E;
+                        // ascending block (bit `size` of the element index clear) and lower element of the pair (bit `stride` clear):
+                        // both bits lie in the lane part of the index
+                        const bool up = size >= 32 * E ? true : ((lane & (size / E)) == 0);
+                        const bool want_small = (((lane & lane_stride) == 0) == up);
 #pragma unroll
                         for (int b = 0; b < E; ++b) {
-                            const int idx = lane * E + b;
-                            const bool up = ((idx & size) == 0), lower = ((idx & stride) == 0);
                             Cand o;
                             o.d = __shfl_xor_sync(0xffffffffu, c[b].d, lane_stride);
                             o.orig = __shfl_xor_sync(0xffffffffu, c[b].orig, lane_stride);
                             o.pos = __shfl_xor_sync(0xffffffffu, c[b].pos, lane_stride);
                             // keep the smaller one if I am the lower element of an ascending pair (or the upper of a descending one)
-                            const bool want_small = (lower == up);
-                            const bool o_less = cand_less(o, c[b]);
-                            if (o_less == want_small) c[b] = o;
+                            const bool take = (less_nb(o, c[b]) == want_small);
+                            c[b].d = take ? o.d : c[b].d;
+                            c[b].orig = take ? o.orig : c[b].orig;
+                            c[b].pos = take ? o.pos : c[b].pos;
                         }
                     } else {                                  // both elements are mine
 #pragma unroll
                         for (int b = 0; b < E; ++b) {
                             if ((b & stride) == 0) {
-                                const int idx = lane * E + b;
-                                const bool up = ((idx & size) == 0);
-                                const bool sw = cand_less(c[b + stride], c[b]) == up;
-                                if (sw) { const Cand t = c[b]; c[b] = c[b + stride]; c[b + stride] = t; }
+                                const bool up = size >= 32 * E ? true : size >= E ? ((lane & (size / E)) == 0) : ((b & size) == 0);
+                                const Cand lo = c[b], hi = c[b + stride];
+                                const bool sw = (less_nb(hi, lo) == up);
+                                c[b].d = sw ? hi.d : lo.d; c[b].orig = sw ? hi.orig : lo.orig; c[b].pos = sw ? hi.pos : lo.pos;
+                                c[b + stride].d = sw ? lo.d : hi.d; c[b + stride].orig = sw ? lo.orig : hi.orig;
+                                c[b + stride].pos = sw ? lo.pos : hi.pos;
                             }
                         }
                     }
