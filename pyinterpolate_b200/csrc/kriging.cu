@@ -1011,6 +1011,9 @@ struct GjSmem {
     int dup;
 };
 
+#ifndef PIB_GJ_LOOKAHEAD
+#define PIB_GJ_LOOKAHEAD 1
+#endif
 #ifndef PIB_GJ64_THREADS
 #define PIB_GJ64_THREADS 384
 #endif
@@ -1121,13 +1124,24 @@ __global__ void __launch_bounds__(gj_threads<K>(), K == 32 ? 2 : 1) solve_gj_ker
         double *const cand = S.G;
 
         if (!dup) {
+            // Look-ahead: the search key of column j + 1 (and the reciprocal every row would publish as the pivot's) is formed as
+            // soon as step j has updated that one column, AHEAD of the step's other K - j - 2 columns, so the warp reduction
+            // and the reciprocal's dependent chain run in the shadow of the trailing update instead of heading the next step
+            // (PIB_GJ_LOOKAHEAD=0 builds the plain order)
+            // |v| >= 0, so the fp64 order is the order of the bit pattern: high words first (inactive rows 0, NaN on top)
+            double av = fabs(a[0]);
+            unsigned hi = active ? (unsigned)__double2hiint(av) + 1u : 0u;
+            unsigned hmax = __reduce_max_sync(0xffffffffu, hi);
+            double inv_own = __drcp_rn(a[0]);                                   // dgetf2 scales by the reciprocal of the pivot
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 // ---- my warp's candidate for column j: largest |a[j]| among its rows not yet used, lowest row on ties ----
-                const double av = fabs(a[j]);
-                // |v| >= 0, so the fp64 order is the order of the bit pattern: high words first (inactive rows 0, NaN on top)
-                const unsigned hi = active ? (unsigned)__double2hiint(av) + 1u : 0u;
-                const unsigned hmax = __reduce_max_sync(0xffffffffu, hi);
+                if (!PIB_GJ_LOOKAHEAD && j > 0) {
+                    av = fabs(a[j]);
+                    hi = active ? (unsigned)__double2hiint(av) + 1u : 0u;
+                    hmax = __reduce_max_sync(0xffffffffu, hi);
+                    inv_own = __drcp_rn(a[j]);
+                }
                 unsigned lead = __ballot_sync(0xffffffffu, hi == hmax);
                 if (__popc(lead) > 1 && hmax != 0u) {                           // rare: equal high words, look at the low words
                     const unsigned lo = (hi == hmax) ? (unsigned)__double2loint(av) : 0u;
@@ -1142,7 +1156,7 @@ __global__ void __launch_bounds__(gj_threads<K>(), K == 32 ? 2 : 1) solve_gj_ker
                         if (c > j) C[c] = a[c];
                     C[K] = r0; C[K + 1] = r1;
                     C[K + 2] = hmax ? av : -1.0;
-                    C[K + 3] = __drcp_rn(a[j]);                                 // dgetf2 scales by the reciprocal of the pivot
+                    C[K + 3] = inv_own;
                     reinterpret_cast<int *>(C + K + 4)[0] = t;
                 }
                 sys_sync<TPS>(sid);
@@ -1163,9 +1177,16 @@ __global__ void __launch_bounds__(gj_threads<K>(), K == 32 ? 2 : 1) solve_gj_ker
                 if (is_p) { active = false; my_step = j; my_inv = inv; }
                 // Gauss-Jordan: EVERY other row eliminates column j, the rows already used included
                 const double l = is_p ? 0.0 : a[j] * inv;
+                if (PIB_GJ_LOOKAHEAD && j + 1 < K) {
+                    a[j + 1] = __fma_rn(-l, P[j + 1], a[j + 1]);
+                    av = fabs(a[j + 1]);
+                    hi = active ? (unsigned)__double2hiint(av) + 1u : 0u;
+                    hmax = __reduce_max_sync(0xffffffffu, hi);
+                    inv_own = __drcp_rn(a[j + 1]);
+                }
 #pragma unroll
                 for (int c = 0; c < K; ++c)
-                    if (c > j) a[c] = __fma_rn(-l, P[c], a[c]);
+                    if (c > j + (PIB_GJ_LOOKAHEAD ? 1 : 0)) a[c] = __fma_rn(-l, P[c], a[c]);
                 r0 = __fma_rn(-l, P[K], r0);
                 if (WANT_OK) r1 = __fma_rn(-l, P[K + 1], r1);
             }
@@ -1795,6 +1816,7 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
     PIB_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * solve_warps)));
     const size_t knn_smem = (size_t)KNN_WARPS * 2 * k2 * sizeof(Cand);
     PIB_CUDA(cudaFuncSetAttribute(knn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem));
+    PIB_CUDA(cudaFuncSetAttribute(knn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem));
     PIB_CUDA(cudaFuncSetAttribute(knn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem));
     PIB_CUDA(cudaFuncSetAttribute(knn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem));
     const char *knn_env = std::getenv("PIB_KNN_FAST");
@@ -1844,6 +1866,8 @@ int krige_device(const double *d_known, int64_t n, const double *d_values, int n
             knn_dir_kernel<<<(int)((count + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, knn_smem, stream>>>(kp);
         } else if (directional)
             knn_dir_kernel<<<(int)((count + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, knn_smem, stream>>>(kp);
+        else if (knn_fast && kk <= 16 && r0 == 1)             // a 3 x 3 window (~36 points): 64 register slots are enough
+            knn_kernel<2><<<(int)((count + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, knn_smem, stream>>>(kp);
         else if (knn_fast && kk <= 40)
             knn_kernel<4><<<(int)((count + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, knn_smem, stream>>>(kp);
         else if (knn_fast && kk <= 96)
