@@ -250,3 +250,24 @@ def test_directional_variogram_passes_custom_weights(monkeypatch):
     w = np.ones(10)
     vg.DirectionalVariogram(np.zeros((10, 3)), 1.0, 4.0, custom_weights=w, dir_neighbors_selection_method="e")
     assert len(seen) == 5 and all(s is w for s in seen)
+
+
+def test_torch_ops_are_registered_and_have_no_cpu_kernel():
+    """torch.ops.pyinterpolate_b200.* (pyinterpolate_b200/torch_ops.py): schemas, output shapes of the fake kernels, and no CPU
+    implementation behind them."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from pyinterpolate_b200 import _lib, torch_ops
+    torch_ops.register()
+    torch_ops.register()
+    with pytest.raises(NotImplementedError):
+        torch.ops.pyinterpolate_b200.variogram_sums(torch.zeros(4, 3, dtype=torch.float64), torch.tensor([1.0, 2.0], dtype=torch.float64),
+                                                    torch_ops.empty_f64(), torch_ops.empty_f64(), 0, 1)
+    with FakeTensorMode():
+        x = torch.empty(10, 3, dtype=torch.float64, device="cuda")
+        s, c = torch.ops.pyinterpolate_b200.variogram_sums(x, torch.empty(5, dtype=torch.float64), torch.empty(0, dtype=torch.float64),
+                                                           torch.empty(8, dtype=torch.float64), 0, 1)
+        assert tuple(s.shape) == (3, 2, 5) and tuple(c.shape) == (2, 5) and c.dtype == torch.int64
+        o, st = torch.ops.pyinterpolate_b200.krige(x, torch.empty(7, 2, dtype=torch.float64, device="cuda"),
+                                                   torch.empty(1, 3, dtype=torch.float64), 0, _lib.KRIGE_BOTH, 0.0, 4)
+        assert tuple(o.shape) == (2, 1, 7, 4) and tuple(st.shape) == (2, 1, 7) and st.dtype == torch.uint8
