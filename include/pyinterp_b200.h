@@ -263,6 +263,11 @@ PIB_API int pib_gamma_host(int model, double nugget, double sill, double rang,
  * Synchronises on the recorded events. */
 PIB_API int pib_last_kernel_ms(int which, double *ms_out, int *launches_out);
 
+/* on != 0: the kernel-time records are kept ACROSS calls from now on (pib_last_kernel_ms then returns the sum and the launch
+ * count over every call since), so a benchmark can time K back-to-back calls without reading — and synchronising on — the
+ * events after each one; on == 0: back to per-call records.  Either value clears the records. */
+PIB_API int pib_timing_accumulate(int on);
+
 /* Name of the kernel variant behind pib_last_kernel_ms(which) in the last call (e.g. "pair_ring6_kernel<16,512,1,8>"),
  * copied into buf (NUL terminated, at most len bytes). */
 PIB_API int pib_last_kernel_name(int which, char *buf, int len);

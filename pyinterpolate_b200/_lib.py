@@ -23,7 +23,8 @@ STATUS_LSA, STATUS_ZERO_MATRIX = 4, 5
 EXPORTS = ("pib_trim", "pib_last_kernel_name", "pib_krige_loo_host", "pib_krige_ex_device", "pib_krige_ex_host", "pib_last_error", "pib_version", "pib_device_sm_count", "pib_variogram_device",
            "pib_variogram_host", "pib_krige_device", "pib_krige_host", "pib_gamma_host",
            "pib_fp64_peak_tflops", "pib_last_kernel_ms", "pib_variogram_cloud_host",
-           "pib_variogram_weighted_host", "pib_variogram_triangle_host", "pib_variogram_triangle_cloud_host")
+           "pib_variogram_weighted_host", "pib_variogram_triangle_host", "pib_variogram_triangle_cloud_host",
+           "pib_timing_accumulate")
 
 _lib = None
 
@@ -59,6 +60,7 @@ def load():
     L.pib_gamma_host.argtypes = [i32, f64, f64, f64, dp, i64, dp]
     L.pib_fp64_peak_tflops.argtypes = [dp]
     L.pib_last_kernel_ms.argtypes = [i32, dp, dp]
+    L.pib_timing_accumulate.argtypes = [i32]
     L.pib_last_kernel_name.argtypes = [i32, ctypes.c_char_p, i32]
     L.pib_variogram_cloud_host.argtypes = [dp, i64, dp, dp, i32, dp, i32, dp, dp]
     L.pib_variogram_weighted_host.argtypes = [dp, dp, i64, dp, dp, i32, dp, i32, dp, dp]
@@ -285,6 +287,12 @@ def last_kernel_ms(which):
     check(L.pib_last_kernel_ms(int(which), ctypes.cast(ctypes.byref(ms), ctypes.c_void_p),
                                ctypes.cast(ctypes.byref(launches), ctypes.c_void_p)), "pib_last_kernel_ms")
     return float(ms.value), int(launches.value)
+
+
+def timing_accumulate(on):
+    """Keep the kernel-time records across calls (``last_kernel_ms`` then covers every call since) or go back to per-call
+    records; either way the records are cleared."""
+    check(load().pib_timing_accumulate(1 if on else 0), "pib_timing_accumulate")
 
 
 def last_kernel_name(which):

@@ -61,9 +61,16 @@ struct Segment { cudaEvent_t a, b; };
 static std::vector<Segment> g_segments[PIB_T_COUNT];
 static std::mutex g_timing_mutex;
 
+static bool g_timing_keep = false;     // pib_timing_accumulate: records survive the per-call reset
+static void timing_clear(int which)
+{
+    for (auto &s : g_segments[which]) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    g_segments[which].clear();
+}
 void timing_reset(int which)
 {
     std::lock_guard<std::mutex> lock(g_timing_mutex);
+    if (g_timing_keep) return;
     for (auto &s : g_segments[which]) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     g_segments[which].clear();
 }
@@ -558,6 +565,14 @@ int pib_last_kernel_ms(int which, double *ms_out, int *launches_out)
     }
     *ms_out = total;
     if (launches_out) *launches_out = (int)g_segments[which].size();
+    return PIB_OK;
+}
+
+int pib_timing_accumulate(int on)
+{
+    std::lock_guard<std::mutex> lock(g_timing_mutex);
+    for (int w = 0; w < PIB_T_COUNT; ++w) timing_clear(w);
+    g_timing_keep = on != 0;
     return PIB_OK;
 }
 

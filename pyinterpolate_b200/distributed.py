@@ -59,14 +59,17 @@ def allreduce_variogram_sums(sums, device=None, group=None):
     shape = tuple(sums["count"].shape)
     n = int(np.prod(shape))
     parts = [to_t(sums[k]).reshape(-1) for k in ("sum_sq", "sum_prod", "sum_val", "count")]
-    extra = torch.tensor([float(int(sums.get("pairs_evaluated", 0)))], dtype=torch.float64, device=parts[0].device)
-    buf = torch.cat(parts + [extra])
+    # the evaluated-pairs counter rides along only when the caller asked for it: reading it back is a host synchronisation
+    has_pairs = bool(sums.get("pairs_evaluated"))
+    if has_pairs:
+        parts.append(torch.tensor([float(int(sums["pairs_evaluated"]))], dtype=torch.float64, device=parts[0].device))
+    buf = torch.cat(parts)
     if device is not None:
         buf = buf.to(device)
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     cnt = buf[3 * n:4 * n].round().to(torch.int64)
     out = dict(sum_sq=buf[:n].reshape(shape), sum_prod=buf[n:2 * n].reshape(shape), sum_val=buf[2 * n:3 * n].reshape(shape),
-               count=cnt.reshape(shape), pairs_evaluated=int(round(float(buf[-1].item()))))
+               count=cnt.reshape(shape), pairs_evaluated=int(round(float(buf[-1].item()))) if has_pairs else 0)
     if as_numpy:
         out = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
     return out
