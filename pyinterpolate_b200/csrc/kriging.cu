@@ -1427,6 +1427,7 @@ __global__ void __launch_bounds__(gj2_threads<K>(), gj2_min_ctas<K>()) solve_gj2
             }
             // rows t come before rows t + TPS
             const int src = __ffs(lead0 ? lead0 : lead1) - 1;
+            PIB_DBG_ASSERT(src >= (lane & ~(TPS - 1)) && src < (lane & ~(TPS - 1)) + TPS);          // a lane of my own system
             double *const C = cand + (j & 1) * CS;
             if (lane == src) {
                 if (lead0) {
@@ -1453,6 +1454,7 @@ __global__ void __launch_bounds__(gj2_threads<K>(), gj2_min_ctas<K>()) solve_gj2
             if (go && !singular) {
                 const double inv = C[K + 3];
                 const int prow = reinterpret_cast<const int *>(C + K + 4)[0];
+                PIB_DBG_ASSERT(prow >= 0 && prow < K);
                 const bool is_p0 = (prow == t), is_p1 = (prow == t + TPS);
                 if (is_p0) { active[0] = false; my_step[0] = j; my_inv[0] = inv; }
                 if (is_p1) { active[1] = false; my_step[1] = j; my_inv[1] = inv; }
@@ -1483,6 +1485,7 @@ __global__ void __launch_bounds__(gj2_threads<K>(), gj2_min_ctas<K>()) solve_gj2
         for (int rr = 0; rr < 2; ++rr) {
             const bool real = (my_step[rr] >= 0 && my_step[rr] < kk);
             const double u = real ? r0[rr] * my_inv[rr] : 0.0, v = real ? r1[rr] * my_inv[rr] : 0.0;
+            PIB_DBG_ASSERT(my_step[rr] >= -1 && my_step[rr] < K);
             const double zn = real ? S.zv[my_step[rr]] : 0.0, gn = real ? S.g0[my_step[rr]] : 0.0;
             s[0] += u; s[1] += v; s[2] += u * zn; s[3] += v * zn; s[4] += u * gn; s[5] += v * gn;
         }

@@ -2249,7 +2249,8 @@ int variogram_triangle_device(const double *d_xyz, int64_t n, const double *tri_
 template <bool WRITE>
 __global__ void triangle_cloud_kernel(const double *__restrict__ xyz, int64_t n, const TriLag *__restrict__ lags, int n_lags,
                                       double cos_t, double sin_t, double inv_tol, double band_rel,
-                                      unsigned long long *__restrict__ cursor /* [n_lags][n] */, double *__restrict__ values)
+                                      unsigned long long *__restrict__ cursor /* [n_lags][n] */, double *__restrict__ values,
+                                      unsigned long long n_values)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -2262,6 +2263,7 @@ __global__ void triangle_cloud_kernel(const double *__restrict__ xyz, int64_t n,
             unsigned long long *c = cursor + (size_t)k * n + i;
             if (WRITE) {
                 const double dz = pz - xyz[3 * j + 2];
+                PIB_DBG_ASSERT(*c < n_values);
                 values[(*c)++] = dz * dz;
             } else ++(*c);
         });
@@ -2285,7 +2287,7 @@ int variogram_triangle_cloud_device(const double *d_xyz, int64_t n, const double
     PIB_CUDA(cudaMemcpyAsync(d_off, lag_offsets, n_lags * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
     PIB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long) * n_lags * n, stream));
     const int grid = (int)((n + 127) / 128);
-    triangle_cloud_kernel<false><<<grid, 128, 0, stream>>>(d_xyz, n, d_lags, n_lags, cos_t, sin_t, 1.0 / tolerance, 1e-9, d_cursor, nullptr);
+    triangle_cloud_kernel<false><<<grid, 128, 0, stream>>>(d_xyz, n, d_lags, n_lags, cos_t, sin_t, 1.0 / tolerance, 1e-9, d_cursor, nullptr, 0);
     PIB_CUDA(cudaGetLastError());
     cloud_scan_kernel<<<n_lags, 1024, 0, stream>>>(d_cursor, n, d_off, d_end);
     PIB_CUDA(cudaGetLastError());
@@ -2295,7 +2297,8 @@ int variogram_triangle_cloud_device(const double *d_xyz, int64_t n, const double
     PIB_CUDA(cudaStreamSynchronize(stream));
     for (int b = 0; b < n_lags; ++b)
         PIB_CHECK((int64_t)end[b] == lag_offsets[b + 1], PIB_ERR_INVALID, "triangle cloud: lag_offsets do not match the pair counts");
-    triangle_cloud_kernel<true><<<grid, 128, 0, stream>>>(d_xyz, n, d_lags, n_lags, cos_t, sin_t, 1.0 / tolerance, 1e-9, d_cursor, d_values);
+    triangle_cloud_kernel<true><<<grid, 128, 0, stream>>>(d_xyz, n, d_lags, n_lags, cos_t, sin_t, 1.0 / tolerance, 1e-9, d_cursor, d_values,
+                                                           (unsigned long long)lag_offsets[n_lags]);
     PIB_CUDA(cudaGetLastError());
     return PIB_OK;
 }
