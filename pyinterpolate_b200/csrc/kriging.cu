@@ -1072,14 +1072,22 @@ struct GjSmem {
 #ifndef PIB_GJ_LOOKAHEAD
 #define PIB_GJ_LOOKAHEAD 1
 #endif
+#ifndef PIB_GJ32_THREADS
+#define PIB_GJ32_THREADS 256
+#endif
+#ifndef PIB_GJ32_CTAS
+#define PIB_GJ32_CTAS 2
+#endif
 #ifndef PIB_GJ64_THREADS
 #define PIB_GJ64_THREADS 384
 #endif
 template <int K>
-__host__ __device__ constexpr int gj_threads() { return K == 64 ? PIB_GJ64_THREADS : 256; }
+__host__ __device__ constexpr int gj_threads() { return K == 64 ? PIB_GJ64_THREADS : K == 32 ? PIB_GJ32_THREADS : 256; }
+template <int K>
+__host__ __device__ constexpr int gj_min_ctas() { return K == 32 ? PIB_GJ32_CTAS : 1; }
 
 template <int K, int MODE>      // MODE: PIB_KRIGE_ORDINARY, PIB_KRIGE_SIMPLE or PIB_KRIGE_BOTH
-__global__ void __launch_bounds__(gj_threads<K>(), K == 32 ? 2 : 1) solve_gj_kernel(const SolveParams p)
+__global__ void __launch_bounds__(gj_threads<K>(), gj_min_ctas<K>()) solve_gj_kernel(const SolveParams p)
 {
     constexpr int TPS = K < 32 ? 32 : K;          // threads per system
     constexpr int SPC = gj_threads<K>() / TPS;    // systems per CTA
