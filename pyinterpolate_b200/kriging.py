@@ -37,8 +37,10 @@ def _prepare(theoretical_model, known_locations, unknown_locations, use_all_neig
         raise ValueError("known_locations must be rows of [x, y, value]")
     if unknown.ndim != 2 or unknown.shape[1] != 2:
         raise ValueError("unknown_locations must be rows of [x, y]")
-    # a finite sum means every term is finite (NaN and +-inf propagate); only an overflowing sum needs the exact scan
-    if not (np.isfinite(known[:, :2].sum()) and np.isfinite(unknown.sum())):
+    # a finite sum means every term is finite (NaN and +-inf propagate); only an overflowing sum (or a non-finite VALUE, which is
+    # not an error here) needs the exact scan of the coordinate columns.  The sum runs over the whole contiguous array: the
+    # strided `known[:, :2].sum()` cost 3.5 ms per million points, most of the fixed cost of a call
+    if not (np.isfinite(known.sum()) and np.isfinite(unknown.sum())):
         if not (np.isfinite(known[:, :2]).all() and np.isfinite(unknown).all()):
             raise ValueError("coordinates must be finite")
     # neighbors_range defaults to the model range (kriging/utils/point_kriging_solve.py:68-69)

@@ -271,3 +271,24 @@ def test_torch_ops_are_registered_and_have_no_cpu_kernel():
         o, st = torch.ops.pyinterpolate_b200.krige(x, torch.empty(7, 2, dtype=torch.float64, device="cuda"),
                                                    torch.empty(1, 3, dtype=torch.float64), 0, _lib.KRIGE_BOTH, 0.0, 4)
         assert tuple(o.shape) == (2, 1, 7, 4) and tuple(st.shape) == (2, 1, 7) and st.dtype == torch.uint8
+
+
+def test_kriging_inputs_with_non_finite_coordinates_are_refused():
+    """The Python layer rejects NaN / inf coordinates before anything reaches the library (a NaN location would select no
+    neighbours); a non-finite VALUE is not a coordinate error."""
+    from pyinterpolate_b200.kriging import _prepare
+    mdl = {"variogram_model_type": "linear", "nugget": 0.0, "sill": 1.0, "rang": 10.0}
+    known = np.random.default_rng(3).uniform(0, 100, (50, 3))
+    unk = np.random.default_rng(4).uniform(0, 100, (7, 2))
+    _prepare(mdl, known, unk, False, False)
+    for bad in (np.nan, np.inf, -np.inf):
+        k2 = known.copy(); k2[17, 1] = bad
+        with pytest.raises(ValueError):
+            _prepare(mdl, k2, unk, False, False)
+        u2 = unk.copy(); u2[3, 0] = bad
+        with pytest.raises(ValueError):
+            _prepare(mdl, known, u2, False, False)
+    k3 = known.copy(); k3[5, 2] = np.nan                    # a missing value is the caller's business, like in the reference
+    _prepare(mdl, k3, unk, False, False)
+    k4 = known.copy(); k4[:, 2] = 1e308                      # values whose sum overflows: exact scan of the coordinates decides
+    _prepare(mdl, k4, unk, False, False)
