@@ -1353,13 +1353,17 @@ static int launch_solve_gj_m(const SolveParams &sp, cudaStream_t stream)
 #ifndef PIB_GJ2_32_THREADS
 #define PIB_GJ2_32_THREADS 64
 #endif
+#ifndef PIB_GJ2_SMALL_CTAS
+#define PIB_GJ2_SMALL_CTAS 8
+#endif
 #ifndef PIB_GJ2_32_CTAS
 #define PIB_GJ2_32_CTAS 5
 #endif
 template <int K>
 __host__ __device__ constexpr int gj2_threads() { return K == 32 ? PIB_GJ2_32_THREADS : 64; }
 template <int K>
-__host__ __device__ constexpr int gj2_min_ctas() { return K == 32 ? PIB_GJ2_32_CTAS : 8; }
+// (K = 16: 8 CTAs of 64 threads at 128 registers — 10 / 12 CTAs spill: 2.44 -> 3.30 / 4.47 ms; K = 8: 12 CTAs at 80 registers, 0.84 -> 0.74 ms)
+__host__ __device__ constexpr int gj2_min_ctas() { return K == 32 ? PIB_GJ2_32_CTAS : K == 8 ? 12 : PIB_GJ2_SMALL_CTAS; }
 
 template <int K, int MODE>
 __global__ void __launch_bounds__(gj2_threads<K>(), gj2_min_ctas<K>()) solve_gj2_kernel(const SolveParams p)
