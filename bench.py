@@ -455,7 +455,7 @@ def run_b200(args):
         del ok4, sk4
         # the k = 32 public call of config 1's shape (ordinary kriging, linear model), same strong-scaled split
         mdl1 = {"variogram_model_type": "linear", "nugget": 0.0, "sill": var, "rang": 8000.0}
-        m1 = min(m4, 4_000_000)
+        m1 = m4                                              # the same 10M locations as config 4, split over the ranks
         b1, e1 = (rank * m1) // world, ((rank + 1) * m1) // world
         pib.ordinary_kriging(mdl1, pts, unk4[b1:min(e1, b1 + 2_200_000)], no_neighbors=32)
         t1s = []
