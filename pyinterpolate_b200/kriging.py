@@ -178,7 +178,8 @@ def indicator_kriging(theoretical_models, thresholds, known_locations, unknown_l
     if any(p[4] is not None for p in parsed):
         raise NotImplementedError("directional indicator models are not implemented")
     params = np.array([[p[1], p[2], p[3]] for p in parsed])
-    values = np.stack([(known[:, 2] <= float(t)).astype(np.float64) for t in thresholds])
+    z = np.ascontiguousarray(known[:, 2])
+    values = (z[None, :] <= np.asarray(thresholds, dtype=np.float64)[:, None]).astype(np.float64)     # [T, N] indicator columns
     sel = dict(use_all=bool(use_all_neighbors_in_range), allow_lsa=bool(allow_approximate_solutions))
     ranges = params[:, 2] if neighbors_range is None else np.full(len(parsed), float(neighbors_range))
     if use_all_neighbors_in_range and len(set(ranges.tolist())) > 1:
@@ -194,9 +195,10 @@ def indicator_kriging(theoretical_models, thresholds, known_locations, unknown_l
                                          values=values, neighbors_range=float(ranges[0]), **sel)
     _raise_on_singular(status)
     col = 1 if reference_variance_column else 0
-    res = out[:, :, col].T.copy()
+    # indicator.py:399-403 sets values below 0 to 0 and above 1 to 1 (NaN stays NaN): one clipping pass from the strided
+    # [T, M, 4] block into the contiguous [M, T] result
+    res = np.empty((out.shape[1], out.shape[0]))
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        res[res < 0] = 0                                              # indicator.py:399-403
-        res[res > 1] = 1
+        np.clip(out[:, :, col].T, 0.0, 1.0, out=res)
     return res
