@@ -360,6 +360,9 @@ struct HostStage {
     }
 };
 
+#ifndef PIB_KRIGE_LANES_DEFAULT
+#define PIB_KRIGE_LANES_DEFAULT 2
+#endif
 // Host-buffer kriging: the known points go to the device once, the locations stream through in chunks on TWO lanes
 // (stream + pinned staging each): while lane A computes chunk i, lane B's results of chunk i-1 travel back and the
 // host refills B's input — host<->device copies overlap the kernels instead of bracketing them
@@ -384,9 +387,12 @@ int pib_krige_ex_host(const double *known, int64_t n, const double *values, int 
     const char *chunk_env = std::getenv("PIB_KRIGE_CHUNK");
     if (chunk_env && std::atoll(chunk_env) > 0) chunk = std::atoll(chunk_env);
     chunk = std::min(chunk, m);
-    const int n_lanes = m > chunk ? 2 : 1;
+    // lanes of the pipeline: chunks in flight at once (stream + pinned staging each); PIB_KRIGE_LANES overrides (1 .. 4)
+    constexpr int MAX_LANES = 4;
+    int n_lanes = m > 2 * chunk ? PIB_KRIGE_LANES_DEFAULT : m > chunk ? 2 : 1;
+    { const char *le = std::getenv("PIB_KRIGE_LANES"); if (le && std::atoi(le) >= 1) n_lanes = std::min({std::atoi(le), MAX_LANES, (int)((m + chunk - 1) / chunk)}); }
 
-    static thread_local HostStage stage[2];
+    static thread_local HostStage stage[MAX_LANES];
     const size_t in_bytes = (size_t)chunk * 2 * sizeof(double);
     const size_t out_bytes = blocks * chunk * 4 * sizeof(double);
     const size_t idx_bytes = nbr_idx ? (size_t)chunk * k * sizeof(int32_t) : 0;
@@ -395,7 +401,7 @@ int pib_krige_ex_host(const double *known, int64_t n, const double *values, int 
     const size_t lane_bytes = align256(in_bytes) + align256(out_bytes) + align256(idx_bytes) + align256(st_bytes);
     for (int b = 0; b < n_lanes; ++b) PIB_TRY(stage[b].reserve(lane_bytes));
 
-    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaStream_t s[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t index_ready = nullptr;
     int rc = PIB_OK;
     for (int b = 0; b < n_lanes && rc == PIB_OK; ++b)
@@ -415,7 +421,7 @@ int pib_krige_ex_host(const double *known, int64_t n, const double *values, int 
         }
         if (rc == PIB_OK) rc = krige_build_index(d_known, n, ws, s[0], &grid);
         if (rc == PIB_OK && (cudaEventRecord(index_ready, s[0]) != cudaSuccess ||
-                             (n_lanes > 1 && cudaStreamWaitEvent(s[1], index_ready, 0) != cudaSuccess))) {
+                             [&] { for (int b = 1; b < n_lanes; ++b) if (cudaStreamWaitEvent(s[b], index_ready, 0) != cudaSuccess) return true; return false; }())) {
             set_error("krige: event failed"); rc = PIB_ERR_CUDA;
         }
         timing_reset(PIB_T_KNN);
@@ -423,7 +429,7 @@ int pib_krige_ex_host(const double *known, int64_t n, const double *values, int 
 
         struct Lane { Scratch *ws = nullptr; double *d_unk = nullptr, *d_out = nullptr; int32_t *d_idx = nullptr; uint8_t *d_st = nullptr;
                       int64_t begin = -1, count = 0; };
-        Lane lane[2];
+        Lane lane[MAX_LANES];
         // copy a finished chunk out of the lane's pinned staging into the caller's arrays
         auto drain = [&](int b) -> int {
             Lane &L = lane[b];
@@ -478,7 +484,7 @@ int pib_krige_ex_host(const double *known, int64_t n, const double *values, int 
         for (int b = 0; b < n_lanes; ++b) if (s[b]) cudaStreamSynchronize(s[b]);
     }
     if (index_ready) cudaEventDestroy(index_ready);
-    for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < MAX_LANES; ++b)
         if (s[b]) { cudaStreamSynchronize(s[b]); cudaStreamDestroy(s[b]); }
     return rc;
 }

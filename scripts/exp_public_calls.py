@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Host-side copy threads of the kriging chunk pipeline (PIB_HOST_THREADS, read once per process): time of the public k = 32 call
-on 10M / 1.25M / 500k locations and of BASELINE config 5 (indicator kriging).  usage: PIB_HOST_THREADS=n python scripts/exp_host_threads.py"""
+"""Public kriging calls with host arrays under a setting of the chunk pipeline (PIB_KRIGE_LANES, PIB_KRIGE_CHUNK): time of the
+k = 32 call on 10M / 1.25M / 500k locations and of BASELINE config 5 (indicator kriging).
+usage: PIB_KRIGE_LANES=n python scripts/exp_public_calls.py"""
 import os
 import sys
 import time
@@ -17,7 +18,7 @@ known = dem_like_field(1_000_000, seed=2)
 unk = uniform_locations(10_000_000, seed=5)
 var = float(np.var(known[:, 2]))
 mdl = {"variogram_model_type": "linear", "nugget": 0.0, "sill": var, "rang": 8000.0}
-print("PIB_HOST_THREADS =", os.environ.get("PIB_HOST_THREADS", "(default 4)"))
+print("PIB_KRIGE_LANES =", os.environ.get("PIB_KRIGE_LANES", "(default)"), " PIB_KRIGE_CHUNK =", os.environ.get("PIB_KRIGE_CHUNK", "(default)"))
 for m in (10_000_000, 1_250_000, 500_000):
     best = 1e9
     for rep in range(3):
