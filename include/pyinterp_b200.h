@@ -245,6 +245,18 @@ PIB_API int pib_krige_ex_host(const double *known, int64_t n,
                       double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
                       double *out, int32_t *nbr_idx, uint8_t *status);
 
+/* pib_krige_ex_host that hands back ONE column of the result rows: column 0 = predictions, 1 = kriging variances (NaN where
+ * negative), out_column [n_sets][m] ([2][n_sets][m] for PIB_KRIGE_BOTH).  A quarter of the device-to-host traffic and of the
+ * host-side copies — for callers that keep one column per parameter set, e.g. the reference's IndicatorKriging
+ * (kriging/point/indicator.py:290-313 stores _pred_arr[0][1] per threshold). */
+PIB_API int pib_krige_column_host(const double *known, int64_t n,
+                          const double *values, int n_sets, const double *params,
+                          const double *unknown, int64_t m,
+                          int model, int mode, double process_mean, int k,
+                          double neighbors_range, double direction, double max_tick,
+                          int use_all, int allow_lsa,
+                          int column, double *out_column, uint8_t *status);
+
 /* Leave-one-out cross-validation in one batched call — replaces the loop of evaluate/cross_validation.py:78-131
  * (np.delete(points, i) + ordinary_kriging / simple_kriging at point i, for every i): location i is known row i,
  * and the neighbour search skips that row.  out [n][4] = [zhat_i, sigma^2_i, x_i, y_i]; status as above.

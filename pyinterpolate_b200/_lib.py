@@ -24,7 +24,7 @@ EXPORTS = ("pib_trim", "pib_last_kernel_name", "pib_krige_loo_host", "pib_krige_
            "pib_variogram_host", "pib_krige_device", "pib_krige_host", "pib_gamma_host",
            "pib_fp64_peak_tflops", "pib_last_kernel_ms", "pib_variogram_cloud_host",
            "pib_variogram_weighted_host", "pib_variogram_triangle_host", "pib_variogram_triangle_cloud_host",
-           "pib_timing_accumulate")
+           "pib_timing_accumulate", "pib_krige_column_host")
 
 _lib = None
 
@@ -56,6 +56,7 @@ def load():
     kr_ex = kr_args[:11] + [f64, f64, f64, i32, i32] + kr_args[11:]
     L.pib_krige_ex_device.argtypes = kr_ex + [ctypes.c_void_p]
     L.pib_krige_ex_host.argtypes = kr_ex
+    L.pib_krige_column_host.argtypes = kr_args[:11] + [f64, f64, f64, i32, i32, i32, dp, dp]
     L.pib_krige_loo_host.argtypes = [dp, i64, dp, i32, i32, f64, i32, f64, f64, f64, i32, i32, dp, dp]
     L.pib_gamma_host.argtypes = [i32, f64, f64, f64, dp, i64, dp]
     L.pib_fp64_peak_tflops.argtypes = [dp]
@@ -220,6 +221,26 @@ def krige_host(known, unknown, model, params, mode, k, process_mean=0.0, values=
     return out, idx, status
 
 
+def krige_column_host(known, unknown, model, params, mode, k, column, process_mean=0.0, values=None, neighbors_range=0.0,
+                      direction=None, max_tick=5.0, use_all=False, allow_lsa=False):
+    """``krige_host`` that brings back one column of the result rows: ``column`` 0 = predictions, 1 = kriging variances.
+    Returns (col[n_sets, m], status[n_sets, m]) (a leading axis of 2 with ``mode=KRIGE_BOTH``)."""
+    L = load()
+    known, unknown = _f64(known), _f64(unknown).reshape(-1, 2)
+    params = _f64(params).reshape(-1, 3)
+    n, m, n_sets = known.shape[0], unknown.shape[0], params.shape[0]
+    values_c = None if values is None else _f64(values).reshape(n_sets, n)
+    lead = (2,) if int(mode) == KRIGE_BOTH else ()
+    col = np.empty(lead + (n_sets, m))
+    status = np.zeros(lead + (n_sets, m), dtype=np.uint8)
+    rc = L.pib_krige_column_host(_host_ptr(known), n, _host_ptr(values_c), n_sets, _host_ptr(params), _host_ptr(unknown), m,
+                                 int(model), int(mode), float(process_mean), int(k), float(neighbors_range),
+                                 float("nan") if direction is None else float(direction), float(max_tick),
+                                 1 if use_all else 0, 1 if allow_lsa else 0, int(column), _host_ptr(col), _host_ptr(status))
+    check(rc, "pib_krige_column_host")
+    return col, status
+
+
 def krige_loo_host(known, model, params, mode, k, process_mean=0.0, neighbors_range=0.0, direction=None, max_tick=5.0,
                    use_all=False, allow_lsa=False):
     """Leave-one-out kriging of every known row from the others.  Returns (out[n, 4], status[n])."""
@@ -292,7 +313,7 @@ def last_kernel_ms(which):
 def timing_accumulate(on):
     """Keep the kernel-time records across calls (``last_kernel_ms`` then covers every call since) or go back to per-call
     records; either way the records are cleared."""
-    check(load().pib_timing_accumulate(1 if on else 0), "pib_timing_accumulate")
+    check(load().pib_timing_accumulate(1 if on else 0), "pib_timing_accumulate", "pib_krige_column_host")
 
 
 def last_kernel_name(which):

@@ -367,12 +367,23 @@ struct HostStage {
 // (stream + pinned staging each): while lane A computes chunk i, lane B's results of chunk i-1 travel back and the
 // host refills B's input — host<->device copies overlap the kernels instead of bracketing them
 // (reference loop: kriging/point/ordinary.py:205-219; SURVEY.md section 8e asks for per-chunk pipelining).
-int pib_krige_ex_host(const double *known, int64_t n, const double *values, int n_sets, const double *params,
-                      const double *unknown, int64_t m, int model, int mode, double process_mean, int k,
-                      double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
-                      double *out, int32_t *nbr_idx, uint8_t *status)
+// one column of the [blocks][count][4] result rows -> [blocks][count]
+__global__ void extract_column_kernel(const double *__restrict__ rows, int64_t n_rows, int col, double *__restrict__ out)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n_rows) out[i] = rows[4 * i + col];
+}
+
+// out_col < 0: `out` receives the full [zhat, sigma^2, x, y] rows ([blocks][m][4]); 0 / 1: only that column ([blocks][m]) —
+// a quarter of the device-to-host traffic and of the host-side copy for callers that keep one column (indicator kriging)
+static int krige_host_impl(const double *known, int64_t n, const double *values, int n_sets, const double *params,
+                           const double *unknown, int64_t m, int model, int mode, double process_mean, int k,
+                           double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
+                           int out_col, double *out, int32_t *nbr_idx, uint8_t *status)
 {
     PIB_CHECK(known && (unknown || m == 0) && (out || m == 0), PIB_ERR_INVALID, "krige: NULL pointer");
+    PIB_CHECK(out_col < 2, PIB_ERR_INVALID, "krige: the result column is 0 (prediction) or 1 (variance)");
+    const size_t width = out_col < 0 ? 4 : 1;                     // doubles per location and block that travel back
     PIB_CHECK(n >= 1 && m >= 0 && k >= 1 && n_sets >= 1, PIB_ERR_INVALID, "krige: need n >= 1, m >= 0, k >= 1");
     PIB_CHECK(mode == PIB_KRIGE_ORDINARY || mode == PIB_KRIGE_SIMPLE || mode == PIB_KRIGE_BOTH, PIB_ERR_INVALID, "krige: unknown mode");
     if (m == 0) return PIB_OK;
@@ -394,7 +405,7 @@ int pib_krige_ex_host(const double *known, int64_t n, const double *values, int 
 
     static thread_local HostStage stage[MAX_LANES];
     const size_t in_bytes = (size_t)chunk * 2 * sizeof(double);
-    const size_t out_bytes = blocks * chunk * 4 * sizeof(double);
+    const size_t out_bytes = blocks * chunk * width * sizeof(double);
     const size_t idx_bytes = nbr_idx ? (size_t)chunk * k * sizeof(int32_t) : 0;
     const size_t st_bytes = status ? blocks * chunk : 0;
     auto align256 = [](size_t b) { return (b + 255) / 256 * 256; };
@@ -427,7 +438,7 @@ int pib_krige_ex_host(const double *known, int64_t n, const double *values, int 
         timing_reset(PIB_T_KNN);
         timing_reset(PIB_T_SOLVE);
 
-        struct Lane { Scratch *ws = nullptr; double *d_unk = nullptr, *d_out = nullptr; int32_t *d_idx = nullptr; uint8_t *d_st = nullptr;
+        struct Lane { Scratch *ws = nullptr; double *d_unk = nullptr, *d_out = nullptr, *d_col = nullptr; int32_t *d_idx = nullptr; uint8_t *d_st = nullptr;
                       int64_t begin = -1, count = 0; };
         Lane lane[MAX_LANES];
         // copy a finished chunk out of the lane's pinned staging into the caller's arrays
@@ -438,7 +449,7 @@ int pib_krige_ex_host(const double *known, int64_t n, const double *values, int 
             char *base = static_cast<char *>(stage[b].ptr);
             const double *h_out = reinterpret_cast<const double *>(base + align256(in_bytes));
             for (size_t blk = 0; blk < blocks; ++blk)
-                std::memcpy(out + (blk * (size_t)m + L.begin) * 4, h_out + blk * (size_t)L.count * 4, sizeof(double) * 4 * L.count);
+                std::memcpy(out + (blk * (size_t)m + L.begin) * width, h_out + blk * (size_t)L.count * width, sizeof(double) * width * L.count);
             if (nbr_idx)
                 std::memcpy(nbr_idx + (size_t)L.begin * k, base + align256(in_bytes) + align256(out_bytes), sizeof(int32_t) * L.count * k);
             if (status) {
@@ -458,6 +469,7 @@ int pib_krige_ex_host(const double *known, int64_t n, const double *values, int 
             L.ws = new Scratch(s[b]);
             rc = L.ws->alloc(&L.d_unk, (size_t)L.count * 2);
             if (rc == PIB_OK) rc = L.ws->alloc(&L.d_out, blocks * L.count * 4);
+            if (rc == PIB_OK && out_col >= 0) rc = L.ws->alloc(&L.d_col, blocks * L.count);
             if (rc == PIB_OK && nbr_idx) rc = L.ws->alloc(&L.d_idx, (size_t)L.count * k);
             if (rc == PIB_OK && status) rc = L.ws->alloc(&L.d_st, blocks * L.count);
             if (rc != PIB_OK) break;
@@ -468,6 +480,13 @@ int pib_krige_ex_host(const double *known, int64_t n, const double *values, int 
             rc = krige_device(d_known, n, d_values, n_sets, params, L.d_unk, L.count, model, mode, process_mean, k, neighbors_range,
                               direction, max_tick, use_all, allow_lsa, nullptr, L.d_out, L.d_idx, L.d_st, s[b], &grid);
             if (rc != PIB_OK) break;
+            if (out_col >= 0) {
+                const int64_t rows = (int64_t)blocks * L.count;
+                extract_column_kernel<<<(int)((rows + 255) / 256), 256, 0, s[b]>>>(L.d_out, rows, out_col, L.d_col);
+                e = cudaGetLastError();
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(base + align256(in_bytes), L.d_col, sizeof(double) * rows, cudaMemcpyDeviceToHost, s[b]);
+            } else
             e = cudaMemcpyAsync(base + align256(in_bytes), L.d_out, sizeof(double) * 4 * blocks * L.count, cudaMemcpyDeviceToHost, s[b]);
             if (e == cudaSuccess && nbr_idx)
                 e = cudaMemcpyAsync(base + align256(in_bytes) + align256(out_bytes), L.d_idx, sizeof(int32_t) * L.count * k, cudaMemcpyDeviceToHost, s[b]);
@@ -487,6 +506,25 @@ int pib_krige_ex_host(const double *known, int64_t n, const double *values, int 
     for (int b = 0; b < MAX_LANES; ++b)
         if (s[b]) { cudaStreamSynchronize(s[b]); cudaStreamDestroy(s[b]); }
     return rc;
+}
+
+int pib_krige_ex_host(const double *known, int64_t n, const double *values, int n_sets, const double *params,
+                      const double *unknown, int64_t m, int model, int mode, double process_mean, int k,
+                      double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
+                      double *out, int32_t *nbr_idx, uint8_t *status)
+{
+    return krige_host_impl(known, n, values, n_sets, params, unknown, m, model, mode, process_mean, k, neighbors_range, direction,
+                           max_tick, use_all, allow_lsa, -1, out, nbr_idx, status);
+}
+
+int pib_krige_column_host(const double *known, int64_t n, const double *values, int n_sets, const double *params,
+                          const double *unknown, int64_t m, int model, int mode, double process_mean, int k,
+                          double neighbors_range, double direction, double max_tick, int use_all, int allow_lsa,
+                          int column, double *out_column, uint8_t *status)
+{
+    PIB_CHECK(column == 0 || column == 1, PIB_ERR_INVALID, "krige: the result column is 0 (prediction) or 1 (variance)");
+    return krige_host_impl(known, n, values, n_sets, params, unknown, m, model, mode, process_mean, k, neighbors_range, direction,
+                           max_tick, use_all, allow_lsa, column, out_column, nullptr, status);
 }
 
 // leave-one-out: location i = known row i, kriged from the other rows

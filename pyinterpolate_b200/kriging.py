@@ -182,6 +182,7 @@ def indicator_kriging(theoretical_models, thresholds, known_locations, unknown_l
     values = (z[None, :] <= np.asarray(thresholds, dtype=np.float64)[:, None]).astype(np.float64)     # [T, N] indicator columns
     sel = dict(use_all=bool(use_all_neighbors_in_range), allow_lsa=bool(allow_approximate_solutions))
     ranges = params[:, 2] if neighbors_range is None else np.full(len(parsed), float(neighbors_range))
+    col = 1 if reference_variance_column else 0
     if use_all_neighbors_in_range and len(set(ranges.tolist())) > 1:
         outs, stats = [], []
         for t in range(len(parsed)):
@@ -190,15 +191,15 @@ def indicator_kriging(theoretical_models, thresholds, known_locations, unknown_l
             outs.append(o[0])
             stats.append(st[0])
         out, status = np.stack(outs), np.stack(stats)
+        cols = out[:, :, col]
     else:
-        out, _, status = _lib.krige_host(known, unknown, parsed[0][0], params, _lib.KRIGE_ORDINARY, int(no_neighbors),
-                                         values=values, neighbors_range=float(ranges[0]), **sel)
+        # only the column the caller keeps travels back (pib_krige_column_host): [T, M] instead of [T, M, 4]
+        cols, status = _lib.krige_column_host(known, unknown, parsed[0][0], params, _lib.KRIGE_ORDINARY, int(no_neighbors), col,
+                                              values=values, neighbors_range=float(ranges[0]), **sel)
     _raise_on_singular(status)
-    col = 1 if reference_variance_column else 0
-    # indicator.py:399-403 sets values below 0 to 0 and above 1 to 1 (NaN stays NaN): one clipping pass from the strided
-    # [T, M, 4] block into the contiguous [M, T] result
-    res = np.empty((out.shape[1], out.shape[0]))
+    # indicator.py:399-403 sets values below 0 to 0 and above 1 to 1 (NaN stays NaN): one clipping pass into the [M, T] result
+    res = np.empty((cols.shape[1], cols.shape[0]))
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        np.clip(out[:, :, col].T, 0.0, 1.0, out=res)
+        np.clip(cols.T, 0.0, 1.0, out=res)
     return res

@@ -168,6 +168,26 @@ def test_two_row_solver_vs_oracle_and_one_row_solver(pib, oracle, monkeypatch, k
         np.testing.assert_allclose(o1[mi, 0][fine, :2], ref[fine, :2], rtol=RTOL)
 
 
+def test_column_entry_point_equals_the_full_rows(pib):
+    """pib_krige_column_host (one column of the result rows travels back; what indicator kriging keeps) against the full
+    [zhat, sigma^2, x, y] rows of pib_krige_ex_host: bit-identical, over several chunks, two value / parameter sets, both modes."""
+    from pyinterpolate_b200 import _lib
+    known = dem_like_field(30_000, seed=71)
+    unk = uniform_locations(300_001, seed=72)                 # more than one chunk of the host pipeline, ragged last chunk
+    var, mean = float(np.var(known[:, 2])), float(known[:, 2].mean())
+    params = np.array([[1.0, var, 15000.0], [0.05, 0.25, 9000.0]])
+    values = np.stack([known[:, 2], (known[:, 2] <= np.median(known[:, 2])).astype(np.float64)])
+    mid = _lib.MODEL_IDS["spherical"]
+    for mode in (_lib.KRIGE_ORDINARY, _lib.KRIGE_BOTH):
+        full, _, st = _lib.krige_host(known, unk, mid, params, mode, 12, process_mean=mean, values=values)
+        for col in (0, 1):
+            got, st2 = _lib.krige_column_host(known, unk, mid, params, mode, 12, col, process_mean=mean, values=values)
+            np.testing.assert_array_equal(got, full[..., col])
+            np.testing.assert_array_equal(st2, st)
+    with pytest.raises(_lib.PibError):
+        _lib.krige_column_host(known, unk[:10], mid, params, _lib.KRIGE_ORDINARY, 12, 2, values=values)
+
+
 def test_clustered_and_outside_locations(pib, oracle):
     """Strongly non-uniform density and locations far outside the data's bounding box."""
     rng = np.random.default_rng(3)
