@@ -313,7 +313,7 @@ def last_kernel_ms(which):
 def timing_accumulate(on):
     """Keep the kernel-time records across calls (``last_kernel_ms`` then covers every call since) or go back to per-call
     records; either way the records are cleared."""
-    check(load().pib_timing_accumulate(1 if on else 0), "pib_timing_accumulate", "pib_krige_column_host")
+    check(load().pib_timing_accumulate(1 if on else 0), "pib_timing_accumulate")
 
 
 def last_kernel_name(which):

@@ -292,3 +292,11 @@ def test_kriging_inputs_with_non_finite_coordinates_are_refused():
     _prepare(mdl, k3, unk, False, False)
     k4 = known.copy(); k4[:, 2] = 1e308                      # values whose sum overflows: exact scan of the coordinates decides
     _prepare(mdl, k4, unk, False, False)
+
+
+def test_timing_record_switch_needs_no_device():
+    """pib_timing_accumulate only manages the host-side records: callable (and harmless) without a GPU — bench.py brackets its
+    timed region with it."""
+    from pyinterpolate_b200 import _lib
+    _lib.timing_accumulate(True)
+    _lib.timing_accumulate(False)
